@@ -1,0 +1,1061 @@
+"""CPU oracle for the pygradflow inner Newton/KKT path.  TEST INFRASTRUCTURE ONLY.
+
+This module is a dense-NumPy restatement of the reference algorithm
+(chrhansk/pygradflow v0.5.24) for the hot path named in BASELINE.json.  It is
+*not* product code: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
+The product package ``pygradflow_b200`` never imports anything from here.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` runs the real reference
+(imported from ``/root/reference`` in the build container) on the synthetic
+problem families and on the reference's own test fixtures and stores the traces
+under ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this
+restatement against those traces (iterates <= 1e-10 rel, identical active sets,
+accept sequences, iteration counts and status).
+
+The factorisation arithmetic in the reference is SuperLU inside SciPy
+(``scipy.sparse.linalg.splu``, scipy unpinned ">=1.14", 1.18.1 installed; call
+sites ``pygradflow/linear_solver/lu_solver.py:14,21``).  The oracle calls the
+same routine on the same CSC matrix (``linear_solver="splu"``, default) so it is
+a faithful CPU baseline; ``linear_solver="lapack"`` uses dense ``getrf`` instead.
+
+Every function cites the reference ``file:line`` it follows (paths relative to
+``/root/reference/``).
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import numpy as np
+import scipy.linalg
+import scipy.sparse
+import scipy.sparse.linalg
+
+# --------------------------------------------------------------------------
+# status words (pygradflow/status.py:4-31) -- values are the enum's auto() ints
+# --------------------------------------------------------------------------
+STATUS_OPTIMAL = 1
+STATUS_ITERATION_LIMIT = 2
+STATUS_TIME_LIMIT = 3
+STATUS_UNBOUNDED = 4
+STATUS_LOCALLY_INFEASIBLE = 5
+# not a reference status: Solver.solve raises when lamb >= lamb_max
+# (pygradflow/solver.py:323-326); the batched driver needs a word for it.
+STATUS_LAMB_MAX = 6
+STATUS_LINE_SEARCH_FAILED = 7
+
+STATUS_NAMES = {
+    0: "running",
+    1: "optimal",
+    2: "iteration_limit",
+    3: "time_limit",
+    4: "unbounded",
+    5: "infeasible",
+    6: "lamb_max_exceeded",
+    7: "line_search_failed",
+}
+
+
+class LinearSolverError(Exception):
+    """pygradflow/linear_solver/linear_solver.py:8-15."""
+
+
+class StepSolverError(Exception):
+    """pygradflow/step/step_solver_error.py:1-7."""
+
+
+class LambMaxError(Exception):
+    """Raised where pygradflow/solver.py:323-326 raises a bare Exception."""
+
+
+class LineSearchError(Exception):
+    """Raised where pygradflow/newton.py:294 raises a bare Exception."""
+
+
+@dataclass
+class OracleParams:
+    """The subset of pygradflow/params.py:197-265 the hot path reads (same names, same defaults)."""
+
+    rho: float = 1e-8
+    theta_max: float = 0.9
+    theta_ref: float = 0.5
+    lamb_init: float = 1.0
+    lamb_min: float = 1e-12
+    lamb_max: float = 1e12
+    lamb_inc: float = 2.0
+    lamb_red: float = 0.5
+    K_P: float = 0.2
+    K_I: float = 0.005
+    opt_tol: float = 1e-6
+    active_tol: float = 1e-8
+    local_infeas_tol: float = 1e-8
+    newton_type: str = "simplified"  # simplified | full | active_set | globalized
+    newton_tol: float = 1e-8
+    penalty_update: str = "dual_norm"  # dual_norm | constant
+    iteration_limit: Optional[int] = None
+    obj_lower_limit: float = -1e10
+    inertia_correction: bool = False
+    linear_solver: str = "splu"  # splu | lapack
+    # plugin hook, same contract as pygradflow/step/solver/__init__.py:18-19
+    step_solver: Optional[Callable] = None
+    dtype = np.float64
+
+
+def _dense(a) -> np.ndarray:
+    if scipy.sparse.issparse(a):
+        return np.asarray(a.toarray(), dtype=np.float64)
+    return np.asarray(a, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------
+# Problem base (pygradflow/problem.py:32-192) and families
+# --------------------------------------------------------------------------
+class OracleProblem:
+    """Equality-constrained (c(x)=0) + bound-constrained problem, reference callback names."""
+
+    def __init__(self, var_lb, var_ub, num_cons=0):
+        self.var_lb = np.array(var_lb, dtype=np.float64)
+        self.var_ub = np.array(var_ub, dtype=np.float64)
+        assert self.var_lb.shape == self.var_ub.shape and self.var_lb.ndim == 1
+        assert (self.var_lb <= self.var_ub).all()
+        self.num_cons = int(num_cons)
+        self.cons_lb = np.zeros(self.num_cons)
+        self.cons_ub = np.zeros(self.num_cons)
+
+    @property
+    def num_vars(self):
+        return self.var_lb.shape[0]
+
+    def obj(self, x):
+        raise NotImplementedError
+
+    def obj_grad(self, x):
+        raise NotImplementedError
+
+    def cons(self, x):
+        return np.zeros(0)
+
+    def cons_jac(self, x):
+        return np.zeros((0, self.num_vars))
+
+    def lag_hess(self, x, y):
+        raise NotImplementedError
+
+
+class DenseQP(OracleProblem):
+    """f = 1/2 x'Hx + g'x, c = Ax + b  (same formulas as tests/pygradflow/qp.py:4-30)."""
+
+    def __init__(self, H, A, g, b, lb, ub):
+        super().__init__(lb, ub, num_cons=A.shape[0])
+        self.H = np.asarray(H, dtype=np.float64)
+        self.A = np.asarray(A, dtype=np.float64)
+        self.g = np.asarray(g, dtype=np.float64)
+        self.b = np.asarray(b, dtype=np.float64)
+
+    def obj(self, x):
+        return 0.5 * x @ (self.H @ x) + self.g @ x
+
+    def obj_grad(self, x):
+        return self.H @ x + self.g
+
+    def cons(self, x):
+        return self.A @ x + self.b
+
+    def cons_jac(self, x):
+        return self.A
+
+    def lag_hess(self, x, y):
+        return self.H
+
+
+class ChainedRosenbrock(OracleProblem):
+    """f = sum_i b_i (x_{i+1} - x_i^2)^2 + (a_i - x_i)^2, i = 0..n-2.
+
+    n = 2, a = 1, b = 100 is the reference's tests/pygradflow/rosenbrock.py:7-46.
+    """
+
+    def __init__(self, a, b, lb, ub):
+        super().__init__(lb, ub, num_cons=0)
+        self.a = np.asarray(a, dtype=np.float64)
+        self.b = np.asarray(b, dtype=np.float64)
+        assert self.a.shape == (self.num_vars - 1,) and self.b.shape == self.a.shape
+
+    def obj(self, x):
+        r = x[1:] - x[:-1] ** 2
+        return float(np.sum(self.b * r * r + (self.a - x[:-1]) ** 2))
+
+    def obj_grad(self, x):
+        r = x[1:] - x[:-1] ** 2
+        g = np.zeros_like(x)
+        g[:-1] += -4.0 * self.b * r * x[:-1] - 2.0 * (self.a - x[:-1])
+        g[1:] += 2.0 * self.b * r
+        return g
+
+    def lag_hess(self, x, y):
+        n = x.shape[0]
+        r = x[1:] - x[:-1] ** 2
+        H = np.zeros((n, n))
+        idx = np.arange(n - 1)
+        H[idx, idx] += 8.0 * self.b * x[:-1] ** 2 - 4.0 * self.b * r + 2.0
+        H[idx + 1, idx + 1] += 2.0 * self.b
+        off = -4.0 * self.b * x[:-1]
+        H[idx, idx + 1] += off
+        H[idx + 1, idx] += off
+        return H
+
+
+class Tame(OracleProblem):
+    """f=(x0-x1)^2, c = x0+x1-1 (tests/pygradflow/tame.py:7-36)."""
+
+    def __init__(self):
+        super().__init__(np.full(2, -np.inf), np.full(2, np.inf), num_cons=1)
+
+    def obj(self, z):
+        return (z[0] - z[1]) ** 2
+
+    def obj_grad(self, z):
+        d = z[0] - z[1]
+        return np.array([2 * d, -2 * d])
+
+    def cons(self, z):
+        return np.array([z[0] + z[1] - 1])
+
+    def cons_jac(self, z):
+        return np.array([[1.0, 1.0]])
+
+    def lag_hess(self, z, lag):
+        return np.array([[2.0, -2.0], [-2.0, 2.0]])
+
+
+class HS71(OracleProblem):
+    """Hock-Schittkowski 71 with a slack on the product constraint (tests/pygradflow/hs71.py:7-95)."""
+
+    def __init__(self):
+        super().__init__(
+            np.array([1.0, 1.0, 1.0, 1.0, 0.0]),
+            np.array([5.0, 5.0, 5.0, 5.0, np.inf]),
+            num_cons=2,
+        )
+
+    def obj(self, x):
+        return x[0] * x[3] * (x[0] + x[1] + x[2]) + x[2]
+
+    def obj_grad(self, x):
+        s = x[0] + x[1] + x[2]
+        return np.array([s * x[3] + x[0] * x[3], x[0] * x[3], x[0] * x[3] + 1, s * x[0], 0.0])
+
+    def cons(self, x):
+        xx = x[:4]
+        return np.array([np.prod(xx) - x[4] - 25.0, np.dot(xx, xx) - 40.0])
+
+    def cons_jac(self, x):
+        a, b, c, d = x[:4]
+        return np.array(
+            [[b * c * d, a * c * d, a * b * d, a * b * c, -1.0], [2 * a, 2 * b, 2 * c, 2 * d, 0.0]]
+        )
+
+    def lag_hess(self, x, lag):
+        a, b, c, d = x[:4]
+        H = np.zeros((5, 5))
+        s = 2 * a + b + c
+        H[:4, :4] = [[2 * d, d, d, s], [d, 0, 0, a], [d, 0, 0, a], [s, a, a, 0]]
+        P = np.array(
+            [[0, c * d, b * d, b * c], [c * d, 0, a * d, a * c], [b * d, a * d, 0, a * b], [b * c, a * c, a * b, 0]]
+        )
+        H[:4, :4] += lag[0] * P + lag[1] * 2.0 * np.eye(4)
+        return H
+
+
+# --------------------------------------------------------------------------
+# Iterate (pygradflow/iterate.py:19-208)
+# --------------------------------------------------------------------------
+def norm_mult(*vs) -> float:
+    """pygradflow/util.py:15-24."""
+    total = 0.0
+    for v in vs:
+        total += np.dot(v, v)
+    return float(np.sqrt(total))
+
+
+class Iterate:
+    def __init__(self, problem, params, x, y):
+        self.problem = problem
+        self.params = params
+        self.x = np.array(x, dtype=np.float64)
+        self.y = np.array(y, dtype=np.float64)
+        assert self.x.shape == (problem.num_vars,) and self.y.shape == (problem.num_cons,)
+        self._cache = {}
+
+    def _get(self, key, fn):
+        if key not in self._cache:
+            self._cache[key] = fn()
+        return self._cache[key]
+
+    # evaluations: iterate.py:59-76 (cached)
+    @property
+    def obj(self):
+        return self._get("obj", lambda: float(self.problem.obj(self.x)))
+
+    @property
+    def obj_grad(self):
+        return self._get("g", lambda: np.asarray(self.problem.obj_grad(self.x), dtype=np.float64))
+
+    @property
+    def cons(self):
+        if self.problem.num_cons == 0:
+            return np.zeros(0)
+        return self._get("c", lambda: np.asarray(self.problem.cons(self.x), dtype=np.float64))
+
+    @property
+    def cons_jac(self):
+        if self.problem.num_cons == 0:
+            return np.zeros((0, self.problem.num_vars))
+        return self._get("J", lambda: _dense(self.problem.cons_jac(self.x)))
+
+    def lag_hess(self, y):
+        return _dense(self.problem.lag_hess(self.x, y))
+
+    # iterate.py:91-110
+    def aug_lag_deriv_x(self, rho):
+        return self.obj_grad + self.cons_jac.T @ (rho * self.cons + self.y)
+
+    def aug_lag_deriv_y(self):
+        return self.cons
+
+    def aug_lag_deriv_xy(self):
+        return self.cons_jac
+
+    def aug_lag_deriv_xx(self, rho):
+        mult = self.y + rho * self.cons
+        if rho == 0.0:
+            return self.lag_hess(mult)
+        J = self.cons_jac
+        return self.lag_hess(mult) + rho * (J.T @ J)
+
+    # active_set.py:4-29
+    def bound_sets(self):
+        def make():
+            tol = self.params.active_tol
+            lb, ub, x = self.problem.var_lb, self.problem.var_ub, self.x
+            lo = np.abs(x - lb) <= tol
+            up = np.abs(ub - x) <= tol
+            both = lo & up
+            return (lo & ~both, up & ~both, both)
+
+        return self._get("sets", make)
+
+    # iterate.py:136-181
+    @property
+    def bounds_dual(self):
+        def make():
+            r = -(self.obj_grad + self.cons_jac.T @ self.y)
+            at_lower, at_upper, at_both = self.bound_sets()
+            d = np.zeros_like(self.x)
+            d[at_upper] = np.maximum(r[at_upper], 0.0)
+            d[at_lower] = np.minimum(r[at_lower], 0.0)
+            d[at_both] = r[at_both]
+            return d
+
+        return self._get("d", make)
+
+    @property
+    def bound_violation(self):
+        lb, ub, x = self.problem.var_lb, self.problem.var_ub, self.x
+        if x.size == 0:
+            return 0.0
+        return max(float(np.max(np.maximum(lb - x, 0.0))), float(np.max(np.maximum(x - ub, 0.0))))
+
+    @property
+    def cons_violation(self):
+        c = self.cons
+        return 0.0 if c.size == 0 else float(np.max(np.abs(c)))
+
+    @property
+    def stat_res(self):
+        r = self.obj_grad + self.cons_jac.T @ self.y + self.bounds_dual
+        return float(np.max(np.abs(r)))
+
+    @property
+    def total_res(self):
+        return max(self.cons_violation, self.bound_violation, self.stat_res)
+
+    def is_feasible(self, tol):
+        return self.cons_violation <= tol and self.bound_violation <= tol
+
+    def locally_infeasible(self, feas_tol, local_infeas_tol):
+        """iterate.py:115-134."""
+        if self.cons_violation <= feas_tol:
+            return False
+        r = self.cons_jac.T @ self.cons
+        at_lower, at_upper, _ = self.bound_sets()
+        r = r.copy()
+        r[at_lower] = np.minimum(r[at_lower], 0.0)
+        r[at_upper] = np.maximum(r[at_upper], 0.0)
+        return bool(np.max(np.abs(r)) <= local_infeas_tol) if r.size else True
+
+    def dist(self, other):
+        return norm_mult(self.x - other.x, self.y - other.y)
+
+    def check_eval(self):
+        self.obj
+        self.obj_grad
+        if self.problem.num_cons > 0:
+            self.cons
+            self.cons_jac
+
+
+# --------------------------------------------------------------------------
+# Residual functions (pygradflow/implicit_func.py)
+# --------------------------------------------------------------------------
+ACTIVE_SLACK = 1e-8  # implicit_func.py:44
+
+
+def box_active_set(p, lb, ub):
+    """implicit_func.py:21-44."""
+    return np.logical_or(p < lb - ACTIVE_SLACK, p > ub + ACTIVE_SLACK)
+
+
+def box_project(p, lb, ub, active):
+    """implicit_func.py:46-60: clip only the entries flagged active."""
+    out = np.array(p, copy=True)
+    out[active] = np.clip(p[active], lb[active], ub[active])
+    return out
+
+
+class ScaledImplicitFunc:
+    """lambda-scaled residual (implicit_func.py:202-294)."""
+
+    def __init__(self, problem, orig_iterate, dt):
+        self.problem = problem
+        self.orig_iterate = orig_iterate
+        self.dt = dt
+        self.lamb = 1.0 / dt
+        self.lb = self.lamb * problem.var_lb
+        self.ub = self.lamb * problem.var_ub
+        self.n = problem.num_vars
+        self.m = problem.num_cons
+
+    def projection_initial(self, iterate, rho, tau=None):
+        x0 = self.orig_iterate.x
+        lamb = self.lamb
+        if tau is not None:  # :237-244
+            lamb = 1.0 / self.dt
+            return (
+                lamb * (1 - tau * lamb) * iterate.x
+                + (tau * lamb * lamb) * x0
+                - (tau * lamb) * iterate.aug_lag_deriv_x(rho)
+            )
+        return lamb * x0 - iterate.aug_lag_deriv_x(rho)  # :246
+
+    def active_set_at_point(self, p):
+        return box_active_set(p, self.lb, self.ub)
+
+    def compute_active_set(self, iterate, rho, tau=None):
+        return self.active_set_at_point(self.projection_initial(iterate, rho, tau))
+
+    def project(self, p, active):
+        return box_project(p, self.lb, self.ub, active)
+
+    def value_at(self, iterate, rho, active_set=None):
+        """:219-231 (tau never enters the residual)."""
+        lamb = self.lamb
+        y0 = self.orig_iterate.y
+        p = self.projection_initial(iterate, rho)
+        if active_set is None:
+            active_set = self.compute_active_set(iterate, rho)
+        xval = lamb * iterate.x - self.project(p, active_set)
+        yval = -(lamb * iterate.y - (lamb * y0 + iterate.aug_lag_deriv_y()))
+        return np.concatenate([xval, yval])
+
+    def deriv_at(self, iterate, rho, active_set=None):
+        """:254-294: [[lamb I + P_I H_rho, P_I J'], [-J, lamb I]] as a dense array."""
+        if active_set is None:
+            active_set = self.compute_active_set(iterate, rho)
+        lamb = 1.0 / self.dt
+        H = iterate.aug_lag_deriv_xx(rho)
+        J = iterate.aug_lag_deriv_xy()
+        keep = np.logical_not(active_set).astype(np.float64)[:, None]
+        n, m = self.n, self.m
+        F = np.zeros((n + m, n + m))
+        F[:n, :n] = lamb * np.eye(n) + keep * H
+        F[:n, n:] = keep * J.T
+        F[n:, :n] = -J
+        F[n:, n:] = lamb * np.eye(m)
+        return F
+
+
+class ImplicitFunc:
+    """Unscaled residual (implicit_func.py:102-199); used for the controller's ||F||."""
+
+    def __init__(self, problem, orig_iterate, dt):
+        self.problem = problem
+        self.orig_iterate = orig_iterate
+        self.dt = dt
+        self.n = problem.num_vars
+        self.m = problem.num_cons
+
+    def projection_initial(self, iterate, rho, tau=None):
+        x0 = self.orig_iterate.x
+        dt = self.dt
+        if tau is not None:
+            lamb = 1.0 / dt
+            return (1.0 - tau * lamb) * iterate.x + (tau * lamb) * x0 - tau * iterate.aug_lag_deriv_x(rho)
+        return x0 - dt * iterate.aug_lag_deriv_x(rho)
+
+    def active_set_at_point(self, p):
+        return box_active_set(p, self.problem.var_lb, self.problem.var_ub)
+
+    def compute_active_set(self, iterate, rho, tau=None):
+        return self.active_set_at_point(self.projection_initial(iterate, rho, tau))
+
+    def project(self, p, active):
+        return box_project(p, self.problem.var_lb, self.problem.var_ub, active)
+
+    def value_at(self, iterate, rho, active_set=None):
+        """:150-161."""
+        y0 = self.orig_iterate.y
+        dt = self.dt
+        p = self.projection_initial(iterate, rho)
+        if active_set is None:
+            active_set = self.compute_active_set(iterate, rho)
+        xval = iterate.x - self.project(p, active_set)
+        yval = iterate.y - (y0 + dt * iterate.aug_lag_deriv_y())
+        return np.concatenate([xval, yval])
+
+    def deriv_at(self, iterate, rho, active_set=None):
+        """:163-199."""
+        if active_set is None:
+            active_set = self.compute_active_set(iterate, rho)
+        dt = self.dt
+        H = iterate.aug_lag_deriv_xx(rho)
+        J = iterate.aug_lag_deriv_xy()
+        keep = np.logical_not(active_set).astype(np.float64)[:, None]
+        n, m = self.n, self.m
+        F = np.zeros((n + m, n + m))
+        F[:n, :n] = np.eye(n) + keep * (dt * H)
+        F[:n, n:] = keep * (dt * J.T)
+        F[n:, :n] = -dt * J
+        F[n:, n:] = np.eye(m)
+        return F
+
+
+# --------------------------------------------------------------------------
+# Linear solver (pygradflow/linear_solver/lu_solver.py:8-21)
+# --------------------------------------------------------------------------
+class OracleLUSolver:
+    def __init__(self, K: np.ndarray, kind: str = "splu", symmetric: bool = False):
+        self.K = K
+        self.N = K.shape[0]
+        self.kind = kind
+        self.symmetric = symmetric
+        self._neg = None
+        if self.N == 0:
+            return
+        if kind == "splu":
+            try:
+                self.lu = scipy.sparse.linalg.splu(scipy.sparse.csc_matrix(K))
+            except RuntimeError as err:  # exactly singular (lu_solver.py:15-17)
+                raise LinearSolverError("LU decomposition failed") from err
+        else:
+            if not np.all(np.isfinite(K)):
+                raise LinearSolverError("non-finite matrix")
+            self.lu = scipy.linalg.lu_factor(K, check_finite=False)
+            if np.any(np.diag(self.lu[0]) == 0.0):
+                raise LinearSolverError("LU decomposition failed")
+
+    def solve(self, rhs, trans=False, initial_sol=None):
+        if self.N == 0:
+            return np.zeros(0)
+        if self.kind == "splu":
+            return self.lu.solve(rhs, trans="T" if trans else "N")
+        return scipy.linalg.lu_solve(self.lu, rhs, trans=1 if trans else 0, check_finite=False)
+
+    def num_neg_eigvals(self):
+        """The reference LUSolver returns None; the oracle offers the exact count for the
+        inertia contract of the symmetric solvers (ma57_solver.py:76-79 et al.)."""
+        if not self.symmetric:
+            return None
+        if self._neg is None:
+            self._neg = 0 if self.N == 0 else int((np.linalg.eigvalsh(0.5 * (self.K + self.K.T)) < 0).sum())
+        return self._neg
+
+    def rcond(self):
+        return None
+
+
+# --------------------------------------------------------------------------
+# Step result / step solver (pygradflow/step/solver/*.py)
+# --------------------------------------------------------------------------
+class StepResult:
+    """step_solver.py:16-63."""
+
+    def __init__(self, orig_iterate, dx, dy, active_set, rcond=None):
+        self.orig_iterate = orig_iterate
+        self.dy = dy
+        self.active_set = active_set
+        self.rcond = rcond
+        lb, ub = orig_iterate.problem.var_lb, orig_iterate.problem.var_ub
+        x = orig_iterate.x
+        xn = x - dx
+        dx = np.array(dx, copy=True)
+        low = xn < lb
+        xn[low] = lb[low]
+        dx[low] = x[low] - lb[low]
+        high = xn > ub
+        xn[high] = ub[high]
+        dx[high] = x[high] - ub[high]
+        self.dx = dx
+        self.xn = xn
+        self._iterate = None
+
+    @property
+    def iterate(self):
+        if self._iterate is None:
+            o = self.orig_iterate
+            self._iterate = Iterate(o.problem, o.params, self.xn, o.y - self.dy)
+        return self._iterate
+
+    @property
+    def diff(self):
+        return norm_mult(self.dx, self.dy)
+
+
+def kkt_system(H0, J, active, lamb, rho, b0, b1, b2t):
+    """Dense reduced symmetric KKT matrix and right-hand side.
+
+    symmetric_step_solver.py:27-39 (H0 + lamb I, inactive rows), :49-77 (bmat), :79-94 (rhs).
+    Returns (K, rhs) with K of order |I| + m.
+    """
+    inactive = np.logical_not(active)
+    n = H0.shape[0]
+    m = J.shape[0]
+    Hl = H0 + lamb * np.eye(n)
+    HI = Hl[inactive, :]
+    JI = J[:, inactive]
+    nI = int(inactive.sum())
+    K = np.zeros((nI + m, nI + m))
+    K[:nI, :nI] = HI[:, inactive]
+    K[:nI, nI:] = JI.T
+    K[nI:, :nI] = JI
+    K[nI:, nI:] = (-lamb / (1.0 + lamb * rho)) * np.eye(m)
+    rhs = np.concatenate([b1 - HI[:, active] @ b0, b2t - J[:, active] @ b0])
+    return K, rhs
+
+
+class SymmetricStepSolver:
+    """scaled_step_solver.py:15-107 + symmetric_step_solver.py:13-164 on dense arrays."""
+
+    def __init__(self, problem, params, orig_iterate, dt, rho):
+        assert dt > 0.0 and rho > 0.0
+        self.problem = problem
+        self.params = params
+        self.orig_iterate = orig_iterate
+        self.dt = dt
+        self.rho = rho
+        self.n = problem.num_vars
+        self.m = problem.num_cons
+        self._func = ScaledImplicitFunc(problem, orig_iterate, dt)
+        self.active_set = None
+        self.jac = None
+        self.hess = None
+        self.solver = None
+        self.K = None
+        self.num_factorizations = 0
+
+    @property
+    def func(self):
+        return self._func
+
+    def update_derivs(self, iterate):
+        self.jac = np.array(iterate.aug_lag_deriv_xy(), copy=True)
+        self.hess = np.array(iterate.aug_lag_deriv_xx(0.0), copy=True)  # multiplier y only
+        self.solver = None
+        self.K = None
+
+    def update_active_set(self, active_set):
+        self.active_set = np.array(active_set, copy=True)
+        self.solver = None
+        self.K = None
+
+    def initial_rhs(self, iterate):
+        """scaled_step_solver.py:38-60."""
+        F = self._func.value_at(iterate, self.rho, self.active_set)
+        rx, ry = F[: self.n], F[self.n :]
+        A = self.active_set
+        return self.dt * rx[A], rx[~A], ry
+
+    def linear_solver(self, K):
+        return OracleLUSolver(K, self.params.linear_solver, symmetric=True)
+
+    def solve(self, iterate):
+        """scaled_step_solver.py:85-107 + symmetric_step_solver.py:96-164."""
+        b0, b1, b2 = self.initial_rhs(iterate)
+        rho = self.rho
+        lamb = 1.0 / self.dt
+        fact = 1.0 / (1.0 + lamb * rho)
+        b2t = fact * b2
+        A = self.active_set
+        K, rhs = kkt_system(self.hess, self.jac, A, lamb, rho, b0, b1, b2t)
+        if self.K is None:
+            self.K = K
+        try:
+            if self.solver is None:
+                self.solver = self.linear_solver(self.K)
+                self.num_factorizations += 1
+            s = self.solver.solve(rhs)
+            if self.params.inertia_correction:
+                neg = self.solver.num_neg_eigvals()
+                if neg is None:
+                    raise Exception("Inertia correction requested but not available")
+                if neg != self.m:
+                    raise LinearSolverError("Invalid matrix inertia")
+        except LinearSolverError as err:
+            raise StepSolverError() from err
+        self.last_rhs = rhs
+        self.last_sol = s
+        nI = int((~A).sum())
+        dx = np.zeros(self.n)
+        dx[~A] = s[:nI]
+        dx[A] = b0
+        dy = fact * (s[nI:] - rho * b2)
+        return StepResult(iterate, dx, dy, self.active_set, None)
+
+
+def make_step_solver(problem, params, iterate, dt, rho):
+    """step/solver/__init__.py:12-31 (only the plugin hook and the Symmetric default)."""
+    assert dt > 0.0 and rho > 0.0
+    if params.step_solver is not None:
+        return params.step_solver(problem, params, iterate, dt, rho)
+    return SymmetricStepSolver(problem, params, iterate, dt, rho)
+
+
+# --------------------------------------------------------------------------
+# Newton methods (pygradflow/newton.py)
+# --------------------------------------------------------------------------
+class NewtonMethod:
+    def __init__(self, problem, orig_iterate, dt, rho, solver, tau=None):
+        self.problem = problem
+        self.orig_iterate = orig_iterate
+        self.dt = dt
+        self.rho = rho
+        self.tau = tau
+        self.step_solver = solver
+        self.func = solver.func
+
+
+class SimplifiedNewton(NewtonMethod):
+    """newton.py:35-60: active set and derivatives frozen at the initial iterate."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        A = self.func.compute_active_set(self.orig_iterate, self.rho, self.tau)
+        self.step_solver.update_active_set(A)
+        self.step_solver.update_derivs(self.orig_iterate)
+
+    def step(self, iterate):
+        return self.step_solver.solve(iterate)
+
+
+class FullNewton(NewtonMethod):
+    """newton.py:63-89."""
+
+    def step(self, iterate):
+        A = self.func.compute_active_set(iterate, self.rho, self.tau)
+        self.step_solver.update_active_set(A)
+        self.step_solver.update_derivs(iterate)
+        return self.step_solver.solve(iterate)
+
+
+class ActiveSetNewton(NewtonMethod):
+    """newton.py:181-215: derivatives frozen, refactor only when the active set changes."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.step_solver.update_derivs(self.orig_iterate)
+        self._current = None
+
+    def step(self, iterate):
+        A = self.func.compute_active_set(iterate, self.rho, self.tau)
+        if self._current is None or (self._current != A).any():
+            self.step_solver.update_active_set(A)
+        self._current = A
+        return self.step_solver.solve(iterate)
+
+
+class GlobalizedNewton(NewtonMethod):
+    """newton.py:218-304 including its quirks (rhs at orig_iterate, '+' Armijo sign)."""
+
+    def step(self, iterate):
+        params = iterate.params
+        self.step_solver.update_derivs(iterate)
+        A = self.func.compute_active_set(iterate, self.rho, self.tau)
+        self.step_solver.update_active_set(A)
+        result = self.step_solver.solve(self.orig_iterate)  # :248
+        F = self.func.value_at(iterate, self.rho)
+        res = 0.5 * np.dot(F, F)
+        if res <= params.newton_tol:
+            return result
+        grad = self.func.deriv_at(iterate, self.rho).T @ F
+        n = self.problem.num_vars
+        dx, dy = result.dx, result.dy
+        inner = np.dot(grad[:n], dx) + np.dot(grad[n:], dy)
+        alpha = 1.0
+        self.trials = 0
+        for _ in range(30):
+            self.trials += 1
+            trial = Iterate(self.problem, params, iterate.x - dx, iterate.y - dy)
+            Fn = self.func.value_at(trial, self.rho)
+            nres = 0.5 * np.dot(Fn, Fn)
+            if nres <= params.newton_tol:
+                break
+            if nres <= res + (1e-4 * alpha * inner):
+                break
+            alpha *= 0.5
+            dx = alpha * result.dx
+            dy = alpha * result.dy
+        else:
+            raise LineSearchError("Line search failed to converge")
+        out = StepResult(self.orig_iterate, dx, dy, None, None)
+        out.active_set = self.func.compute_active_set(out.iterate, self.rho, self.tau)
+        return out
+
+
+def newton_method(problem, params, iterate, dt, rho, tau=None):
+    """newton.py:307-323."""
+    assert dt > 0.0 and rho > 0.0
+    solver = make_step_solver(problem, params, iterate, dt, rho)
+    cls = {
+        "simplified": SimplifiedNewton,
+        "full": FullNewton,
+        "active_set": ActiveSetNewton,
+        "globalized": GlobalizedNewton,
+    }[params.newton_type]
+    return cls(problem, iterate, dt, rho, solver, tau)
+
+
+# --------------------------------------------------------------------------
+# Step-size control (distance_ratio_control.py, controller.py, step_control.py)
+# --------------------------------------------------------------------------
+class LogPIController:
+    """controller.py:29-77.  The integral term is never reset."""
+
+    def __init__(self, params):
+        self.K_P = params.K_P
+        self.K_I = params.K_I
+        self.log_ref = math.log(params.theta_ref)
+        self.error_sum = 0.0
+
+    def update(self, theta):
+        assert theta > 0.0
+        err = self.log_ref - math.log(theta)
+        self.error_sum += err
+        return math.exp(self.K_P * err + self.K_I * self.error_sum)
+
+
+@dataclass
+class ControlResult:
+    iterate: Iterate
+    lamb: float
+    active_set: Optional[np.ndarray]
+    accepted: bool
+    newton_steps: int = 0
+    theta: float = float("nan")
+
+
+class DistanceRatioController:
+    """distance_ratio_control.py:12-78; one instance lives for the whole solve."""
+
+    def __init__(self, problem, params):
+        self.problem = problem
+        self.params = params
+        self.pi = LogPIController(params)
+        self.total_newton_steps = 0
+        self.total_factorizations = 0
+        self.trace_hook = None
+
+    def _newton(self, iterate, rho, dt):
+        # newton_control.py:22-38 with compute_tau -> None (ActiveSetType.Standard, :75-76)
+        return newton_method(self.problem, self.params, iterate, dt, rho, None)
+
+    def step(self, iterate, rho, dt):
+        assert dt > 0.0
+        p = self.params
+        lamb = 1.0 / dt
+        method = self._newton(iterate, rho, dt)
+        func = ImplicitFunc(self.problem, iterate, dt)
+
+        mid = method.step(iterate)
+        self.total_newton_steps += 1
+        if self.trace_hook:
+            self.trace_hook(method, 0, mid)
+        mid_norm = float(np.linalg.norm(func.value_at(mid.iterate, rho)))
+        if mid_norm <= p.newton_tol:
+            return ControlResult(mid.iterate, max(lamb * p.lamb_red, p.lamb_min), mid.active_set, True, 1)
+        d1 = mid.diff
+        if d1 == 0.0:
+            return ControlResult(mid.iterate, lamb, mid.active_set, True, 1)
+
+        fin = method.step(mid.iterate)
+        self.total_newton_steps += 1
+        if self.trace_hook:
+            self.trace_hook(method, 1, fin)
+        d2 = fin.diff
+        if d2 == 0.0:
+            return ControlResult(fin.iterate, lamb, fin.active_set, True, 2)
+        theta = d2 / d1
+        accepted = theta <= p.theta_max
+        if accepted:
+            lamb_n = max(p.lamb_min, lamb / self.pi.update(theta))
+        else:
+            lamb_n = lamb * p.lamb_inc
+        return ControlResult(fin.iterate, lamb_n, fin.active_set, accepted, 2, theta)
+
+    def compute_step(self, iterate, rho, dt):
+        """step_control.py:67-107: solver failure => reject and double lambda."""
+        try:
+            res = self.step(iterate, rho, dt)
+            if res.accepted:
+                res.iterate.check_eval()
+            return res
+        except StepSolverError:
+            return ControlResult(iterate, 2.0 * (1.0 / dt), None, False, 0)
+
+
+# --------------------------------------------------------------------------
+# Penalty (pygradflow/penalty.py:36-74)
+# --------------------------------------------------------------------------
+class Penalty:
+    def __init__(self, problem, params):
+        self.problem = problem
+        self.params = params
+        self.rho = params.rho
+
+    def update(self, next_iterate):
+        if self.params.penalty_update == "constant":
+            return self.params.rho
+        if self.problem.num_cons == 0:
+            return self.rho
+        ynorm = float(np.max(np.abs(next_iterate.y)))
+        if ynorm >= 10.0 * self.rho:
+            self.rho = min(ynorm, 10.0 * self.rho)
+        return self.rho
+
+
+# --------------------------------------------------------------------------
+# Outer loop (pygradflow/solver.py)
+# --------------------------------------------------------------------------
+@dataclass
+class SolveResult:
+    x: np.ndarray
+    y: np.ndarray
+    d: np.ndarray
+    status: int
+    iterations: int
+    accepted_steps: int
+    newton_steps: int
+    lamb: float
+    rho: float
+    trace: List[dict] = field(default_factory=list)
+
+    @property
+    def success(self):
+        return self.status == STATUS_OPTIMAL
+
+
+def check_terminate(iterate, iteration, params):
+    """solver.py:180-205 (time limit omitted: never set on this path)."""
+    if params.iteration_limit is not None and iteration >= params.iteration_limit:
+        return STATUS_ITERATION_LIMIT
+    if iterate.total_res <= params.opt_tol:
+        return STATUS_OPTIMAL
+    if iterate.locally_infeasible(params.opt_tol, params.local_infeas_tol):
+        return STATUS_LOCALLY_INFEASIBLE
+    if iterate.obj <= params.obj_lower_limit and iterate.is_feasible(params.opt_tol):
+        return STATUS_UNBOUNDED
+    return None
+
+
+def initial_iterate(problem, params, x0=None, y0=None):
+    """transform.py:29-54 without scaling."""
+    if x0 is None:
+        x = np.clip(np.zeros(problem.num_vars), problem.var_lb, problem.var_ub)
+    else:
+        x = np.broadcast_to(x0, (problem.num_vars,))
+    y = np.zeros(problem.num_cons) if y0 is None else np.broadcast_to(y0, (problem.num_cons,))
+    return Iterate(problem, params, x.astype(np.float64), y.astype(np.float64))
+
+
+class Solver:
+    """Scalar restatement of solver.py:26-431 (display, timers, scaling, slack transform omitted)."""
+
+    def __init__(self, problem, params=None):
+        self.problem = problem
+        self.params = params if params is not None else OracleParams()
+
+    def perform_iteration(self, x0=None, y0=None):
+        """solver.py:207-231."""
+        p = self.params
+        it = initial_iterate(self.problem, p, x0, y0)
+        ctrl = DistanceRatioController(self.problem, p)
+        res = ctrl.compute_step(it, p.rho, 1.0 / p.lamb_init)
+        nxt = res.iterate
+        return nxt.x, nxt.y, nxt.bounds_dual
+
+    def solve(self, x0=None, y0=None, record=False, step_hook=None) -> SolveResult:
+        """solver.py:233-431."""
+        p = self.params
+        problem = self.problem
+        iterate = initial_iterate(problem, p, x0, y0)
+        iterate.check_eval()
+        lamb = p.lamb_init
+        ctrl = DistanceRatioController(problem, p)
+        ctrl.trace_hook = step_hook
+        penalty = Penalty(problem, p)
+        rho = penalty.rho
+        iteration = 0
+        accepted_steps = 0
+        trace = []
+        while True:
+            status = check_terminate(iterate, iteration, p)
+            if status is not None:
+                break
+            res = ctrl.compute_step(iterate, rho, 1.0 / lamb)
+            accept = res.accepted
+            lamb_used = lamb
+            lamb = res.lamb
+            if lamb >= p.lamb_max:
+                raise LambMaxError(f"Inverse step size {lamb} exceeded maximum {p.lamb_max}")
+            if record:
+                trace.append(
+                    dict(
+                        x=res.iterate.x.copy(),
+                        y=res.iterate.y.copy(),
+                        accept=bool(accept),
+                        lamb_used=lamb_used,
+                        lamb_next=lamb,
+                        rho=rho,
+                        active=None if res.active_set is None else res.active_set.copy(),
+                        newton_steps=res.newton_steps,
+                        theta=res.theta,
+                    )
+                )
+            if accept:
+                rho = penalty.update(res.iterate)
+                iterate = res.iterate
+                accepted_steps += 1
+            iteration += 1
+        return SolveResult(
+            x=iterate.x,
+            y=iterate.y,
+            d=iterate.bounds_dual,
+            status=status,
+            iterations=iteration,
+            accepted_steps=accepted_steps,
+            newton_steps=ctrl.total_newton_steps,
+            lamb=lamb,
+            rho=rho,
+            trace=trace,
+        )

@@ -1,0 +1,315 @@
+"""Generate golden fixtures by running the REAL reference (chrhansk/pygradflow v0.5.24).
+
+Run in the build container only (the reference lives at /root/reference and cannot travel):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  The fixtures pin the CPU oracle (oracle/gradflow_oracle.py) and,
+on the GPU box, the CUDA path.  Problem data comes from pygradflow_b200.synth (seeded), the
+reference-side Problem classes below follow tests/pygradflow/qp.py:4-30 of the reference
+(scipy.sparse matrices, so the arithmetic goes through scipy's sparsetools like the
+reference's own tests).
+"""
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "_stubs"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import scipy.sparse as sps  # noqa: E402
+
+from pygradflow.callbacks import CallbackType  # noqa: E402
+from pygradflow.implicit_func import ImplicitFunc, ScaledImplicitFunc  # noqa: E402
+from pygradflow.iterate import Iterate  # noqa: E402
+from pygradflow.linear_solver import linear_solver  # noqa: E402
+from pygradflow.newton import newton_method  # noqa: E402
+from pygradflow.params import LinearSolverType, NewtonType, Params  # noqa: E402
+from pygradflow.problem import Problem  # noqa: E402
+from pygradflow.solver import Solver  # noqa: E402
+from pygradflow.status import SolverStatus  # noqa: E402
+from pygradflow.step.solver.symmetric_step_solver import SymmetricStepSolver  # noqa: E402
+
+from pygradflow_b200 import synth  # noqa: E402
+
+
+# ---------------------------------------------------------------- reference-side problems
+class RefQP(Problem):
+    def __init__(self, d):
+        self.H = sps.csc_matrix(d["H"])
+        self.A = sps.csr_matrix(d["A"])
+        self.g = d["g"]
+        self.b = d["b"]
+        super().__init__(d["lb"], d["ub"], num_cons=d["A"].shape[0])
+
+    def obj(self, x):
+        return 0.5 * x @ (self.H @ x) + self.g @ x
+
+    def obj_grad(self, x):
+        return self.H @ x + self.g
+
+    def cons(self, x):
+        return self.A @ x + self.b
+
+    def cons_jac(self, x):
+        return self.A
+
+    def lag_hess(self, x, _):
+        return self.H
+
+
+class RefChainedRosenbrock(Problem):
+    def __init__(self, d):
+        self.a = d["a"]
+        self.b = d["b"]
+        super().__init__(d["lb"], d["ub"])
+
+    def obj(self, x):
+        r = x[1:] - x[:-1] ** 2
+        return float(np.sum(self.b * r * r + (self.a - x[:-1]) ** 2))
+
+    def obj_grad(self, x):
+        r = x[1:] - x[:-1] ** 2
+        g = np.zeros_like(x)
+        g[:-1] += -4.0 * self.b * r * x[:-1] - 2.0 * (self.a - x[:-1])
+        g[1:] += 2.0 * self.b * r
+        return g
+
+    def cons(self, x):
+        return np.array([])
+
+    def cons_jac(self, x):
+        return sps.coo_matrix(np.zeros((0, x.shape[0])))
+
+    def lag_hess(self, x, _):
+        n = x.shape[0]
+        r = x[1:] - x[:-1] ** 2
+        main = np.zeros(n)
+        main[:-1] += 8.0 * self.b * x[:-1] ** 2 - 4.0 * self.b * r + 2.0
+        main[1:] += 2.0 * self.b
+        off = -4.0 * self.b * x[:-1]
+        return sps.diags([off, main, off], [-1, 0, 1], format="csc")
+
+
+STATUS_CODE = {s: s.value for s in SolverStatus}
+
+
+def _load_ref_fixture(name):
+    """Load a problem class of the reference's own tests (tests/pygradflow/<name>.py) by path."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(f"_ref_fixture_{name}", f"/root/reference/tests/pygradflow/{name}.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def ref_rosenbrock():
+    return _load_ref_fixture("rosenbrock").Rosenbrock()
+
+
+def ref_tame():
+    return _load_ref_fixture("tame").Tame()
+
+
+def ref_hs71():
+    return _load_ref_fixture("hs71").HS71()
+
+
+def trace_solve(problem, params, x0, y0, keep_every=1):
+    """Run Solver.solve with the ComputedStep callback (solver.py:331) as trace hook."""
+    solver = Solver(problem, params)
+    xs, ys, accepts = [], [], []
+
+    def cb(iterate, next_iterate, accept):
+        xs.append(next_iterate.x.copy())
+        ys.append(next_iterate.y.copy())
+        accepts.append(bool(accept))
+
+    solver.callbacks.register(CallbackType.ComputedStep, cb)
+    res = solver.solve(x0, y0)
+    xs = np.array(xs).reshape(len(accepts), -1)
+    ys = np.array(ys).reshape(len(accepts), -1)
+    sel = np.arange(0, len(accepts), keep_every)
+    return dict(
+        x=np.asarray(res.x),
+        y=np.asarray(res.y),
+        d=np.asarray(res.d),
+        status=np.int32(STATUS_CODE[res.status]),
+        iterations=np.int32(res.iterations),
+        accepted_steps=np.int32(res.num_accepted_steps),
+        accepts=np.array(accepts, dtype=bool),
+        trace_idx=sel.astype(np.int32),
+        trace_x=xs[sel],
+        trace_y=ys[sel],
+    )
+
+
+def flat(prefix, d):
+    return {f"{prefix}/{k}": v for k, v in d.items()}
+
+
+def params_for(newton="Simplified", **kw):
+    return Params(validate_input=False, newton_type=NewtonType[newton], **kw)
+
+
+# ---------------------------------------------------------------- fixtures
+def golden_linear_solver():
+    """tests/pygradflow/test_linear_solver.py:19-79 through the reference LUSolver."""
+    base = np.array(
+        [[2, 1, 0, 0, 0], [1, 4, 1, 0, 1], [0, 1, 3, 2, 0], [0, 0, 2, -1, 0], [0, 1, 0, 0, 2]], dtype=float
+    )
+    ev = np.linalg.eigvalsh(base)
+    posdef = base + np.diag([-min(2.0 * ev.min(), 0.0)] * 5)
+    negdef = base + np.diag([-max(2.0 * ev.max(), 0.0)] * 5)
+    rhs = np.array([4.0, 17.0, 19.0, 2.0, 12.0])
+    out = {"rhs": rhs}
+    for name, mat in (("indef", base), ("posdef", posdef), ("negdef", negdef)):
+        s = linear_solver(sps.csc_matrix(mat), LinearSolverType.LU, symmetric=True)
+        out[f"{name}/mat"] = mat
+        out[f"{name}/sol"] = s.solve(rhs)
+        out[f"{name}/sol_trans"] = s.solve(rhs, trans=True)
+        out[f"{name}/neg"] = np.int32((np.linalg.eigvalsh(mat) < 0).sum())
+    # cfg5-style quasi-definite KKT matrices
+    for N in (12, 48, 96, 200):
+        K, r, m = synth.kkt_instance(N)
+        s = linear_solver(sps.csc_matrix(K), LinearSolverType.LU, symmetric=True)
+        out[f"kkt{N}/sol"] = s.solve(r)
+        out[f"kkt{N}/sol_trans"] = s.solve(r, trans=True)
+        out[f"kkt{N}/neg"] = np.int32(m)
+    np.savez_compressed(os.path.join(HERE, "linear_solver.npz"), **out)
+
+
+def record_newton_steps(problem, params, x0, y0, dt, rho, nsteps=2):
+    """newton_method(...).step twice, recording the dense K / rhs / sol of the step solver."""
+    iterate = Iterate(problem, params, x0, y0)
+    method = newton_method(problem, params, iterate, dt, rho)
+    out = {}
+    cur = iterate
+    for j in range(nsteps):
+        res = method.step(cur)
+        ss = method.step_solver
+        out[f"s{j}/active"] = np.asarray(res.active_set, dtype=bool)
+        out[f"s{j}/dx"] = res.dx
+        out[f"s{j}/dy"] = res.dy
+        out[f"s{j}/xn"] = res.iterate.x
+        out[f"s{j}/yn"] = res.iterate.y
+        out[f"s{j}/diff"] = np.float64(res.diff)
+        if isinstance(ss, SymmetricStepSolver) and ss._deriv is not None:
+            out[f"s{j}/K"] = ss.deriv.toarray()
+        func = ImplicitFunc(problem, iterate, dt)
+        out[f"s{j}/Fnorm_unscaled"] = np.float64(np.linalg.norm(func.value_at(res.iterate, rho)))
+        sfunc = ScaledImplicitFunc(problem, iterate, dt)
+        out[f"s{j}/F_scaled_next"] = sfunc.value_at(res.iterate, rho)
+        cur = res.iterate
+    return out
+
+
+def golden_newton():
+    out = {}
+    # QP family, a few sizes / seeds, one Newton step pair per Newton type
+    for (n, m, k, dt, rho) in [(16, 8, 0, 1.0, 1e-8), (64, 32, 1, 1.0, 1e-2), (64, 32, 2, 0.05, 1.0), (48, 0, 3, 0.5, 1e-8)]:
+        d = synth.qp_instance(k, n, m)
+        prob = RefQP(d)
+        rng = np.random.default_rng(77 + k)
+        x0 = np.clip(rng.uniform(-1.2, 1.2, n), d["lb"], d["ub"])
+        y0 = 0.1 * rng.standard_normal(m)
+        for newton in ("Simplified", "Full", "ActiveSet"):
+            key = f"qp_n{n}_m{m}_k{k}/{newton}"
+            rec = record_newton_steps(prob, params_for(newton), x0, y0, dt, rho)
+            out.update(flat(key, rec))
+            out[f"{key}/x0"] = x0
+            out[f"{key}/y0"] = y0
+            out[f"{key}/dt"] = np.float64(dt)
+            out[f"{key}/rho"] = np.float64(rho)
+    # chained Rosenbrock
+    for (n, k, dt, rho) in [(8, 0, 0.1, 1e-8), (64, 1, 0.02, 1e-8)]:
+        d = synth.rosenbrock_instance(k, n)
+        prob = RefChainedRosenbrock(d)
+        for newton in ("Simplified", "Full", "ActiveSet"):
+            key = f"ros_n{n}_k{k}/{newton}"
+            rec = record_newton_steps(prob, params_for(newton), d["x0"], d["y0"], dt, rho)
+            out.update(flat(key, rec))
+            out[f"{key}/dt"] = np.float64(dt)
+            out[f"{key}/rho"] = np.float64(rho)
+    np.savez_compressed(os.path.join(HERE, "newton_steps.npz"), **out)
+
+
+def golden_globalized():
+    """GlobalizedNewtonMethod.step (newton.py:242-304) on small QPs; may raise on failure."""
+    out = {}
+    for (n, m, k, dt, rho) in [(16, 8, 0, 0.05, 1e-2), (32, 16, 4, 0.01, 1.0), (24, 0, 5, 0.1, 1e-8)]:
+        d = synth.qp_instance(k, n, m)
+        prob = RefQP(d)
+        rng = np.random.default_rng(99 + k)
+        x0 = np.clip(rng.uniform(-1.0, 1.0, n), d["lb"], d["ub"])
+        y0 = 0.1 * rng.standard_normal(m)
+        key = f"qp_n{n}_m{m}_k{k}"
+        params = params_for("Globalized")
+        iterate = Iterate(prob, params, x0, y0)
+        method = newton_method(prob, params, iterate, dt, rho)
+        cur = iterate
+        for j in range(2):
+            try:
+                res = method.step(cur)
+            except Exception as e:  # line search failure (newton.py:294)
+                out[f"{key}/s{j}/failed"] = np.bool_(True)
+                break
+            out[f"{key}/s{j}/failed"] = np.bool_(False)
+            out[f"{key}/s{j}/dx"] = res.dx
+            out[f"{key}/s{j}/dy"] = res.dy
+            out[f"{key}/s{j}/xn"] = res.iterate.x
+            out[f"{key}/s{j}/yn"] = res.iterate.y
+            out[f"{key}/s{j}/active"] = np.asarray(res.active_set, dtype=bool)
+            cur = res.iterate
+        out[f"{key}/x0"] = x0
+        out[f"{key}/y0"] = y0
+        out[f"{key}/dt"] = np.float64(dt)
+        out[f"{key}/rho"] = np.float64(rho)
+    np.savez_compressed(os.path.join(HERE, "globalized.npz"), **out)
+
+
+def golden_solves():
+    out = {}
+    # cfg1: docs/solve_rosenbrock.py (2-D Rosenbrock, defaults) -> 30 its / 25 accepted
+    res = trace_solve(ref_rosenbrock(), Params(), None, None)
+    out.update(flat("rosenbrock2d", res))
+    res = trace_solve(ref_tame(), params_for("Simplified"), np.zeros(2), np.zeros(1))
+    out.update(flat("tame", res))
+    for newton in ("Simplified", "Full", "ActiveSet"):
+        res = trace_solve(ref_hs71(), params_for(newton), np.array([1.0, 5.0, 5.0, 1.0, 0.0]), np.zeros(2))
+        out.update(flat(f"hs71/{newton}", res))
+    # cfg3-style QPs (small), full traces
+    for (n, m, k) in [(16, 8, 0), (16, 8, 1), (32, 16, 2), (64, 32, 3), (64, 32, 4), (48, 0, 5)]:
+        d = synth.qp_instance(k, n, m)
+        for newton in ("Simplified",) if n > 16 else ("Simplified", "Full", "ActiveSet"):
+            res = trace_solve(RefQP(d), params_for(newton), d["x0"], d["y0"])
+            out.update(flat(f"qp_n{n}_m{m}_k{k}/{newton}", res))
+    # cfg2-style chained Rosenbrock: long runs, thin the stored trace
+    for (n, k) in [(8, 0), (8, 1), (16, 2), (64, 1)]:
+        d = synth.rosenbrock_instance(k, n)
+        res = trace_solve(RefChainedRosenbrock(d), params_for("Simplified"), d["x0"], d["y0"], keep_every=10)
+        out.update(flat(f"ros_n{n}_k{k}/Simplified", res))
+    np.savez_compressed(os.path.join(HERE, "solves.npz"), **out)
+
+
+def golden_full_size_qp():
+    """One cfg3-size instance (n=512, m=256): status / counts / final point + thinned trace."""
+    d = synth.qp_instance(0, 512, 256)
+    res = trace_solve(RefQP(d), params_for("Simplified"), d["x0"], d["y0"], keep_every=8)
+    np.savez_compressed(os.path.join(HERE, "qp512.npz"), **flat("qp_n512_m256_k0/Simplified", res))
+
+
+if __name__ == "__main__":
+    golden_linear_solver()
+    golden_newton()
+    golden_globalized()
+    golden_solves()
+    golden_full_size_qp()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,250 @@
+"""Pin the CPU oracle (oracle/gradflow_oracle.py) against fixtures produced by the real
+reference (tests/golden/make_golden.py).  CPU only.
+
+Tolerances: iterates and KKT solutions 1e-10 relative (inf-norm, relative to max(1, |.|));
+active sets, accept sequences, iteration counts and status identical.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import gradflow_oracle as orc
+from pygradflow_b200 import synth
+
+RTOL = 1e-10
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+def make_qp(n, m, k):
+    d = synth.qp_instance(k, n, m)
+    return orc.DenseQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"]), d
+
+
+def make_ros(n, k):
+    d = synth.rosenbrock_instance(k, n)
+    return orc.ChainedRosenbrock(d["a"], d["b"], d["lb"], d["ub"]), d
+
+
+NEWTON = {"Simplified": "simplified", "Full": "full", "ActiveSet": "active_set"}
+
+
+# ------------------------------------------------------------------ linear solver
+@pytest.mark.parametrize("kind", ["splu", "lapack"])
+@pytest.mark.parametrize("name", ["indef", "posdef", "negdef"])
+def test_linear_solver_fixtures(golden, name, kind):
+    g = golden("linear_solver")
+    mat, rhs = g[f"{name}/mat"], g["rhs"]
+    s = orc.OracleLUSolver(mat, kind, symmetric=True)
+    sol = s.solve(rhs)
+    assert np.allclose(mat @ sol - rhs, 0.0)  # the reference's own criterion (test_linear_solver.py:101)
+    assert rel_err(sol, g[f"{name}/sol"]) <= RTOL
+    assert rel_err(s.solve(rhs, trans=True), g[f"{name}/sol_trans"]) <= RTOL
+    assert s.num_neg_eigvals() == int(g[f"{name}/neg"])
+
+
+@pytest.mark.parametrize("N", [12, 48, 96, 200])
+def test_linear_solver_kkt(golden, N):
+    g = golden("linear_solver")
+    K, rhs, m = synth.kkt_instance(N)
+    for kind in ("splu", "lapack"):
+        s = orc.OracleLUSolver(K, kind, symmetric=True)
+        assert rel_err(s.solve(rhs), g[f"kkt{N}/sol"]) <= RTOL
+        assert rel_err(s.solve(rhs, trans=True), g[f"kkt{N}/sol_trans"]) <= RTOL
+    assert s.num_neg_eigvals() == m == int(g[f"kkt{N}/neg"])
+
+
+# ------------------------------------------------------------------ Newton steps
+def _check_newton_steps(g, key, problem, x0, y0, newton):
+    params = orc.OracleParams(newton_type=NEWTON[newton])
+    dt, rho = float(g[f"{key}/dt"]), float(g[f"{key}/rho"])
+    it = orc.Iterate(problem, params, x0, y0)
+    method = orc.newton_method(problem, params, it, dt, rho)
+    cur = it
+    for j in range(2):
+        res = method.step(cur)
+        assert np.array_equal(res.active_set, g[f"{key}/s{j}/active"])
+        assert rel_err(res.dx, g[f"{key}/s{j}/dx"]) <= RTOL
+        assert rel_err(res.dy, g[f"{key}/s{j}/dy"]) <= RTOL
+        assert rel_err(res.iterate.x, g[f"{key}/s{j}/xn"]) <= RTOL
+        assert rel_err(res.iterate.y, g[f"{key}/s{j}/yn"]) <= RTOL
+        assert abs(res.diff - float(g[f"{key}/s{j}/diff"])) <= RTOL * max(1.0, res.diff)
+        if f"{key}/s{j}/K" in g.files:
+            K = method.step_solver.K
+            assert np.array_equal(K, g[f"{key}/s{j}/K"])  # pure copies: bit-exact
+        f = orc.ImplicitFunc(problem, it, dt)
+        fn = float(np.linalg.norm(f.value_at(res.iterate, rho)))
+        assert abs(fn - float(g[f"{key}/s{j}/Fnorm_unscaled"])) <= 1e-9 * max(1.0, fn)
+        sf = orc.ScaledImplicitFunc(problem, it, dt)
+        assert rel_err(sf.value_at(res.iterate, rho), g[f"{key}/s{j}/F_scaled_next"]) <= 1e-9
+        cur = res.iterate
+
+
+@pytest.mark.parametrize("newton", list(NEWTON))
+@pytest.mark.parametrize("n,m,k", [(16, 8, 0), (64, 32, 1), (64, 32, 2), (48, 0, 3)])
+def test_newton_steps_qp(golden, n, m, k, newton):
+    g = golden("newton_steps")
+    key = f"qp_n{n}_m{m}_k{k}/{newton}"
+    problem, _ = make_qp(n, m, k)
+    _check_newton_steps(g, key, problem, g[f"{key}/x0"], g[f"{key}/y0"], newton)
+
+
+@pytest.mark.parametrize("newton", list(NEWTON))
+@pytest.mark.parametrize("n,k", [(8, 0), (64, 1)])
+def test_newton_steps_rosenbrock(golden, n, k, newton):
+    g = golden("newton_steps")
+    key = f"ros_n{n}_k{k}/{newton}"
+    problem, d = make_ros(n, k)
+    _check_newton_steps(g, key, problem, d["x0"], d["y0"], newton)
+
+
+@pytest.mark.parametrize("n,m,k", [(16, 8, 0), (32, 16, 4), (24, 0, 5)])
+def test_globalized_steps(golden, n, m, k):
+    g = golden("globalized")
+    key = f"qp_n{n}_m{m}_k{k}"
+    problem, _ = make_qp(n, m, k)
+    params = orc.OracleParams(newton_type="globalized")
+    it = orc.Iterate(problem, params, g[f"{key}/x0"], g[f"{key}/y0"])
+    method = orc.newton_method(problem, params, it, float(g[f"{key}/dt"]), float(g[f"{key}/rho"]))
+    cur = it
+    for j in range(2):
+        if f"{key}/s{j}/failed" not in g.files:
+            break
+        if bool(g[f"{key}/s{j}/failed"]):
+            with pytest.raises(orc.LineSearchError):
+                method.step(cur)
+            break
+        res = method.step(cur)
+        assert rel_err(res.dx, g[f"{key}/s{j}/dx"]) <= RTOL
+        assert rel_err(res.dy, g[f"{key}/s{j}/dy"]) <= RTOL
+        assert rel_err(res.iterate.x, g[f"{key}/s{j}/xn"]) <= RTOL
+        assert np.array_equal(res.active_set, g[f"{key}/s{j}/active"])
+        cur = res.iterate
+
+
+# ------------------------------------------------------------------ full solves
+THETA_NOISE = 1e-8
+
+
+def noise_horizon(trace):
+    """Index of the first outer iteration whose contraction ratio theta = |d2|/|d1| is rounding
+    noise (the second simplified-Newton step of a QP whose frozen active set was already solved
+    exactly is ~1e-16).  The reference feeds log(theta) into its PI step-size controller
+    (distance_ratio_control.py:57-63), so from there on lambda -- and the trajectory -- depends on
+    the last bits of the linear solve; strict 1e-10 parity is only meaningful before it."""
+    for i, t in enumerate(trace):
+        if t["theta"] == t["theta"] and t["theta"] < THETA_NOISE:
+            return i
+    return len(trace)
+
+
+def _check_solve(g, key, problem, x0, y0, newton="Simplified", tol=RTOL):
+    params = orc.OracleParams(newton_type=NEWTON[newton])
+    res = orc.Solver(problem, params).solve(x0, y0, record=True)
+    assert res.status == int(g[f"{key}/status"])
+    horizon = noise_horizon(res.trace)
+    accepts = list(g[f"{key}/accepts"])
+    assert [t["accept"] for t in res.trace][: horizon + 1] == accepts[: horizon + 1]
+    for row, i in enumerate(g[f"{key}/trace_idx"]):
+        if i <= horizon and i < len(res.trace):
+            assert rel_err(res.trace[i]["x"], g[f"{key}/trace_x"][row]) <= tol, (key, i)
+            assert rel_err(res.trace[i]["y"], g[f"{key}/trace_y"][row]) <= tol, (key, i)
+    if horizon == len(res.trace):
+        assert res.iterations == int(g[f"{key}/iterations"])
+        assert res.accepted_steps == int(g[f"{key}/accepted_steps"])
+        assert rel_err(res.x, g[f"{key}/x"]) <= tol
+        assert rel_err(res.y, g[f"{key}/y"]) <= tol
+        assert rel_err(res.d, g[f"{key}/d"]) <= max(tol, 1e-9)
+    else:  # past the noise horizon only the converged point is comparable (to opt_tol accuracy)
+        assert rel_err(res.x, g[f"{key}/x"]) <= 1e-4
+    res.horizon = horizon
+    return res
+
+
+def test_solve_rosenbrock_docs_example(golden):
+    """cfg1: docs/solve_rosenbrock.output:5-14 -> 30 iterations, 25 accepted, x=[0.99999959 0.99999917]."""
+    g = golden("solves")
+    p = orc.ChainedRosenbrock(np.array([1.0]), np.array([100.0]), np.full(2, -np.inf), np.full(2, np.inf))
+    res = _check_solve(g, "rosenbrock2d", p, None, None)
+    assert res.iterations == 30 and res.accepted_steps == 25
+    assert np.array2string(res.x, precision=8) == "[0.99999959 0.99999917]"
+
+
+def test_solve_tame(golden):
+    res = _check_solve(golden("solves"), "tame", orc.Tame(), np.zeros(2), np.zeros(1))
+    assert np.allclose(res.x, [0.5, 0.5], atol=1e-6)  # tests/pygradflow/instances.py:57-68
+
+
+@pytest.mark.parametrize("newton", list(NEWTON))
+def test_solve_hs71(golden, newton):
+    res = _check_solve(
+        golden("solves"), f"hs71/{newton}", orc.HS71(), np.array([1.0, 5.0, 5.0, 1.0, 0.0]), np.zeros(2), newton
+    )
+    # tests/pygradflow/instances.py:38-40
+    assert np.allclose(res.x, [1.0, 4.74299964, 3.82114998, 1.37940829, 0.0], atol=1e-6)
+    assert np.allclose(res.y, [-0.55229366, 0.16146857], atol=1e-6)
+
+
+@pytest.mark.parametrize(
+    "n,m,k,newton",
+    [(16, 8, 0, "Simplified"), (16, 8, 0, "Full"), (16, 8, 0, "ActiveSet"), (16, 8, 1, "Simplified"),
+     (16, 8, 1, "Full"), (32, 16, 2, "Simplified"), (64, 32, 3, "Simplified"), (64, 32, 4, "Simplified"),
+     (48, 0, 5, "Simplified")],
+)
+def test_solve_qp(golden, n, m, k, newton):
+    problem, d = make_qp(n, m, k)
+    _check_solve(golden("solves"), f"qp_n{n}_m{m}_k{k}/{newton}", problem, d["x0"], d["y0"], newton)
+
+
+@pytest.mark.parametrize("n,k", [(8, 0), (8, 1), (16, 2), (64, 1)])
+def test_solve_chained_rosenbrock(golden, n, k):
+    problem, d = make_ros(n, k)
+    _check_solve(golden("solves"), f"ros_n{n}_k{k}/Simplified", problem, d["x0"], d["y0"], tol=1e-9)
+
+
+def test_solve_qp_full_size(golden):
+    """One cfg3-size instance (n=512, m=256)."""
+    problem, d = make_qp(512, 256, 0)
+    _check_solve(golden("qp512"), "qp_n512_m256_k0/Simplified", problem, d["x0"], d["y0"])
+
+
+# ------------------------------------------------------------------ reference unit-test restatements
+def test_identity_limit_steps():
+    """tests/pygradflow/test_newton.py:142-214: dt -> 0 gives F' ~ I and x+ ~ clip(x)."""
+    for newton in ("simplified", "full", "active_set", "globalized"):
+        p = orc.ChainedRosenbrock(np.array([1.0]), np.array([100.0]), np.full(2, -np.inf), np.full(2, np.inf))
+        params = orc.OracleParams(newton_type=newton)
+        it = orc.Iterate(p, params, np.zeros(2), np.zeros(0))
+        f = orc.ImplicitFunc(p, it, 1e-10)
+        assert np.allclose(f.deriv_at(it, 1.0), np.eye(2))
+        nxt = orc.newton_method(p, params, it, 1e-10, 1.0).step(it).iterate
+        assert np.allclose(nxt.x, it.x)
+        # everything active (:176-214)
+        p2 = orc.ChainedRosenbrock(np.array([1.0]), np.array([100.0]), np.ones(2), np.array([1.0, np.inf]))
+        it2 = orc.Iterate(p2, params, np.zeros(2), np.zeros(0))
+        nxt2 = orc.newton_method(p2, params, it2, 1e-12, 1.0).step(it2).iterate
+        assert np.allclose(nxt2.x, np.clip(it2.x, p2.var_lb, p2.var_ub))
+
+
+def test_one_step_convergence_tame():
+    """tests/pygradflow/test_solver.py:191-215."""
+    for newton in ("simplified", "full", "active_set", "globalized"):
+        p = orc.Tame()
+        params = orc.OracleParams(newton_type=newton)
+        it = orc.Iterate(p, params, np.zeros(2), np.zeros(1))
+        nxt = orc.newton_method(p, params, it, 10.0, 1.0).step(it).iterate
+        assert np.allclose(orc.ImplicitFunc(p, it, 10.0).value_at(nxt, 1.0), 0.0)
+
+
+def test_func_zero_at_origin():
+    """tests/pygradflow/test_func.py:10-26: F(x^, y^) -> 0 as dt -> 0."""
+    p = orc.HS71()
+    it = orc.Iterate(p, orc.OracleParams(), np.array([1.0, 5.0, 5.0, 1.0, 0.0]), np.zeros(2))
+    assert np.allclose(orc.ImplicitFunc(p, it, 1e-12).value_at(it, 1.0), 0.0, atol=1e-8)
