@@ -1,0 +1,181 @@
+/* libgradflow_b200 -- C ABI of the B200-native batched Newton/KKT path of pygradflow.
+ *
+ * Drop-in boundary.  The reference is pure Python; its plug-in points for this path are
+ *   - Params.step_solver (pygradflow/params.py:234), called as step_solver(problem, params, iterate, dt, rho)
+ *     by pygradflow/step/solver/__init__.py:18-19 and expected to return a StepSolver
+ *     (pygradflow/step/solver/step_solver.py:66-130);
+ *   - StepSolver.linear_solver(mat) (step_solver.py:94-98) returning a LinearSolver
+ *     (pygradflow/linear_solver/linear_solver.py:18-31).
+ * A maintainer binds this library with ctypes; pygradflow_b200/native.py is that
+ * binding.  Each entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are owned by the caller
+ *     (torch tensors); the library allocates nothing except inside the *_host entry points' workspace,
+ *     which the caller also provides;
+ *   - all floating point is IEEE binary64, matrices row-major and contiguous, batch index outermost:
+ *     x[B,n] y[B,m] grad[B,n] cons[B,m] J[B,m,n] H[B,n,n] (symmetric) K[B,ld,ld] rhs[B,ld];
+ *   - per-instance scalars are arrays: dt[B] (= 1/lambda, the reference passes dt and recomputes
+ *     lambda = 1/dt: implicit_func.py:212), rho[B];
+ *   - work / nwork_dev / nwork: optional work list.  The batch dimension of the grid has `nwork` CTAs;
+ *     CTA w handles instance work[w] (or w when work == NULL) and exits if nwork_dev != NULL and
+ *     w >= *nwork_dev.  This is how finished / rejected instances are skipped without a host sync;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - return value: 0 ok, GF_ERR_ARG bad argument, GF_ERR_UNSUPPORTED shape not supported,
+ *     1000 + cudaError_t on a launch error.  Numerical failures are per instance in info[B].
+ */
+#ifndef GRADFLOW_B200_H
+#define GRADFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status words: SolverStatus of pygradflow/status.py:4-31 (enum auto() values); 0 = still running */
+#define GF_STATUS_RUNNING 0
+#define GF_STATUS_OPTIMAL 1
+#define GF_STATUS_ITERATION_LIMIT 2
+#define GF_STATUS_TIME_LIMIT 3
+#define GF_STATUS_UNBOUNDED 4
+#define GF_STATUS_LOCALLY_INFEASIBLE 5
+/* solver.py:323-326 raises when lambda >= lamb_max; a batch records it per instance instead */
+#define GF_STATUS_LAMB_MAX 6
+/* newton.py:294 raises when the Armijo search is exhausted */
+#define GF_STATUS_LINE_SEARCH_FAILED 7
+
+/* phase of an instance inside one outer iteration (DistanceRatioController.step) */
+#define GF_PHASE_IDLE 0
+#define GF_PHASE_SECOND 1
+#define GF_PHASE_ACCEPT_MID 2
+#define GF_PHASE_ACCEPT_FINAL 3
+#define GF_PHASE_REJECT 4
+#define GF_PHASE_FAILED 5
+
+/* info[B] of the factorisations: 0 ok, k > 0 zero/non-finite pivot at column k, -1 non-finite matrix,
+ * -2 pivot signs are not those of a quasi-definite matrix (unpivoted LDL' not trusted; refactor with LU) */
+#define GF_INFO_NONFINITE (-1)
+#define GF_INFO_NOT_QUASIDEFINITE (-2)
+
+int gf_version(void);
+
+/* ---- problem-family evaluators (Problem callbacks: pygradflow/problem.py:112-192, iterate.py:59-76) ---- */
+
+/* QP family (tests/pygradflow/qp.py:17-30): grad = H x + g, cons = A x + b, obj = x'Hx/2 + g'x. */
+int gf_qp_eval(int B, int n, int m, const double* H, const double* A, const double* g, const double* b,
+               const double* x, double* grad, double* cons, double* obj, const int32_t* work,
+               const int32_t* nwork_dev, int nwork, void* stream);
+
+/* chained Rosenbrock (n = 2 is tests/pygradflow/rosenbrock.py:15-46): gradient / objective, and the three
+ * diagonals of the dense Hessian (H must be zero elsewhere). */
+int gf_rosen_eval(int B, int n, const double* a, const double* b, const double* x, double* grad, double* obj,
+                  const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+int gf_rosen_hess(int B, int n, const double* a, const double* b, const double* x, double* H,
+                  const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
+/* Iterate.aug_lag_deriv_x (iterate.py:91-94): dL = grad + J'(rho c + y); optionally J'y (iterate.py:138,171)
+ * and J'c (iterate.py:125) from the same pass over J.  dL / jty / jtc may be NULL. */
+int gf_aug_lag_grad(int B, int n, int m, const double* J, const double* grad, const double* cons, const double* y,
+                    const double* rho, double* dL, double* jty, double* jtc, const int32_t* work,
+                    const int32_t* nwork_dev, int nwork, void* stream);
+
+/* ---- residual, active set (implicit_func.py) ---- */
+
+/* StepFunc.value_at / compute_active_set (implicit_func.py:21-60,150-161,219-252).
+ * scaled != 0: ScaledImplicitFunc, else ImplicitFunc.  active_mode 0: recompute the active set from
+ * p (stored to `active` when non-NULL), 1: use `active`.  F[B,n+m] and nrm[B] (= ||F||_2) may be NULL.
+ * dL / cons are evaluated at (x, y); (x0, y0) is the iterate the implicit-Euler step started from. */
+int gf_residual(int B, int n, int m, const double* x, const double* y, const double* x0, const double* y0,
+                const double* dL, const double* cons, const double* lb, const double* ub, const double* dt,
+                int scaled, int active_mode, uint8_t* active, double* F, double* nrm, const int32_t* work,
+                const int32_t* nwork_dev, int nwork, void* stream);
+
+/* np.where(~active)[0] / np.where(active)[0] (scaled_step_solver.py:51-52): perm[b] = inactive indices
+ * ascending followed by active indices ascending, nI[b] = #inactive, Nvec[b] = nI[b] + m (may be NULL). */
+int gf_index_sets(int B, int n, int m, const uint8_t* active, int32_t* perm, int32_t* nI, int32_t* Nvec,
+                  const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
+/* ---- KKT assembly (step/solver/symmetric_step_solver.py) ---- */
+
+/* compute_hess_jac + _compute_deriv (symmetric_step_solver.py:27-39,49-77):
+ * K = [[H[I,I] + lamb I, J[:,I]'], [J[:,I], -lamb/(1+lamb rho) I]], order N = nI + m, top-left of K[b];
+ * rows/cols N..roundup(N,pad)-1 are set to identity.  lower_only != 0 writes only the lower triangle. */
+int gf_kkt_assemble(int B, int n, int m, int ld, int pad, int lower_only, const double* H, const double* J,
+                    const int32_t* perm, const int32_t* nI, const double* dt, const double* rho, double* K,
+                    const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
+/* initial_rhs + compute_rhs (scaled_step_solver.py:38-60,91-97, symmetric_step_solver.py:79-94):
+ * rhs = [F_x[I] - H[I,A] (dt F_x[A]);  fact F_y - J[:,A] (dt F_x[A])],  fact = 1/(1 + lamb rho). */
+int gf_kkt_rhs(int B, int n, int m, int ld, const double* H, const double* J, const int32_t* perm, const int32_t* nI,
+               const double* F, const double* dt, const double* rho, double* rhs, const int32_t* work,
+               const int32_t* nwork_dev, int nwork, void* stream);
+
+/* ---- linear solver (linear_solver/lu_solver.py:9-21; LinearSolver contract linear_solver.py:18-31) ---- */
+
+/* LUSolver.__init__: in-place LU with partial pivoting of the order-Nvec[b] (or Nmax when Nvec == NULL)
+ * matrix in K[b]; piv[B,ld]; info[B]. */
+int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info,
+                 const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+/* LUSolver.solve(rhs, trans): rhs[B,ldr] is overwritten by the solution of K x = rhs (trans = 0) or
+ * K' x = rhs (trans != 0; only cond_estimate.py:82 uses it). */
+int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, const int32_t* piv, double* rhs,
+                int ldr, int trans, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
+/* Symmetric factorisation with inertia (contract of ma57_solver.py:76-79, mumps_solver.py:81-82,
+ * ssids_solver.py:22-23, cholesky_solver.py:21-22): unpivoted L D L' of the lower triangle, ld % 64 == 0,
+ * matrix padded with identity to a multiple of 64 (gf_kkt_assemble pad = 64).  dvec[B,ld] receives D,
+ * nneg[B] the number of negative pivots (= num_neg_eigvals).  npos_expected (may be NULL): when given, a
+ * pivot whose sign differs from (+ for the first npos_expected[b], - after) sets info = -2. */
+int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, double* dvec, int32_t* info,
+                   int32_t* nneg, const int32_t* npos_expected, const int32_t* work, const int32_t* nwork_dev,
+                   int nwork, void* stream);
+int gf_ldlt_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, double* rhs, int ldr,
+                  const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
+/* ---- step finish (scaled_step_solver.py:99-107, symmetric_step_solver.py:113-121, step_solver.py:16-63) ---- */
+
+/* dx[I] = sol[:nI], dx[A] = dt F_x[A], dy = fact (sol[nI:] - rho F_y); xn = clip(xbase - dx) with the dx
+ * fix-up, yn = ybase - dy, diff = ||(dx, dy)||_2.  dx / dy outputs may be NULL. */
+int gf_step_finish(int B, int n, int m, int ld, const double* xbase, const double* ybase, const double* sol,
+                   const int32_t* perm, const int32_t* nI, const double* F, const double* dt, const double* rho,
+                   const double* lb, const double* ub, double* xn, double* yn, double* dx, double* dy, double* diff,
+                   const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
+/* ---- callers restated per instance (needed for identical iteration counts / status) ---- */
+
+/* Solver._check_terminate (solver.py:180-205) with Iterate.total_res / locally_infeasible
+ * (iterate.py:115-181) and ActiveSet (active_set.py:4-29).  iteration_limit < 0: none.  Only instances with
+ * status == 0 are examined. */
+int gf_check_terminate(int B, int n, int m, const double* x, const double* grad, const double* cons,
+                       const double* jty, const double* jtc, const double* obj, const double* lb, const double* ub,
+                       double opt_tol, double active_tol, double local_infeas_tol, double obj_lower_limit,
+                       int iteration_limit, const int32_t* iters, int32_t* status, double* total_res,
+                       const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
+/* DistanceRatioController.step (distance_ratio_control.py:27-44) after the first Newton step, plus the
+ * solver-failure path of StepController.compute_step (step_control.py:80-83,102-104) when info != 0. */
+int gf_dr_first(int B, const int32_t* status, const int32_t* info, const double* dt, const double* mid_norm,
+                const double* diff1, double newton_tol, double lamb_red, double lamb_min, int32_t* phase,
+                double* lamb_next, void* stream);
+/* ... after the second step (distance_ratio_control.py:46-78) with LogController (controller.py:44-77). */
+int gf_dr_second(int B, const double* dt, const double* diff1, const double* diff2, double theta_max,
+                 double log_theta_ref, double K_P, double K_I, double lamb_min, double lamb_inc, double* err_sum,
+                 int32_t* phase, double* lamb_next, double* theta, void* stream);
+/* End of the outer iteration (solver.py:318-378): lamb_max guard, DualNormUpdate (penalty.py:59-74) or
+ * constant penalty, iterate <- accepted Newton iterate, counters. */
+int gf_commit(int B, int n, int m, const int32_t* phase, const double* lamb_next, double lamb_max,
+              int dual_norm_update, const double* xm, const double* ym, const double* gm, const double* cm,
+              const double* om, const double* xf, const double* yf, const double* gf, const double* cf,
+              const double* of, double* x, double* y, double* grad, double* cons, double* obj, double* lamb,
+              double* rho, int32_t* iters, int32_t* accepted, int32_t* status, void* stream);
+
+/* helpers of the batched driver: ordered compaction of { b in parent (or 0..B-1) : (lo <= key[b] <= hi) != invert } */
+int gf_build_worklist(int B, const int32_t* key, int lo, int hi, int invert, const int32_t* parent,
+                      const int32_t* parent_count, int32_t* list, int32_t* count, void* stream);
+int gf_dt_from_lamb(int B, const double* lamb, double* dt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRADFLOW_B200_H */

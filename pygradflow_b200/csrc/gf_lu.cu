@@ -1,0 +1,436 @@
+// Batched dense FP64 LU with partial pivoting + forward/back substitution (a13, a14).
+//
+// Replaces pygradflow/linear_solver/lu_solver.py:9-21 (scipy.sparse.linalg.splu / SuperLU gstrf, gstrs).
+//
+// Storage: K[b] is ld x ld row-major, the matrix of order N_b sits in its top-left corner.  The kernels
+// factor the column-major view M = K' (M(i,j) = K[j*ld + i]) with LAPACK-style row interchanges,
+// P M = L U, so the pivot search walks a contiguous storage row (coalesced).  Hence
+//   K x = r   <=>  U' w = r, L' v = w, x = P' v        (trans = 0; both sweeps are row-contiguous dots)
+//   K' x = r  <=>  L z = P r, U x = z                  (trans = 1; row-contiguous axpys)
+// For the symmetric KKT matrix of the Symmetric step solver M = K.
+//
+//   lu_smem_kernel   N <= ~150: whole matrix resident in shared memory, one CTA per matrix (cfg2, n=64).
+//   lu_panel_kernel  larger N: right-looking blocked, NB-wide pivoted panel in shared memory, TRSM +
+//                    register-tiled trailing update streamed through L2/HBM.  Robust general path; the
+//                    throughput path for quasi-definite K is the LDL' in gf_ldlt.cu.
+//   lu_solve_kernel  blocked substitution, factors streamed once (HBM-bound).
+#include "gf_common.cuh"
+#include "../../include/gradflow_b200.h"
+
+namespace {
+
+struct MaxLoc {
+    double v;
+    int i;
+};
+
+__device__ __forceinline__ MaxLoc maxloc_combine(MaxLoc a, MaxLoc b) {
+    // larger |value| wins, ties go to the smaller index (LAPACK idamax); NaN never wins over a number
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+
+__device__ __forceinline__ MaxLoc block_maxloc(MaxLoc m, MaxLoc* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxLoc other;
+        other.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+        other.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+        m = maxloc_combine(m, other);
+    }
+    __syncthreads();
+    if (lane == 0) scratch[wid] = m;
+    __syncthreads();
+    MaxLoc r = scratch[0];
+    for (int w = 1; w < nw; w++) r = maxloc_combine(r, scratch[w]);
+    return r;
+}
+
+// absmax = |pivot| as found by the search (-1 when the whole column was NaN)
+__device__ __forceinline__ void record_pivot(double absmax, int col, int32_t* info) {
+    if (*info == 0) {
+        if (absmax < 0.0 || isinf(absmax)) *info = -1;
+        else if (absmax == 0.0) *info = col + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void lu_smem_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, double* __restrict__ K,
+                               int32_t* __restrict__ piv, int32_t* __restrict__ info, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    extern __shared__ double S[];
+    __shared__ MaxLoc scratch[32];
+    __shared__ int32_t sinfo;
+    const int pitch = N | 1;
+    double* Kb = K + (size_t)b * ld * ld;
+    int32_t* pb = piv + (size_t)b * ld;
+    if (threadIdx.x == 0) sinfo = 0;
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int c = e / N, i = e - c * N;
+        S[c * pitch + i] = Kb[(size_t)c * ld + i];
+    }
+    __syncthreads();
+    for (int j = 0; j < N; j++) {
+        MaxLoc best{-1.0, N};
+        for (int i = j + threadIdx.x; i < N; i += blockDim.x) {
+            const double a = fabs(S[j * pitch + i]);
+            if (a > best.v) { best.v = a; best.i = i; }
+        }
+        best = block_maxloc(best, scratch);
+        const int p = best.i < N ? best.i : j;
+        if (threadIdx.x == 0) {
+            pb[j] = p;
+            record_pivot(best.v, j, &sinfo);
+        }
+        if (p != j) {
+            for (int c = threadIdx.x; c < N; c += blockDim.x) {
+                const double t = S[c * pitch + j];
+                S[c * pitch + j] = S[c * pitch + p];
+                S[c * pitch + p] = t;
+            }
+        }
+        __syncthreads();
+        const double pv = S[j * pitch + j];
+        if (pv != 0.0) {
+            for (int i = j + 1 + threadIdx.x; i < N; i += blockDim.x) {
+                const double l = S[j * pitch + i] / pv;
+                S[j * pitch + i] = l;
+                for (int c = j + 1; c < N; c++) S[c * pitch + i] -= l * S[c * pitch + j];
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int c = e / N, i = e - c * N;
+        Kb[(size_t)c * ld + i] = S[c * pitch + i];
+    }
+    if (threadIdx.x == 0) info[b] = sinfo;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                       double* __restrict__ K, int32_t* __restrict__ piv,
+                                                       int32_t* __restrict__ info, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    extern __shared__ double P[];              // NB * N doubles (panel), then 8*NB doubles (U strip)
+    double* Us = P + (size_t)NB * (Nfixed | 1);  // Nfixed = batch-wide Nmax (launch_panel)
+    __shared__ MaxLoc scratch[32];
+    __shared__ int32_t spiv[NB];
+    __shared__ int32_t sinfo;
+    double* Kb = K + (size_t)b * ld * ld;
+    int32_t* pb = piv + (size_t)b * ld;
+    const int T = blockDim.x;
+    if (threadIdx.x == 0) sinfo = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < N; j0 += NB) {
+        const int jb = min(NB, N - j0);
+        const int rows = N - j0;
+        const int pitch = rows | 1;
+        for (int c = 0; c < jb; c++)
+            for (int i = threadIdx.x; i < rows; i += T) P[c * pitch + i] = Kb[(size_t)(j0 + c) * ld + j0 + i];
+        __syncthreads();
+        // ---- pivoted unblocked factorisation of the panel in shared memory
+        for (int jj = 0; jj < jb; jj++) {
+            MaxLoc best{-1.0, rows};
+            for (int i = jj + threadIdx.x; i < rows; i += T) {
+                const double a = fabs(P[jj * pitch + i]);
+                if (a > best.v) { best.v = a; best.i = i; }
+            }
+            best = block_maxloc(best, scratch);
+            const int p = best.i < rows ? best.i : jj;
+            if (threadIdx.x == 0) {
+                spiv[jj] = j0 + p;
+                pb[j0 + jj] = j0 + p;
+                record_pivot(best.v, j0 + jj, &sinfo);
+            }
+            if (p != jj && threadIdx.x < jb) {
+                const double t = P[threadIdx.x * pitch + jj];
+                P[threadIdx.x * pitch + jj] = P[threadIdx.x * pitch + p];
+                P[threadIdx.x * pitch + p] = t;
+            }
+            __syncthreads();
+            const double pv = P[jj * pitch + jj];
+            if (pv != 0.0) {
+                for (int i = jj + 1 + threadIdx.x; i < rows; i += T) {
+                    const double l = P[jj * pitch + i] / pv;
+                    P[jj * pitch + i] = l;
+                    for (int c = jj + 1; c < jb; c++) P[c * pitch + i] -= l * P[c * pitch + jj];
+                }
+            }
+            __syncthreads();
+        }
+        for (int c = 0; c < jb; c++)
+            for (int i = threadIdx.x; i < rows; i += T) Kb[(size_t)(j0 + c) * ld + j0 + i] = P[c * pitch + i];
+        // ---- row interchanges of M on the storage rows outside the panel, then U12 = L11^{-1} M12
+        for (int c = threadIdx.x; c < N; c += T) {
+            if (c >= j0 && c < j0 + jb) continue;
+            double* row = Kb + (size_t)c * ld;
+            for (int jj = 0; jj < jb; jj++) {
+                const int p = spiv[jj];
+                if (p != j0 + jj) {
+                    const double t = row[j0 + jj];
+                    row[j0 + jj] = row[p];
+                    row[p] = t;
+                }
+            }
+            if (c >= j0 + jb) {
+                double u[NB];
+#pragma unroll
+                for (int k = 0; k < NB; k++) u[k] = (k < jb) ? row[j0 + k] : 0.0;
+#pragma unroll
+                for (int k = 1; k < NB; k++) {
+                    if (k < jb) {
+                        double s = u[k];
+#pragma unroll
+                        for (int q = 0; q < k; q++) s -= P[q * pitch + k] * u[q];
+                        u[k] = s;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NB; k++)
+                    if (k < jb) row[j0 + k] = u[k];
+            }
+        }
+        __syncthreads();
+        // ---- trailing update M22 -= L21 U12, strips of 8 storage rows, 4 x 8 register tile per thread
+        const int tr = rows - jb;  // trailing extent
+        if (tr > 0) {
+            for (int c0 = j0 + jb; c0 < N; c0 += 8) {
+                const int nc = min(8, N - c0);
+                for (int e = threadIdx.x; e < 8 * NB; e += T) {
+                    const int r = e / NB, k = e - r * NB;
+                    Us[e] = (r < nc && k < jb) ? Kb[(size_t)(c0 + r) * ld + j0 + k] : 0.0;
+                }
+                __syncthreads();
+                for (int i0 = jb + threadIdx.x; i0 < rows; i0 += 4 * T) {
+                    double acc[8][4];
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+#pragma unroll
+                        for (int t = 0; t < 4; t++) acc[r][t] = 0.0;
+                    for (int k = 0; k < jb; k++) {
+                        double pk[4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const int i = i0 + t * T;
+                            pk[t] = (i < rows) ? P[k * pitch + i] : 0.0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 8; r++) {
+                            const double u = Us[r * NB + k];
+#pragma unroll
+                            for (int t = 0; t < 4; t++) acc[r][t] = fma(pk[t], u, acc[r][t]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        if (r < nc) {
+                            double* row = Kb + (size_t)(c0 + r) * ld + j0;
+#pragma unroll
+                            for (int t = 0; t < 4; t++) {
+                                const int i = i0 + t * T;
+                                if (i < rows) row[i] -= acc[r][t];
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) info[b] = sinfo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked substitution on the packed LU factors; rhs[b] (length >= N) is overwritten by the solution.
+__global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                       const double* __restrict__ K, const int32_t* __restrict__ piv,
+                                                       double* __restrict__ rhs, int ldr, int trans, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    if (N <= 0) return;
+    extern __shared__ double v[];        // N (+pad) doubles
+    __shared__ double Tb[32][33];
+    __shared__ double part[32];
+    const double* Kb = K + (size_t)b * ld * ld;
+    const int32_t* pb = piv + (size_t)b * ld;
+    double* rb = rhs + (size_t)b * ldr;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) v[i] = rb[i];
+    __syncthreads();
+    if (!trans) {
+        // forward: U' w = r  (storage row j, entries i <= j)
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int jb = min(32, N - j0);
+            for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+                const int jj = e >> 5, ii = e & 31;
+                Tb[jj][ii] = (jj < jb && ii <= jj) ? Kb[(size_t)(j0 + jj) * ld + j0 + ii] : 0.0;
+            }
+            for (int jj = wid; jj < jb; jj += nw) {
+                const double* row = Kb + (size_t)(j0 + jj) * ld;
+                double acc = 0.0;
+                for (int i = lane; i < j0; i += 32) acc += __ldg(row + i) * v[i];
+                acc = warp_sum(acc);
+                if (lane == 0) part[jj] = acc;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                double s = (lane < jb) ? v[j0 + lane] - part[lane] : 0.0;
+                for (int ii = 0; ii < jb; ii++) {
+                    double w = s / Tb[ii][ii];
+                    w = __shfl_sync(0xffffffffu, w, ii);
+                    if (lane == ii) s = w;
+                    else if (lane > ii && lane < jb) s -= Tb[lane][ii] * w;
+                }
+                if (lane < jb) v[j0 + lane] = s;
+            }
+            __syncthreads();
+        }
+        // backward: L' x = w (unit; storage row j, entries i > j)
+        const int nblk = (N + 31) / 32;
+        for (int kb = nblk - 1; kb >= 0; kb--) {
+            const int j0 = kb * 32, jb = min(32, N - j0);
+            for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+                const int jj = e >> 5, ii = e & 31;
+                Tb[jj][ii] = (jj < jb && ii > jj && ii < jb) ? Kb[(size_t)(j0 + jj) * ld + j0 + ii] : 0.0;
+            }
+            for (int jj = wid; jj < jb; jj += nw) {
+                const double* row = Kb + (size_t)(j0 + jj) * ld;
+                double acc = 0.0;
+                for (int i = j0 + jb + lane; i < N; i += 32) acc += __ldg(row + i) * v[i];
+                acc = warp_sum(acc);
+                if (lane == 0) part[jj] = acc;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                double s = (lane < jb) ? v[j0 + lane] - part[lane] : 0.0;
+                for (int ii = jb - 1; ii >= 0; ii--) {
+                    const double w = __shfl_sync(0xffffffffu, s, ii);
+                    if (lane < ii) s -= Tb[lane][ii] * w;
+                }
+                if (lane < jb) v[j0 + lane] = s;
+            }
+            __syncthreads();
+        }
+        // x = P' v : undo the interchanges in reverse order
+        if (threadIdx.x == 0) {
+            for (int j = N - 1; j >= 0; j--) {
+                const int p = pb[j];
+                if (p != j) { const double t = v[j]; v[j] = v[p]; v[p] = t; }
+            }
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x == 0) {
+            for (int j = 0; j < N; j++) {
+                const int p = pb[j];
+                if (p != j) { const double t = v[j]; v[j] = v[p]; v[p] = t; }
+            }
+        }
+        __syncthreads();
+        // forward: L z = P r  (axpy form; L(i,j) = K[j*ld + i], i > j)
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int jb = min(32, N - j0);
+            for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+                const int jj = e >> 5, ii = e & 31;
+                Tb[jj][ii] = (jj < jb && ii > jj && ii < jb) ? Kb[(size_t)(j0 + jj) * ld + j0 + ii] : 0.0;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                double s = (lane < jb) ? v[j0 + lane] : 0.0;
+                for (int jj = 0; jj < jb; jj++) {
+                    const double z = __shfl_sync(0xffffffffu, s, jj);
+                    if (lane > jj) s -= Tb[jj][lane] * z;
+                }
+                if (lane < jb) v[j0 + lane] = s;
+            }
+            __syncthreads();
+            for (int i = j0 + jb + threadIdx.x; i < N; i += blockDim.x) {
+                double acc = 0.0;
+                for (int jj = 0; jj < jb; jj++) acc += __ldg(Kb + (size_t)(j0 + jj) * ld + i) * v[j0 + jj];
+                v[i] -= acc;
+            }
+            __syncthreads();
+        }
+        // backward: U x = z  (U(i,j) = K[j*ld + i], i <= j)
+        const int nblk = (N + 31) / 32;
+        for (int kb = nblk - 1; kb >= 0; kb--) {
+            const int j0 = kb * 32, jb = min(32, N - j0);
+            for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+                const int jj = e >> 5, ii = e & 31;
+                Tb[jj][ii] = (jj < jb && ii <= jj) ? Kb[(size_t)(j0 + jj) * ld + j0 + ii] : 0.0;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                double s = (lane < jb) ? v[j0 + lane] : 0.0;
+                for (int jj = jb - 1; jj >= 0; jj--) {
+                    double xj = s / Tb[jj][jj];
+                    xj = __shfl_sync(0xffffffffu, xj, jj);
+                    if (lane == jj) s = xj;
+                    else if (lane < jj) s -= Tb[jj][lane] * xj;
+                }
+                if (lane < jb) v[j0 + lane] = s;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < j0; i += blockDim.x) {
+                double acc = 0.0;
+                for (int jj = 0; jj < jb; jj++) acc += __ldg(Kb + (size_t)(j0 + jj) * ld + i) * v[j0 + jj];
+                v[i] -= acc;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) rb[i] = v[i];
+}
+
+template <int NB>
+int launch_panel(int ld, int Nmax, const int32_t* Nvec, int Nfixed, double* K, int32_t* piv, int32_t* info,
+                 GfWork w, int nwork, cudaStream_t s) {
+    const size_t smem = ((size_t)NB * (Nmax | 1) + 8 * NB) * sizeof(double);
+    if (smem > 227 * 1024) return GF_ERR_UNSUPPORTED;
+    cudaFuncSetAttribute(lu_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lu_panel_kernel<NB><<<nwork, 256, smem, s>>>(ld, Nvec, Nfixed, K, piv, info, w);
+    return gf_launch_status();
+}
+
+}  // namespace
+
+extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info,
+                            const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream) {
+    if (B <= 0 || ld <= 0 || Nmax < 0 || Nmax > ld || !K || !piv || !info) return GF_ERR_ARG;
+    if (nwork <= 0 || Nmax == 0) return GF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    GfWork w{work, nwork_dev};
+    const size_t full = (size_t)Nmax * (Nmax | 1) * sizeof(double);
+    if (full <= 100 * 1024) {
+        if (full > 48 * 1024) cudaFuncSetAttribute(lu_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full);
+        const int threads = Nmax <= 32 ? 32 : (Nmax <= 64 ? 64 : 128);
+        lu_smem_kernel<<<nwork, threads, full, s>>>(ld, Nvec, Nmax, K, piv, info, w);
+        return gf_launch_status();
+    }
+    if (Nmax <= 830) return launch_panel<32>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
+    if (Nmax <= 1700) return launch_panel<16>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
+    if (Nmax <= 3500) return launch_panel<8>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
+    return GF_ERR_UNSUPPORTED;
+}
+
+extern "C" int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, const int32_t* piv,
+                           double* rhs, int ldr, int trans, const int32_t* work, const int32_t* nwork_dev, int nwork,
+                           void* stream) {
+    if (B <= 0 || ld <= 0 || Nmax < 0 || Nmax > ld || ldr < Nmax || !K || !piv || !rhs) return GF_ERR_ARG;
+    if (nwork <= 0 || Nmax == 0) return GF_OK;
+    const size_t smem = (size_t)(Nmax + 1) * sizeof(double);
+    if (smem > 200 * 1024) return GF_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lu_solve_kernel<<<nwork, 256, smem, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,
+                                                                GfWork{work, nwork_dev});
+    return gf_launch_status();
+}

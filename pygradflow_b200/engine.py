@@ -1,0 +1,101 @@
+"""Batched KKT step engine: the device twin of the reference's ``SymmetricStepSolver`` +
+``LinearSolver`` pair for B instances at once.
+
+Reference call order it reproduces (per instance):
+  StepSolver.update_active_set / update_derivs   scaled_step_solver.py:76-83
+  ScaledStepSolver.solve -> initial_rhs -> solve_scaled -> _solve_active_set -> _compute_deriv
+      -> linear_solver(K) -> LinearSolver.solve(rhs)              symmetric_step_solver.py:96-164
+  StepResult (clip, diff)                                           step_solver.py:16-63
+
+All buffers are preallocated once per (B, n, m) and reused across iterations (SURVEY 8b "Ownership").
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+from .kernels import WorkList
+from .params import LinearSolverType
+
+SMALL_N = 112  # order up to which the shared-memory-resident pivoted LU is used under Auto
+
+
+def _roundup(a: int, b: int) -> int:
+    return ((a + b - 1) // b) * b
+
+
+class KKTEngine:
+    def __init__(self, B: int, n: int, m: int, device, linear: LinearSolverType = LinearSolverType.Auto):
+        self.B, self.n, self.m = B, n, m
+        self.device = device
+        N = n + m
+        if linear == LinearSolverType.Auto:
+            linear = LinearSolverType.LU if N <= SMALL_N else LinearSolverType.LDLT
+        self.linear = linear
+        self.ld = max(_roundup(N, 64), 64) if linear == LinearSolverType.LDLT else max(N, 1)
+        f64 = dict(dtype=torch.float64, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.K = torch.empty((B, self.ld, self.ld), **f64)
+        self.rhs = torch.zeros((B, self.ld), **f64)
+        self.perm = torch.zeros((B, n), **i32)
+        self.nI = torch.zeros((B,), **i32)
+        self.Nvec = torch.zeros((B,), **i32)
+        self.piv = torch.zeros((B, self.ld), **i32)
+        self.info = torch.zeros((B,), **i32)
+        self.active = torch.zeros((B, n), dtype=torch.uint8, device=device)
+        if linear == LinearSolverType.LDLT:
+            self.dvec = torch.zeros((B, self.ld), **f64)
+            self.nneg = torch.zeros((B,), **i32)
+            self.info_lu = torch.zeros((B,), **i32)
+            self.fbkey = torch.zeros((B,), **i32)  # 0: LDL' factor valid, != 0: pivoted-LU fallback
+            self._ok = WorkList(torch.zeros((B,), **i32), torch.zeros((1,), **i32), B)
+            self._fb = WorkList(torch.zeros((B,), **i32), torch.zeros((1,), **i32), B)
+        self.n_factor_calls = 0
+
+    # ---------------------------------------------------------------------------------------
+    def update_active_set(self, work: WorkList, active: Optional[torch.Tensor] = None):
+        """np.where(~A) / np.where(A) for the stored active set (self.active unless given)."""
+        K.index_sets(self.active if active is None else active, self.m, self.perm, self.nI, self.Nvec, work)
+
+    def factor(self, H, J, dt, rho, work: WorkList):
+        """Assemble the reduced symmetric KKT matrix and factorise it; per-instance result in self.info."""
+        self.n_factor_calls += 1
+        Nmax = self.n + self.m
+        if self.linear == LinearSolverType.LU:
+            K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, work)
+            K.lu_factor(self.K, Nmax, self.Nvec, self.piv, self.info, work)
+            return
+        K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 64, True, work)
+        K.ldlt_factor(self.K, Nmax, self.Nvec, self.dvec, self.info, self.nneg, self.nI, work)
+        # Instances whose pivots are not those of a quasi-definite matrix (or hit a zero pivot) are
+        # re-assembled in full and factorised with partial pivoting, like the reference's LU.
+        self.fbkey.copy_(self.info)
+        parent = None if work.list is None and work.count_dev is None else work
+        K.build_worklist(self.fbkey, 0, 0, self._fb, parent=parent, invert=True)
+        self._fb.nwork = work.nwork
+        K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, self._fb)
+        K.lu_factor(self.K, Nmax, self.Nvec, self.piv, self.info_lu, self._fb)
+        torch.where(self.fbkey != 0, self.info_lu, self.info, out=self.info)
+
+    def solve(self, rhs, work: WorkList, trans: bool = False):
+        """rhs[B, ld] <- K^{-1} rhs for the instances in ``work``."""
+        Nmax = self.n + self.m
+        if self.linear == LinearSolverType.LU:
+            K.lu_solve(self.K, Nmax, self.Nvec, self.piv, rhs, trans, work)
+            return
+        parent = None if work.list is None and work.count_dev is None else work
+        K.build_worklist(self.fbkey, 0, 0, self._ok, parent=parent, invert=False)
+        K.build_worklist(self.fbkey, 0, 0, self._fb, parent=parent, invert=True)
+        self._ok.nwork = work.nwork
+        self._fb.nwork = work.nwork
+        K.ldlt_solve(self.K, Nmax, self.Nvec, rhs, self._ok)  # symmetric: trans is irrelevant
+        K.lu_solve(self.K, Nmax, self.Nvec, self.piv, rhs, trans, self._fb)
+
+    def step(self, H, J, xbase, ybase, F, dt, rho, lb, ub, xn, yn, diff, work: WorkList, dx=None, dy=None):
+        """ScaledStepSolver.solve + StepResult for the current factor: rhs, substitution, step finish."""
+        K.kkt_rhs(H, J, self.perm, self.nI, F, dt, rho, self.rhs, work)
+        self.solve(self.rhs, work)
+        K.step_finish(xbase, ybase, self.rhs, self.perm, self.nI, F, dt, rho, lb, ub, xn, yn, dx, dy, diff, work)

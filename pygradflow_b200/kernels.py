@@ -1,0 +1,167 @@
+"""Typed Python front of the C ABI: torch CUDA tensors in, kernels launched on torch's current stream.
+
+One function per entry point of include/gradflow_b200.h.  Tensors must be contiguous, float64 (int32 /
+uint8 where stated) and live on the current CUDA device.  Nothing here computes on the CPU.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native
+from .native import ptr
+
+LAUNCHES = 0  # number of kernel-launching ABI calls (bench.py reports it as gpu_launches evidence)
+
+
+class WorkList:
+    """Optional instance list for the batch dimension (see the header's conventions)."""
+
+    __slots__ = ("list", "count_dev", "nwork")
+
+    def __init__(self, list_t: Optional[torch.Tensor], count_dev: Optional[torch.Tensor], nwork: int):
+        self.list = list_t
+        self.count_dev = count_dev
+        self.nwork = int(nwork)
+
+    @staticmethod
+    def all(B: int) -> "WorkList":
+        return WorkList(None, None, B)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _w(work: WorkList):
+    return (ptr(work.list), ptr(work.count_dev), work.nwork, _stream())
+
+
+def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    native.call(name, *args)
+
+
+def qp_eval(H, A, g, b, x, grad, cons, obj, work: WorkList):
+    B, n = x.shape
+    m = 0 if A is None else A.shape[1]
+    _call("gf_qp_eval", B, n, m, ptr(H), ptr(A), ptr(g), ptr(b), ptr(x), ptr(grad), ptr(cons), ptr(obj), *_w(work))
+
+
+def rosen_eval(a, b, x, grad, obj, work: WorkList):
+    B, n = x.shape
+    _call("gf_rosen_eval", B, n, ptr(a), ptr(b), ptr(x), ptr(grad), ptr(obj), *_w(work))
+
+
+def rosen_hess(a, b, x, H, work: WorkList):
+    B, n = x.shape
+    _call("gf_rosen_hess", B, n, ptr(a), ptr(b), ptr(x), ptr(H), *_w(work))
+
+
+def aug_lag_grad(J, grad, cons, y, rho, dL, jty, jtc, work: WorkList):
+    B, n = grad.shape
+    m = 0 if cons is None else cons.shape[1]
+    _call("gf_aug_lag_grad", B, n, m, ptr(J), ptr(grad), ptr(cons), ptr(y), ptr(rho), ptr(dL), ptr(jty), ptr(jtc),
+          *_w(work))
+
+
+def residual(x, y, x0, y0, dL, cons, lb, ub, dt, scaled: bool, active_mode: int, active, F, nrm, work: WorkList):
+    B, n = x.shape
+    m = 0 if y is None else y.shape[1]
+    _call("gf_residual", B, n, m, ptr(x), ptr(y), ptr(x0), ptr(y0), ptr(dL), ptr(cons), ptr(lb), ptr(ub), ptr(dt),
+          1 if scaled else 0, active_mode, ptr(active), ptr(F), ptr(nrm), *_w(work))
+
+
+def index_sets(active, m: int, perm, nI, Nvec, work: WorkList):
+    B, n = active.shape
+    _call("gf_index_sets", B, n, m, ptr(active), ptr(perm), ptr(nI), ptr(Nvec), *_w(work))
+
+
+def kkt_assemble(H, J, perm, nI, dt, rho, K, pad: int, lower_only: bool, work: WorkList):
+    B, n, _ = H.shape
+    m = 0 if J is None else J.shape[1]
+    ld = K.shape[1]
+    _call("gf_kkt_assemble", B, n, m, ld, pad, 1 if lower_only else 0, ptr(H), ptr(J), ptr(perm), ptr(nI), ptr(dt),
+          ptr(rho), ptr(K), *_w(work))
+
+
+def kkt_rhs(H, J, perm, nI, F, dt, rho, rhs, work: WorkList):
+    B, n, _ = H.shape
+    m = 0 if J is None else J.shape[1]
+    ld = rhs.shape[1]
+    _call("gf_kkt_rhs", B, n, m, ld, ptr(H), ptr(J), ptr(perm), ptr(nI), ptr(F), ptr(dt), ptr(rho), ptr(rhs),
+          *_w(work))
+
+
+def lu_factor(K, Nmax: int, Nvec, piv, info, work: WorkList):
+    B, ld, _ = K.shape
+    _call("gf_lu_factor", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(piv), ptr(info), *_w(work))
+
+
+def lu_solve(K, Nmax: int, Nvec, piv, rhs, trans: bool, work: WorkList):
+    B, ld, _ = K.shape
+    _call("gf_lu_solve", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(piv), ptr(rhs), rhs.shape[1], 1 if trans else 0,
+          *_w(work))
+
+
+def ldlt_factor(K, Nmax: int, Nvec, dvec, info, nneg, npos_expected, work: WorkList):
+    B, ld, _ = K.shape
+    _call("gf_ldlt_factor", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(dvec), ptr(info), ptr(nneg), ptr(npos_expected),
+          *_w(work))
+
+
+def ldlt_solve(K, Nmax: int, Nvec, rhs, work: WorkList):
+    B, ld, _ = K.shape
+    _call("gf_ldlt_solve", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(rhs), rhs.shape[1], *_w(work))
+
+
+def step_finish(xbase, ybase, sol, perm, nI, F, dt, rho, lb, ub, xn, yn, dx, dy, diff, work: WorkList):
+    B, n = xbase.shape
+    m = 0 if ybase is None else ybase.shape[1]
+    ld = sol.shape[1]
+    _call("gf_step_finish", B, n, m, ld, ptr(xbase), ptr(ybase), ptr(sol), ptr(perm), ptr(nI), ptr(F), ptr(dt),
+          ptr(rho), ptr(lb), ptr(ub), ptr(xn), ptr(yn), ptr(dx), ptr(dy), ptr(diff), *_w(work))
+
+
+def check_terminate(x, grad, cons, jty, jtc, obj, lb, ub, opt_tol, active_tol, local_infeas_tol, obj_lower_limit,
+                    iteration_limit, iters, status, total_res, work: WorkList):
+    B, n = x.shape
+    m = 0 if cons is None else cons.shape[1]
+    _call("gf_check_terminate", B, n, m, ptr(x), ptr(grad), ptr(cons), ptr(jty), ptr(jtc), ptr(obj), ptr(lb),
+          ptr(ub), opt_tol, active_tol, local_infeas_tol, obj_lower_limit,
+          -1 if iteration_limit is None else int(iteration_limit), ptr(iters), ptr(status), ptr(total_res), *_w(work))
+
+
+def dr_first(status, info, dt, mid_norm, diff1, newton_tol, lamb_red, lamb_min, phase, lamb_next):
+    _call("gf_dr_first", status.shape[0], ptr(status), ptr(info), ptr(dt), ptr(mid_norm), ptr(diff1), newton_tol,
+          lamb_red, lamb_min, ptr(phase), ptr(lamb_next), _stream())
+
+
+def dr_second(dt, diff1, diff2, theta_max, log_theta_ref, K_P, K_I, lamb_min, lamb_inc, err_sum, phase, lamb_next,
+              theta):
+    _call("gf_dr_second", dt.shape[0], ptr(dt), ptr(diff1), ptr(diff2), theta_max, log_theta_ref, K_P, K_I, lamb_min,
+          lamb_inc, ptr(err_sum), ptr(phase), ptr(lamb_next), ptr(theta), _stream())
+
+
+def commit(phase, lamb_next, lamb_max, dual_norm_update, mid, fin, cur, lamb, rho, iters, accepted, status):
+    """mid / fin / cur: tuples (x, y, grad, cons, obj)."""
+    B, n = cur[0].shape
+    m = 0 if cur[1] is None else cur[1].shape[1]
+    _call("gf_commit", B, n, m, ptr(phase), ptr(lamb_next), lamb_max, 1 if dual_norm_update else 0,
+          *[ptr(t) for t in mid], *[ptr(t) for t in fin], *[ptr(t) for t in cur], ptr(lamb), ptr(rho), ptr(iters),
+          ptr(accepted), ptr(status), _stream())
+
+
+def build_worklist(key, lo: int, hi: int, out: WorkList, parent: Optional[WorkList] = None, invert: bool = False):
+    """out.list / out.count_dev <- ordered { b in parent : (lo <= key[b] <= hi) != invert }."""
+    plist = None if parent is None else parent.list
+    pcount = None if parent is None else parent.count_dev
+    _call("gf_build_worklist", key.shape[0], ptr(key), lo, hi, 1 if invert else 0, ptr(plist), ptr(pcount),
+          ptr(out.list), ptr(out.count_dev), _stream())
+
+
+def dt_from_lamb(lamb, dt):
+    _call("gf_dt_from_lamb", lamb.shape[0], ptr(lamb), ptr(dt), _stream())

@@ -1,0 +1,98 @@
+"""Solver parameters of the hot path -- field names and defaults of the reference's ``Params``
+(pygradflow/params.py:197-265) for every field the Newton/KKT path reads, so a reference ``Params``
+object can be passed in unchanged (duck typing) and this one can be handed to reference-style code.
+"""
+
+from __future__ import annotations
+
+import enum
+import math
+from dataclasses import dataclass
+from typing import Any, Callable, Optional
+
+import numpy as np
+
+
+class NewtonType(enum.Enum):
+    """pygradflow/params.py:19-46."""
+
+    Simplified = enum.auto()
+    Full = enum.auto()
+    ActiveSet = enum.auto()
+    Globalized = enum.auto()
+
+
+class LinearSolverType(enum.Enum):
+    """LU is the reference default (params.py:236).  LDLT is the B200 symmetric factorisation with
+    inertia (the contract of the reference's MA57 / MUMPS / SSIDS / Cholesky wrappers); Auto picks LDLT
+    for quasi-definite systems of order > 112 with a per-instance pivoted-LU fallback, LU otherwise."""
+
+    LU = enum.auto()
+    LDLT = enum.auto()
+    Auto = enum.auto()
+
+
+class PenaltyUpdate(enum.Enum):
+    """pygradflow/params.py:133-139 (only the two strategies on the named path)."""
+
+    Constant = enum.auto()
+    DualNorm = enum.auto()
+
+
+def _enum_name(value) -> str:
+    return value.name if isinstance(value, enum.Enum) else str(value)
+
+
+@dataclass
+class Params:
+    rho: float = 1e-8
+    theta_max: float = 0.9
+    theta_ref: float = 0.5
+    lamb_init: float = 1.0
+    lamb_min: float = 1e-12
+    lamb_max: float = 1e12
+    lamb_inc: float = 2.0
+    lamb_red: float = 0.5
+    K_P: float = 0.2
+    K_I: float = 0.005
+    opt_tol: float = 1e-6
+    active_tol: float = 1e-8
+    local_infeas_tol: float = 1e-8
+    newton_type: NewtonType = NewtonType.Simplified
+    newton_tol: float = 1e-8
+    step_solver: Optional[Callable[..., Any]] = None
+    linear_solver_type: LinearSolverType = LinearSolverType.Auto
+    penalty_update: PenaltyUpdate = PenaltyUpdate.DualNorm
+    iteration_limit: Optional[int] = None
+    obj_lower_limit: float = -1e10
+    inertia_correction: bool = False
+    report_rcond: bool = False
+
+    def __post_init__(self):
+        for key, cls in (("newton_type", NewtonType), ("linear_solver_type", LinearSolverType),
+                         ("penalty_update", PenaltyUpdate)):
+            v = getattr(self, key)
+            if not isinstance(v, cls):
+                setattr(self, key, cls[_enum_name(v)])  # accepts strings and the reference's own enums
+
+    @property
+    def dtype(self):
+        return np.float64
+
+    @property
+    def log_theta_ref(self) -> float:
+        return math.log(self.theta_ref)
+
+    @staticmethod
+    def from_reference(ref) -> "Params":
+        """Copy the hot-path fields out of a reference ``pygradflow.params.Params`` (or any look-alike)."""
+        kw = {}
+        for f in Params.__dataclass_fields__:
+            if f in ("step_solver", "linear_solver_type"):
+                continue
+            if hasattr(ref, f):
+                v = getattr(ref, f)
+                if f == "penalty_update" and _enum_name(v) not in PenaltyUpdate.__members__:
+                    raise ValueError(f"penalty_update={_enum_name(v)} is outside the B200 path (Constant / DualNorm)")
+                kw[f] = v
+        return Params(**kw)

@@ -1,0 +1,351 @@
+"""Drop-in step solver / linear solver for the reference's plug-in points (batch = 1 views of the
+batched CUDA core).
+
+    Solver(problem, Params(step_solver=B200StepSolver)).solve(x0, y0)
+
+``Params.step_solver`` is invoked as ``step_solver(problem, params, iterate, dt, rho)``
+(pygradflow/step/solver/__init__.py:18-19, pygradflow/params.py:234) and must return an object with the
+``StepSolver`` interface (pygradflow/step/solver/step_solver.py:66-130): property ``func`` and methods
+``update_active_set``, ``update_derivs``, ``solve`` -> ``StepResult``.  ``B200LinearSolver`` has the
+``LinearSolver`` interface (pygradflow/linear_solver/linear_solver.py:18-31).  Host arrays go in and out;
+every floating-point operation of the path runs in the CUDA kernels of libgradflow_b200.so -- problem
+callbacks (``Problem.obj_grad`` etc.) stay the user's Python code, exactly as in the reference.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .engine import KKTEngine
+from .kernels import WorkList
+from .params import LinearSolverType
+
+
+class LinearSolverError(Exception):
+    """Same role as pygradflow/linear_solver/linear_solver.py:8-15."""
+
+
+class StepSolverError(Exception):
+    """Same role as pygradflow/step/step_solver_error.py:1-7."""
+
+
+def _reference_errors():
+    """When the reference package is importable, raise ITS exception types so that
+    StepController.compute_step (step_control.py:102-104) catches them."""
+    try:  # pragma: no cover - depends on the host environment
+        from pygradflow.linear_solver import LinearSolverError as RefLSE
+        from pygradflow.step.step_solver_error import StepSolverError as RefSSE
+
+        return RefLSE, RefSSE
+    except Exception:
+        return LinearSolverError, StepSolverError
+
+
+def _dense(a) -> np.ndarray:
+    if hasattr(a, "toarray"):
+        a = a.toarray()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _dev(a, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+
+
+_ONE = None
+
+
+def _one():
+    global _ONE
+    if _ONE is None:
+        _ONE = WorkList.all(1)
+    return _ONE
+
+
+# ------------------------------------------------------------------------------------------------
+class B200LinearSolver:
+    """LinearSolver(matrix, symmetric=False): the constructor factorises, ``solve`` substitutes.
+
+    method: "lu" (pivoted, default for unsymmetric), "ldlt" (symmetric, inertia available), or None =
+    LDL' for symmetric input with a pivoted-LU fallback when a pivot breaks down or the factor grows."""
+
+    GROWTH_LIMIT = 1e8
+
+    def __init__(self, matrix, symmetric: bool = False, method: Optional[str] = None, device="cuda"):
+        self.symmetric = symmetric
+        mat = _dense(matrix)
+        assert mat.ndim == 2 and mat.shape[0] == mat.shape[1]
+        self.N = N = mat.shape[0]
+        self.device = device
+        self._neg: Optional[int] = None
+        self.method = None
+        if N == 0:
+            return
+        LSE, _ = _reference_errors()
+        if not np.all(np.isfinite(mat)):
+            raise LSE("matrix has non-finite entries")
+        want_ldlt = method == "ldlt" or (method is None and symmetric)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.Nvec = torch.full((1,), N, **i32)
+        self.info = torch.zeros((1,), **i32)
+        if want_ldlt:
+            ld = max(((N + 63) // 64) * 64, 64)
+            Kp = np.eye(ld)
+            Kp[:N, :N] = mat
+            self.K = _dev(Kp, device).reshape(1, ld, ld)
+            self.dvec = torch.zeros((1, ld), dtype=torch.float64, device=device)
+            nneg = torch.zeros((1,), **i32)
+            K.ldlt_factor(self.K, N, self.Nvec, self.dvec, self.info, nneg, None, _one())
+            ok = int(self.info.item()) == 0
+            if ok:
+                growth = float(torch.tril(self.K[0, :N, :N], -1).abs().max().item()) if N > 1 else 0.0
+                ok = np.isfinite(growth) and growth <= self.GROWTH_LIMIT
+            if ok:
+                self.method = "ldlt"
+                self._neg = int(nneg.item())
+                return
+            if method == "ldlt":
+                raise LSE("LDL' factorisation broke down (zero pivot or unbounded growth)")
+        self.K = _dev(mat, device).reshape(1, N, N)
+        self.piv = torch.zeros((1, N), **i32)
+        K.lu_factor(self.K, N, self.Nvec, self.piv, self.info, _one())
+        if int(self.info.item()) != 0:  # exactly singular: lu_solver.py:15-17
+            raise LSE("LU decomposition failed")
+        self.method = "lu"
+
+    def solve(self, rhs, trans: bool = False, initial_sol=None) -> np.ndarray:
+        rhs = np.asarray(rhs, dtype=np.float64)
+        assert rhs.shape == (self.N,)
+        if self.N == 0:
+            return np.zeros(0)
+        ld = self.K.shape[1]
+        r = torch.zeros((1, ld), dtype=torch.float64, device=self.device)
+        r[0, : self.N] = torch.from_numpy(rhs).to(self.device)
+        if self.method == "ldlt":
+            K.ldlt_solve(self.K, self.N, self.Nvec, r, _one())
+        else:
+            K.lu_solve(self.K, self.N, self.Nvec, self.piv, r, trans, _one())
+        return r[0, : self.N].cpu().numpy()
+
+    def num_neg_eigvals(self) -> Optional[int]:
+        return self._neg
+
+    def rcond(self) -> Optional[float]:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+class _DeviceIterate:
+    """Device copies of what the kernels read from a host ``Iterate`` (x, y, grad f, c, J)."""
+
+    def __init__(self, iterate, device):
+        problem = iterate.problem
+        n, m = problem.num_vars, problem.num_cons
+        self.x = _dev(iterate.x, device).reshape(1, n)
+        self.y = _dev(iterate.y, device).reshape(1, m)
+        self.grad = _dev(iterate.obj_grad, device).reshape(1, n)
+        self.cons = _dev(iterate.cons, device).reshape(1, m) if m > 0 else torch.zeros((1, 0), dtype=torch.float64, device=device)
+        self.J = _dev(_dense(iterate.cons_jac), device).reshape(1, m, n) if m > 0 else None
+
+
+def _cache(iterate, device) -> _DeviceIterate:
+    c = getattr(iterate, "_b200_cache", None)
+    if c is None:
+        c = _DeviceIterate(iterate, device)
+        try:
+            iterate._b200_cache = c
+        except Exception:  # iterates that forbid new attributes are simply re-uploaded
+            pass
+    return c
+
+
+class B200StepFunc:
+    """StepFunc interface of ScaledImplicitFunc (pygradflow/implicit_func.py:202-294) on the GPU."""
+
+    def __init__(self, problem, orig_iterate, dt: float, device="cuda"):
+        self.problem = problem
+        self.orig_iterate = orig_iterate
+        self.dt = dt
+        self.lamb = 1.0 / dt
+        self.n = problem.num_vars
+        self.m = problem.num_cons
+        self.device = device
+        f64 = dict(dtype=torch.float64, device=device)
+        self.lb_d = _dev(problem.var_lb, device).reshape(1, self.n)
+        self.ub_d = _dev(problem.var_ub, device).reshape(1, self.n)
+        self.dt_d = torch.full((1,), dt, **f64)
+        self.lb = self.lamb * np.asarray(problem.var_lb)
+        self.ub = self.lamb * np.asarray(problem.var_ub)
+        self._dL = torch.zeros((1, self.n), **f64)
+        self._F = torch.zeros((1, self.n + self.m), **f64)
+        self._act = torch.zeros((1, self.n), dtype=torch.uint8, device=device)
+        self._rho = torch.zeros((1,), **f64)
+
+    def _grad_lag(self, it: _DeviceIterate, rho: float):
+        self._rho.fill_(rho)
+        K.aug_lag_grad(it.J, it.grad, it.cons if self.m > 0 else None, it.y if self.m > 0 else None, self._rho,
+                       self._dL, None, None, _one())
+        return self._dL
+
+    def compute_active_set(self, iterate, rho: float, tau=None) -> np.ndarray:
+        if tau is not None:
+            raise NotImplementedError("tau-based active sets (ActiveSetType != Standard) are outside the B200 path")
+        it = _cache(iterate, self.device)
+        o = _cache(self.orig_iterate, self.device)
+        dL = self._grad_lag(it, rho)
+        m = self.m
+        K.residual(it.x, it.y if m > 0 else None, o.x, o.y if m > 0 else None, dL, it.cons if m > 0 else None,
+                   self.lb_d, self.ub_d, self.dt_d, True, 0, self._act, None, None, _one())
+        return self._act[0].cpu().numpy().astype(bool)
+
+    def value_at(self, iterate, rho: float, active_set: Optional[np.ndarray] = None) -> np.ndarray:
+        it = _cache(iterate, self.device)
+        o = _cache(self.orig_iterate, self.device)
+        dL = self._grad_lag(it, rho)
+        m = self.m
+        mode = 0
+        if active_set is not None:
+            self._act.copy_(torch.from_numpy(np.asarray(active_set, dtype=np.uint8)).to(self.device).reshape(1, self.n))
+            mode = 1
+        K.residual(it.x, it.y if m > 0 else None, o.x, o.y if m > 0 else None, dL, it.cons if m > 0 else None,
+                   self.lb_d, self.ub_d, self.dt_d, True, mode, self._act, self._F, None, _one())
+        return self._F[0].cpu().numpy()
+
+    def active_set_at_point(self, p: np.ndarray) -> np.ndarray:
+        return np.logical_or(p < self.lb - 1e-8, p > self.ub + 1e-8)
+
+    def value_device(self, iterate, rho: float, active_d: torch.Tensor) -> torch.Tensor:
+        """F(iterate) with a device-resident active set; result stays on the device."""
+        it = _cache(iterate, self.device)
+        o = _cache(self.orig_iterate, self.device)
+        dL = self._grad_lag(it, rho)
+        m = self.m
+        K.residual(it.x, it.y if m > 0 else None, o.x, o.y if m > 0 else None, dL, it.cons if m > 0 else None,
+                   self.lb_d, self.ub_d, self.dt_d, True, 1, active_d, self._F, None, _one())
+        return self._F
+
+
+class StepResult:
+    """pygradflow/step/solver/step_solver.py:16-63; clip / dx fix-up / diff come from gf_step_finish."""
+
+    def __init__(self, orig_iterate, dx, dy, active_set, rcond=None, xn=None, diff=None):
+        self.orig_iterate = orig_iterate
+        self.dx = dx
+        self.dy = dy
+        self.active_set = active_set
+        self.rcond = rcond
+        self.xn = xn
+        self._diff = diff
+        self._iterate = None
+
+    @property
+    def iterate(self):
+        if self._iterate is None:
+            o = self.orig_iterate
+            cls = type(o)
+            yn = o.y - self.dy
+            ev = getattr(o, "eval", None)
+            if ev is not None:
+                self._iterate = cls(o.problem, o.params, self.xn, yn, ev)
+            else:
+                self._iterate = cls(o.problem, o.params, self.xn, yn)
+        return self._iterate
+
+    @property
+    def diff(self) -> float:
+        return self._diff
+
+
+class B200StepSolver:
+    """StepSolver for ``Params.step_solver``: the Symmetric formulation solved by the CUDA kernels."""
+
+    def __init__(self, problem, params, orig_iterate, dt: float, rho: float, device="cuda",
+                 linear: Optional[LinearSolverType] = None):
+        assert dt > 0.0 and rho > 0.0
+        self.problem = problem
+        self.params = params
+        self.orig_iterate = orig_iterate
+        self.dt = dt
+        self.rho = rho
+        self.n = problem.num_vars
+        self.m = problem.num_cons
+        self.device = device
+        self._func = B200StepFunc(problem, orig_iterate, dt, device)
+        if linear is None:
+            linear = getattr(params, "b200_linear_solver", LinearSolverType.Auto)
+        self.engine = KKTEngine(1, self.n, self.m, device, linear)
+        f64 = dict(dtype=torch.float64, device=device)
+        self.rho_d = torch.full((1,), rho, **f64)
+        self.H = None
+        self.J = None
+        self._have_active = False
+        self._factored = False
+        self._xn = torch.zeros((1, self.n), **f64)
+        self._yn = torch.zeros((1, self.m), **f64)
+        self._dx = torch.zeros((1, self.n), **f64)
+        self._dy = torch.zeros((1, self.m), **f64)
+        self._diff = torch.zeros((1,), **f64)
+        self._active_host = None
+        self.num_factorizations = 0
+
+    @property
+    def func(self) -> B200StepFunc:
+        return self._func
+
+    @property
+    def active_set(self) -> np.ndarray:
+        assert self._active_host is not None
+        return self._active_host
+
+    def reset_deriv(self) -> None:
+        self._factored = False
+
+    def update_derivs(self, iterate) -> None:
+        """scaled_step_solver.py:76-79: J = aug_lag_deriv_xy, H = aug_lag_deriv_xx(rho=0) (multiplier y)."""
+        n, m = self.n, self.m
+        self.J = _dev(_dense(iterate.aug_lag_deriv_xy()), self.device).reshape(1, m, n) if m > 0 else None
+        self.H = _dev(_dense(iterate.aug_lag_deriv_xx(rho=0.0)), self.device).reshape(1, n, n)
+        self.reset_deriv()
+
+    def update_active_set(self, active_set: np.ndarray) -> None:
+        """scaled_step_solver.py:81-83."""
+        a = np.array(active_set, dtype=bool, copy=True)
+        assert a.shape == (self.n,)
+        self._active_host = a
+        self.engine.active.copy_(torch.from_numpy(a.astype(np.uint8)).to(self.device).reshape(1, self.n))
+        self.engine.update_active_set(_one())
+        self._have_active = True
+        self.reset_deriv()
+
+    def linear_solver(self, mat):
+        """StepSolver.linear_solver (step_solver.py:94-98) for callers that hand over an explicit matrix."""
+        return B200LinearSolver(mat, symmetric=True, device=self.device)
+
+    def solve(self, iterate) -> StepResult:
+        """scaled_step_solver.py:85-107 + symmetric_step_solver.py:96-164 + step_solver.py:16-63."""
+        assert self._have_active and self.H is not None
+        eng, f = self.engine, self._func
+        LSE, SSE = _reference_errors()
+        if not self._factored:
+            eng.factor(self.H, self.J, f.dt_d, self.rho_d, _one())
+            self.num_factorizations += 1
+            if int(eng.info.item()) != 0:
+                raise SSE() from LSE("KKT factorisation failed")
+            if getattr(self.params, "inertia_correction", False):
+                if eng.linear != LinearSolverType.LDLT or int(eng.fbkey.item()) != 0:
+                    raise Exception("Inertia correction requested but not available")
+                if int(eng.nneg.item()) != self.m:
+                    raise SSE() from LSE("Invalid matrix inertia")
+            self._factored = True
+        F = f.value_device(iterate, self.rho, eng.active)
+        it = _cache(iterate, self.device)
+        m = self.m
+        eng.step(self.H, self.J, it.x, it.y if m > 0 else None, F, f.dt_d, self.rho_d, f.lb_d, f.ub_d, self._xn,
+                 self._yn if m > 0 else None, self._diff, _one(), dx=self._dx, dy=self._dy if m > 0 else None)
+        out = torch.cat([self._xn[0], self._dx[0], self._dy[0], self._diff]).cpu().numpy()
+        n = self.n
+        xn, dx, dy, diff = out[:n], out[n : 2 * n], out[2 * n : 2 * n + m], float(out[-1])
+        return StepResult(iterate, dx, dy, self._active_host, None, xn=xn.copy(), diff=diff)

@@ -1,0 +1,129 @@
+"""Batched problem families: device-side twins of the reference's ``Problem`` callbacks
+(pygradflow/problem.py:112-192) for B independent instances.
+
+Every family keeps its data in HBM as contiguous float64 tensors with the batch index outermost and
+evaluates through the family's CUDA kernels (no per-instance Python callbacks on the hot loop).
+Constraints are equalities c(x) = 0 plus variable bounds -- the form the reference's
+``ConstrainedProblem`` produces (pygradflow/cons_problem.py:8-55); it is a no-op for such problems.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .kernels import WorkList
+
+
+def _dev(a, device):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).to(device).contiguous()
+
+
+class BatchedProblem:
+    """Base: B instances, n variables, m equality constraints, bounds var_lb/var_ub [B, n]."""
+
+    jac_constant = False   # J does not depend on x (linear constraints)
+    hess_constant = False  # Hessian of the Lagrangian does not depend on (x, y)
+
+    def __init__(self, var_lb: torch.Tensor, var_ub: torch.Tensor, num_cons: int):
+        assert var_lb.shape == var_ub.shape and var_lb.dim() == 2
+        self.var_lb = var_lb.contiguous()
+        self.var_ub = var_ub.contiguous()
+        self.B, self.n = var_lb.shape
+        self.m = int(num_cons)
+        self.device = var_lb.device
+
+    # -- evaluation interface ------------------------------------------------------------------
+    def eval(self, x, grad, cons, obj, work: WorkList) -> None:
+        """obj[B], grad[B,n] = grad f(x), cons[B,m] = c(x)."""
+        raise NotImplementedError
+
+    def jac(self, x, out, work: WorkList) -> Optional[torch.Tensor]:
+        """J(x) [B,m,n]; may return a persistent tensor instead of filling ``out``."""
+        raise NotImplementedError
+
+    def lag_hess(self, x, y, out, work: WorkList) -> torch.Tensor:
+        """Hessian of the Lagrangian at (x, y) [B,n,n], symmetric."""
+        raise NotImplementedError
+
+    def select(self, idx) -> "BatchedProblem":
+        """The sub-batch of instances ``idx`` (used to shard the batch across ranks)."""
+        raise NotImplementedError
+
+
+class BatchedQP(BatchedProblem):
+    """f = x'Hx/2 + g'x, c = Ax + b (the reference's generic QP, tests/pygradflow/qp.py:4-30)."""
+
+    jac_constant = True
+    hess_constant = True
+
+    def __init__(self, H, A, g, b, lb, ub, device="cuda"):
+        H, g = _dev(H, device), _dev(g, device)
+        lb, ub = _dev(lb, device), _dev(ub, device)
+        m = 0 if A is None else A.shape[1]
+        super().__init__(lb, ub, m)
+        self.H, self.g = H, g
+        self.A = _dev(A, device) if m > 0 else None
+        self.b = _dev(b, device) if m > 0 else None
+
+    def eval(self, x, grad, cons, obj, work):
+        K.qp_eval(self.H, self.A, self.g, self.b, x, grad, cons if self.m > 0 else None, obj, work)
+
+    def jac(self, x, out, work):
+        return self.A
+
+    def lag_hess(self, x, y, out, work):
+        return self.H
+
+    def select(self, idx):
+        sel = lambda t: None if t is None else t[idx].contiguous()
+        q = object.__new__(BatchedQP)
+        BatchedProblem.__init__(q, sel(self.var_lb), sel(self.var_ub), self.m)
+        q.H, q.g, q.A, q.b = sel(self.H), sel(self.g), sel(self.A), sel(self.b)
+        return q
+
+
+class BatchedRosenbrock(BatchedProblem):
+    """Chained Rosenbrock with per-instance coefficients a, b [B, n-1]; bounds only (cfg2).
+
+    n = 2, a = 1, b = 100 is the reference's tests/pygradflow/rosenbrock.py."""
+
+    def __init__(self, a, b, lb, ub, device="cuda"):
+        lb, ub = _dev(lb, device), _dev(ub, device)
+        super().__init__(lb, ub, 0)
+        self.a, self.b = _dev(a, device), _dev(b, device)
+        self._zeroed = set()
+
+    def eval(self, x, grad, cons, obj, work):
+        K.rosen_eval(self.a, self.b, x, grad, obj, work)
+
+    def jac(self, x, out, work):
+        return None
+
+    def lag_hess(self, x, y, out, work):
+        if out.data_ptr() not in self._zeroed:  # the kernel writes the three diagonals only
+            out.zero_()
+            self._zeroed.add(out.data_ptr())
+        K.rosen_hess(self.a, self.b, x, out, work)
+        return out
+
+    def select(self, idx):
+        q = object.__new__(BatchedRosenbrock)
+        BatchedProblem.__init__(q, self.var_lb[idx].contiguous(), self.var_ub[idx].contiguous(), 0)
+        q.a, q.b = self.a[idx].contiguous(), self.b[idx].contiguous()
+        q._zeroed = set()
+        return q
+
+
+class BatchedDense(BatchedProblem):
+    """Problem whose derivatives are supplied as dense device tensors by the caller (the batch = 1
+    plug-in path evaluates a Python ``Problem`` on the host and uploads grad / cons / J / H here)."""
+
+    def __init__(self, lb, ub, num_cons, device="cuda"):
+        super().__init__(_dev(lb, device), _dev(ub, device), num_cons)
+
+    def eval(self, x, grad, cons, obj, work):
+        raise RuntimeError("BatchedDense has no device evaluator; derivatives are uploaded by the caller")

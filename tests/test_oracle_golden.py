@@ -8,19 +8,11 @@ active sets, accept sequences, iteration counts and status identical.
 import numpy as np
 import pytest
 
+from helpers import noise_horizon, rel_err
 from oracle import gradflow_oracle as orc
 from pygradflow_b200 import synth
 
 RTOL = 1e-10
-
-
-def rel_err(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    assert a.shape == b.shape, (a.shape, b.shape)
-    if a.size == 0:
-        return 0.0
-    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
 
 
 def make_qp(n, m, k):
@@ -130,21 +122,6 @@ def test_globalized_steps(golden, n, m, k):
 
 
 # ------------------------------------------------------------------ full solves
-THETA_NOISE = 1e-8
-
-
-def noise_horizon(trace):
-    """Index of the first outer iteration whose contraction ratio theta = |d2|/|d1| is rounding
-    noise (the second simplified-Newton step of a QP whose frozen active set was already solved
-    exactly is ~1e-16).  The reference feeds log(theta) into its PI step-size controller
-    (distance_ratio_control.py:57-63), so from there on lambda -- and the trajectory -- depends on
-    the last bits of the linear solve; strict 1e-10 parity is only meaningful before it."""
-    for i, t in enumerate(trace):
-        if t["theta"] == t["theta"] and t["theta"] < THETA_NOISE:
-            return i
-    return len(trace)
-
-
 def _check_solve(g, key, problem, x0, y0, newton="Simplified", tol=RTOL):
     params = orc.OracleParams(newton_type=NEWTON[newton])
     res = orc.Solver(problem, params).solve(x0, y0, record=True)
