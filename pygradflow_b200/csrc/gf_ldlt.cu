@@ -1,5 +1,5 @@
-// Batched dense FP64 LDL' (no pivoting) for symmetric quasi-definite KKT matrices, trailing update on the
-// FP64 tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4), + substitution (a13, a14, inertia contract).
+// Batched dense FP64 LDL' (no pivoting) for symmetric quasi-definite KKT matrices on the FP64 tensor pipe
+// (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4), + substitution (a13, a14, inertia contract).
 //
 // Replaces pygradflow/linear_solver/lu_solver.py:9-21 on the Symmetric step solver's matrix
 // K = [[H_II + lamb I, J_I'], [J_I, -delta I]] (symmetric_step_solver.py:49-77), which is quasi-definite
@@ -7,22 +7,27 @@
 // pivoting; the signs of D give the inertia that ma57_solver.py:76-79 / mumps_solver.py:81-82 /
 // ssids_solver.py:22-23 report (num_neg_eigvals).
 //
-// Layout: K[b] ld x ld row-major, only the lower triangle is read/written; the matrix is padded with an
-// identity block up to Np = roundup(N_b, 64) (gf_kkt_assemble does this) so no kernel has edge tiles
-// inside a 64-block.  d is kept on the diagonal of K and, contiguously, in dvec[b].
+// Layout: K[b] ld x ld row-major, only the lower triangle is read; the matrix is padded with an identity
+// block up to Np = roundup(N_b, 64) (gf_kkt_assemble does this) so no kernel has edge tiles inside a
+// 64-block.  d is kept on the diagonal of K and, contiguously, in dvec[b].  The strict upper triangle of
+// every 64x64 DIAGONAL block is scratch: it receives inv(L_kk)' for the panel kernel.
 //
-// Left-looking by 64-wide block columns, three batched launches per block column k:
-//   update(k)  A[i, k] -= sum_{p<k} (L[i,p] D_p) L[k,p]'   128x64 tiles, DMMA, cp.async 3-stage pipeline
-//   diag(k)    A[k, k] = L_kk D_k L_kk'                    64x64 in shared memory
-//   trsm(k)    L[i, k] = A[i, k] L_kk^{-T} D_k^{-1}        thread-per-row substitution (full-rate DFMA)
-// Each matrix entry is read/written O(1) times (left-looking), operands stream once per block column:
-// ~ 8 N^3 / (6*64) bytes per matrix -> the update is bound by the FP64 pipe, not HBM.
+// Left-looking by 64-wide block columns, two batched launches per block column k (j0 = 64 k):
+//   diag(k)   C = A[k,k] - sum_{p<k} (L[k,p] D_p) L[k,p]'  (DMMA, cp.async pipeline), then in shared memory
+//             C = L_kk D_k L_kk' and X = inv(L_kk) (blocked 16/32/64), one CTA per matrix;
+//   panel(k)  128x64 tiles below the diagonal: C = A[i,k] - sum_{p<k} (L[i,p] D_p) L[k,p]'  (DMMA),
+//             then the triangular solve as one more DMMA product L[i,k] = (C X') D_k^{-1}.
+// Every matrix entry is read and written once, operands stream once per block column
+// (~ 8 N^3 / (6*64) bytes per matrix), so the factorisation is bound by the FP64 pipe, not by HBM.
 #include "gf_common.cuh"
 #include "../../include/gradflow_b200.h"
 
 namespace {
 
 constexpr int NB = 64;
+constexpr int KC = 16;       // k-chunk per pipeline stage
+constexpr int SP = KC + 4;   // smem row pitch of a stage (bank-conflict-free DMMA fragment loads)
+constexpr int EP = NB + 4;   // smem row pitch of 64-wide tiles in the epilogues (same property)
 
 __device__ __forceinline__ int padded_order(const int32_t* Nvec, int Nfixed, int b, int ld) {
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
@@ -30,8 +35,25 @@ __device__ __forceinline__ int padded_order(const int32_t* Nvec, int Nfixed, int
     return Np < ld ? Np : ld;
 }
 
+// dst (M x N, pitch ldd) = -A (M x Kd, pitch lda) * Bm (Kd x N, pitch ldb), all in shared memory.
+__device__ __forceinline__ void smem_neg_matmul(double* dst, int ldd, const double* A, int lda, const double* Bm,
+                                                int ldb, int M, int N, int Kd) {
+    for (int e = threadIdx.x; e < M * N; e += blockDim.x) {
+        const int r = e / N, c = e - r * N;
+        double acc = 0.0;
+        for (int p = 0; p < Kd; p++) acc = fma(A[r * lda + p], Bm[p * ldb + c], acc);
+        dst[r * ldd + c] = -acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ldlt_diag_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k,
+constexpr int DG_STAGES = 3;
+constexpr int DG_BW = 4;  // panel width of the in-shared-memory factorisation
+constexpr int XP = NB + 1;  // pitch of the inverse in shared memory
+constexpr int DG_OPS = (DG_STAGES * NB * SP > NB * XP) ? DG_STAGES * NB * SP : NB * XP;
+constexpr int DG_SMEM = (NB * (NB + 1) + DG_OPS) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 3) ldlt_diag_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k,
                                                         double* __restrict__ K, double* __restrict__ dvec,
                                                         int32_t* __restrict__ info, int32_t* __restrict__ nneg,
                                                         const int32_t* __restrict__ npos_expected, GfWork work) {
@@ -40,42 +62,228 @@ __global__ void __launch_bounds__(256) ldlt_diag_kernel(int ld, const int32_t* _
     const int Np = padded_order(Nvec, Nfixed, b, ld);
     const int j0 = k * NB;
     if (j0 >= Np) return;
-    __shared__ double S[NB][NB + 1];
+    extern __shared__ double sm[];
+    double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);   // 64 x 65
+    double* Ops = sm + NB * (NB + 1);                                 // DG_STAGES x 64 x SP, later X = inv(L)
+    __shared__ double rinv[NB];
+    __shared__ double T[32 * 33];
+    __shared__ double Wp[NB * (DG_BW + 1)];  // W = L D of the current panel
     __shared__ int s_bad, s_neg, s_sign;
     double* Kb = K + (size_t)b * ld * ld;
-    if (threadIdx.x == 0) { s_bad = 0x7fffffff; s_neg = 0; s_sign = 0; }
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-        const int i = e >> 6, c = e & 63;
-        S[i][c] = (c <= i) ? Kb[(size_t)(j0 + i) * ld + j0 + c] : 0.0;
+    const double* db = dvec + (size_t)b * ld;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_bad = 0x7fffffff; s_neg = 0; s_sign = 0; }
+
+    // ---- phase A: diagonal tile minus the contributions of the block columns to its left (DMMA)
+    {
+        const int wm = wid >> 1, wn = wid & 1;  // 4 x 2 warps, 16 x 32 each
+        const int g = lane >> 2, q = lane & 3;
+        double acc[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const int row = j0 + wm * 16 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int col = j0 + wn * 32 + ni * 8 + 2 * q;
+                const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)row * ld + col);
+                acc[mi][ni][0] = v.x;
+                acc[mi][ni][1] = v.y;
+            }
+        }
+        const int nchunks = j0 / KC;
+        auto load_stage = [&](int chunk, int stage) {
+            const int p0 = chunk * KC;
+            double* os = Ops + stage * NB * SP;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int piece = tid + t * 256;  // 512 pieces of 16 B
+                const int r = piece >> 3, part = piece & 7;
+                cp_async16(os + r * SP + part * 2, Kb + (size_t)(j0 + r) * ld + p0 + part * 2);
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < DG_STAGES - 1; s++) {
+            if (s < nchunks) load_stage(s, s);
+            cp_async_commit();
+        }
+        for (int c = 0; c < nchunks; c++) {
+            cp_async_wait<DG_STAGES - 2>();
+            __syncthreads();
+            const int nxt = c + DG_STAGES - 1;
+            if (nxt < nchunks) load_stage(nxt, nxt % DG_STAGES);
+            cp_async_commit();
+            const double* os = Ops + (c % DG_STAGES) * NB * SP;
+            const double* as = os + (wm * 16 + g) * SP + q;
+            const double* bs = os + (wn * 32 + g) * SP + q;
+            const double* dp = db + c * KC + q;
+#pragma unroll
+            for (int kk = 0; kk < KC; kk += 4) {
+                const double nd = -__ldg(dp + kk);
+                double a[2], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) a[mi] = as[mi * 8 * SP + kk] * nd;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * SP + kk];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+            }
+        }
+        cp_async_wait<0>();
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+            const int r = wm * 16 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int c = wn * 32 + ni * 8 + 2 * q;
+                S[r][c] = acc[mi][ni][0];
+                S[r][c + 1] = acc[mi][ni][1];
+            }
+        }
     }
     __syncthreads();
-    const int i = threadIdx.x & 63, cg = threadIdx.x >> 6;
-    // right-looking on W = L D kept in place; scaled to L at the end
-    for (int j = 0; j < NB - 1; j++) {
-        const double d = S[j][j];
-        if (i > j && d != 0.0) {
-            const double li = S[i][j] / d;
-            for (int c = j + 1 + ((cg - (j + 1)) & 3); c <= i; c += 4) S[i][c] -= li * S[c][j];
+
+    // ---- phase B: C = L D L' in place, right-looking in panels of DG_BW columns on W = L D (scaled to L
+    // afterwards).  Every thread factors the small diagonal block redundantly in registers, so a panel
+    // costs two barriers instead of DG_BW.
+    {
+        const int i = tid & 63, cg = tid >> 6;
+        constexpr int BW = DG_BW;
+        for (int jb = 0; jb < NB; jb += BW) {
+            double Dg[BW][BW], rj[BW];
+#pragma unroll
+            for (int r = 0; r < BW; r++)
+#pragma unroll
+                for (int c = 0; c <= r; c++) Dg[r][c] = S[jb + r][jb + c];
+#pragma unroll
+            for (int j = 0; j < BW; j++) {
+                const double d = Dg[j][j];
+                rj[j] = (d != 0.0) ? __drcp_rn(d) : 0.0;
+#pragma unroll
+                for (int i2 = j + 1; i2 < BW; i2++) {
+                    const double l = Dg[i2][j] * rj[j];
+#pragma unroll
+                    for (int c = j + 1; c <= i2; c++) Dg[i2][c] = fma(-l, Dg[c][j], Dg[i2][c]);
+                }
+            }
+            double l[BW], w[BW];
+            const bool below = i >= jb + BW;
+            if (below) {
+#pragma unroll
+                for (int c = 0; c < BW; c++) w[c] = S[i][jb + c];
+#pragma unroll
+                for (int c = 0; c < BW; c++) {
+#pragma unroll
+                    for (int p = 0; p < c; p++) w[c] = fma(-l[p], Dg[c][p], w[c]);
+                    l[c] = w[c] * rj[c];
+                }
+                if (cg == 0) {
+#pragma unroll
+                    for (int c = 0; c < BW; c++) Wp[i * (BW + 1) + c] = w[c];
+                }
+            }
+            __syncthreads();  // Wp complete; nobody reads S[., jb..jb+7] below this line any more
+            if (below) {
+                if (cg == 0) {
+#pragma unroll
+                    for (int c = 0; c < BW; c++) S[i][jb + c] = w[c];
+                }
+                const int cbeg = jb + BW;
+                const int cstart = cbeg + ((cg - cbeg) & 3);
+                for (int c = cstart; c <= i; c += 4) {
+                    double acc = S[i][c];
+#pragma unroll
+                    for (int p = 0; p < BW; p++) acc = fma(-l[p], Wp[c * (BW + 1) + p], acc);
+                    S[i][c] = acc;
+                }
+            } else if (i >= jb && cg == 0) {
+                const int r = i - jb;
+#pragma unroll
+                for (int rr = 0; rr < BW; rr++)
+                    if (rr == r) {
+#pragma unroll
+                        for (int c = 0; c <= rr; c++) S[i][jb + c] = Dg[rr][c];
+                    }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
-    if (threadIdx.x < NB) {
-        const double d = S[threadIdx.x][threadIdx.x];
-        if (!(isfinite(d)) || d == 0.0) atomicMin(&s_bad, (int)threadIdx.x + 1);
+    if (tid < NB) {
+        const double d = S[tid][tid];
+        if (!(isfinite(d)) || d == 0.0) atomicMin(&s_bad, tid + 1);
         const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
-        const int j = j0 + (int)threadIdx.x;
+        const int j = j0 + tid;
         if (d < 0.0 && j < N) atomicAdd(&s_neg, 1);
         // quasi-definite sign pattern: the first npos pivots positive, the remaining (up to N) negative
         if (npos_expected != nullptr && j < N && ((j < npos_expected[b]) != (d > 0.0))) s_sign = 1;
-        dvec[(size_t)b * ld + j0 + threadIdx.x] = d;
+        dvec[(size_t)b * ld + j] = d;
+        rinv[tid] = 1.0 / d;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
         const int r = e >> 6, c = e & 63;
-        if (c < r) Kb[(size_t)(j0 + r) * ld + j0 + c] = S[r][c] / S[c][c];
-        else if (c == r) Kb[(size_t)(j0 + r) * ld + j0 + c] = S[r][r];
+        if (c < r) S[r][c] *= rinv[c];  // W -> L
     }
-    if (threadIdx.x == 0) {
+    __syncthreads();
+
+    // ---- phase C: X = inv(L) (unit lower), blocked 16 -> 32 -> 64; X and the scratch T live in Ops
+    double* X = Ops;                    // 64 x XP
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
+        const int r = e >> 6, c = e & 63;
+        X[r * XP + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (tid < NB) {  // the four 16x16 diagonal blocks, one thread per column
+        const int blk = tid >> 4, j = tid & 15, o = blk * 16;
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 1; i < 16; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int p = 0; p < i; p++) s = fma(S[o + i][o + p], x[p], s);
+            if (i > j) x[i] = -s;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (i > j) X[(o + i) * XP + o + j] = x[i];
+    }
+    __syncthreads();
+    // 32-level: X[h+16:h+32, h:h+16] = -X11' * (L10 * X00), h in {0, 32}
+    for (int h = 0; h < NB; h += 32) {
+        for (int e = tid; e < 16 * 16; e += blockDim.x) {  // T = L10 * X00
+            const int r = e >> 4, c = e & 15;
+            double acc = 0.0;
+            for (int p = c; p < 16; p++) acc = fma(S[h + 16 + r][h + p], X[(h + p) * XP + h + c], acc);
+            T[r * 33 + c] = acc;
+        }
+        __syncthreads();
+        smem_neg_matmul(X + (h + 16) * XP + h, XP, X + (h + 16) * XP + h + 16, XP, T, 33, 16, 16, 16);
+        __syncthreads();
+    }
+    // 64-level: X[32:64, 0:32] = -X[32:64, 32:64] * (L[32:64, 0:32] * X[0:32, 0:32])
+    for (int e = tid; e < 32 * 32; e += blockDim.x) {
+        const int r = e >> 5, c = e & 31;
+        double acc = 0.0;
+        for (int p = c; p < 32; p++) acc = fma(S[32 + r][p], X[p * XP + c], acc);
+        T[r * 33 + c] = acc;
+    }
+    __syncthreads();
+    smem_neg_matmul(X + 32 * XP, XP, X + 32 * XP + 32, XP, T, 33, 32, 32, 32);
+    __syncthreads();
+
+    // ---- write back: L (strict lower), d (diagonal), inv(L)' (strict upper)
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
+        const int r = e >> 6, c = e & 63;
+        double v;
+        if (c < r) v = S[r][c];
+        else if (c == r) v = S[r][r];
+        else v = X[c * XP + r];  // K[j0 + r][j0 + c] = X[c][r], c > r
+        Kb[(size_t)(j0 + r) * ld + j0 + c] = v;
+    }
+    if (tid == 0) {
         int bad = 0;
         if (s_bad != 0x7fffffff) bad = j0 + s_bad;        // zero / non-finite pivot at column `bad`
         else if (s_sign) bad = GF_INFO_NOT_QUASIDEFINITE;  // wrong pivot sign: unpivoted LDL' not trusted
@@ -88,109 +296,58 @@ __global__ void __launch_bounds__(256) ldlt_diag_kernel(int ld, const int32_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int TR_ROWS = 128;
+constexpr int TM = 128, TN = 64, STAGES = 2;
+constexpr int PKC = 32;        // k-chunk per pipeline stage of the panel kernel
+constexpr int PSP = PKC + 4;   // its smem row pitch (== 4 mod 16: conflict-free fragment loads)
+constexpr int PN_SMEM_PIPE = STAGES * (TM + TN) * PSP * (int)sizeof(double);
+constexpr int PN_SMEM_EPI = (TM + TN) * EP * (int)sizeof(double);
+constexpr int PN_SMEM = PN_SMEM_PIPE > PN_SMEM_EPI ? PN_SMEM_PIPE : PN_SMEM_EPI;
 
-__global__ void __launch_bounds__(TR_ROWS) ldlt_trsm_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+__global__ void __launch_bounds__(256, 2) ldlt_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                             int k, double* __restrict__ K,
                                                             const double* __restrict__ dvec, GfWork work) {
     const int b = gf_instance(work, blockIdx.y);
     if (b < 0) return;
     const int Np = padded_order(Nvec, Nfixed, b, ld);
     const int j0 = k * NB;
-    const int i0 = j0 + NB + blockIdx.x * TR_ROWS;
-    if (i0 >= Np) return;
-    const int nrows = min(TR_ROWS, Np - i0);
-    extern __shared__ double sm[];
-    double* Lt = sm;                     // Lt[p*64 + c] = L_kk[c][p] (c > p)
-    double* dk = Lt + NB * NB;           // 64
-    double* Ws = dk + NB;                // TR_ROWS x 65
-    double* Kb = K + (size_t)b * ld * ld;
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-        const int c = e >> 6, p = e & 63;   // coalesced read of storage row j0 + c
-        if (p < c) Lt[p * NB + c] = Kb[(size_t)(j0 + c) * ld + j0 + p];
-    }
-    if (threadIdx.x < NB) dk[threadIdx.x] = dvec[(size_t)b * ld + j0 + threadIdx.x];
-    for (int e = threadIdx.x; e < nrows * NB; e += blockDim.x) {
-        const int r = e >> 6, c = e & 63;
-        Ws[r * (NB + 1) + c] = Kb[(size_t)(i0 + r) * ld + j0 + c];
-    }
-    __syncthreads();
-    const int r = threadIdx.x;
-    if (r < nrows) {
-        double* w = Ws + r * (NB + 1);
-#pragma unroll 1
-        for (int cb = 0; cb < NB; cb += 8) {
-            double acc[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) acc[u] = w[cb + u];
-            for (int p = 0; p < cb; p++) {
-                const double wp = w[p];
-                const double2* l2 = reinterpret_cast<const double2*>(Lt + p * NB + cb);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const double2 l = l2[u];
-                    acc[2 * u] = fma(-wp, l.x, acc[2 * u]);
-                    acc[2 * u + 1] = fma(-wp, l.y, acc[2 * u + 1]);
-                }
-            }
-#pragma unroll
-            for (int u = 1; u < 8; u++)
-#pragma unroll
-                for (int q = 0; q < u; q++) acc[u] = fma(-acc[q], Lt[(cb + q) * NB + cb + u], acc[u]);
-#pragma unroll
-            for (int u = 0; u < 8; u++) w[cb + u] = acc[u];
-        }
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < nrows * NB; e += blockDim.x) {
-        const int rr = e >> 6, c = e & 63;
-        Kb[(size_t)(i0 + rr) * ld + j0 + c] = Ws[rr * (NB + 1) + c] / dk[c];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-constexpr int TM = 128, TN = 64, KC = 16, STAGES = 3, SP = KC + 4;  // SP: smem row pitch (bank-conflict free)
-
-__global__ void __launch_bounds__(256, 2) ldlt_update_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
-                                                             int k, double* __restrict__ K,
-                                                             const double* __restrict__ dvec, GfWork work) {
-    const int b = gf_instance(work, blockIdx.y);
-    if (b < 0) return;
-    const int Np = padded_order(Nvec, Nfixed, b, ld);
-    const int j0 = k * NB;
-    const int i0 = j0 + blockIdx.x * TM;
+    const int i0 = j0 + NB + blockIdx.x * TM;
     if (i0 >= Np) return;
     extern __shared__ double sm[];
-    double* As = sm;                          // STAGES x TM x SP
-    double* Bs = sm + STAGES * TM * SP;       // STAGES x TN x SP
+    double* As = sm;                          // STAGES x TM x PSP
+    double* Bs = sm + STAGES * TM * PSP;      // STAGES x TN x PSP
     double* Kb = K + (size_t)b * ld * ld;
     const double* db = dvec + (size_t)b * ld;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm = wid >> 1, wn = wid & 1;    // 4 x 2 warps, 32 x 32 each
     const int g = lane >> 2, q = lane & 3;
-    const int nchunks = j0 / KC;
+    const int nchunks = j0 / PKC;
 
     auto load_stage = [&](int chunk, int stage) {
-        const int p0 = chunk * KC;
-        double* as = As + stage * TM * SP;
-        double* bs = Bs + stage * TN * SP;
+        const int p0 = chunk * PKC;
+        double* as = As + stage * TM * PSP;
+        double* bs = Bs + stage * TN * PSP;
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int piece = tid + t * 256;          // 1024 pieces of 16 B: row = piece / 8, part = piece % 8
-            const int r = piece >> 3, part = piece & 7;
-            double* dst = as + r * SP + part * 2;
+        for (int t = 0; t < 8; t++) {
+            const int piece = tid + t * 256;          // 2048 pieces of 16 B: row = piece / 16, part = piece % 16
+            const int r = piece >> 4, part = piece & 15;
+            double* dst = as + r * PSP + part * 2;
             if (i0 + r < Np) cp_async16(dst, Kb + (size_t)(i0 + r) * ld + p0 + part * 2);
             else { dst[0] = 0.0; dst[1] = 0.0; }
         }
 #pragma unroll
-        for (int t = 0; t < 2; t++) {
-            const int piece = tid + t * 256;          // 512 pieces
-            const int r = piece >> 3, part = piece & 7;
-            cp_async16(bs + r * SP + part * 2, Kb + (size_t)(j0 + r) * ld + p0 + part * 2);
+        for (int t = 0; t < 4; t++) {
+            const int piece = tid + t * 256;          // 1024 pieces
+            const int r = piece >> 4, part = piece & 15;
+            cp_async16(bs + r * PSP + part * 2, Kb + (size_t)(j0 + r) * ld + p0 + part * 2);
         }
     };
 
-    // accumulators start from the current A tile
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nchunks) load_stage(s, s);
+        cp_async_commit();
+    }
+    // accumulators start from the current A tile (these loads overlap the first pipeline stages)
     double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
@@ -208,45 +365,89 @@ __global__ void __launch_bounds__(256, 2) ldlt_update_kernel(int ld, const int32
             }
         }
     }
-
+    // -d of the first chunk; every later chunk's values are fetched one chunk ahead
+    double nd[PKC / 4];
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nchunks) load_stage(s, s);
-        cp_async_commit();
-    }
+    for (int u = 0; u < PKC / 4; u++) nd[u] = (nchunks > 0) ? -__ldg(db + 4 * u + q) : 0.0;
     for (int c = 0; c < nchunks; c++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         const int nxt = c + STAGES - 1;
         if (nxt < nchunks) load_stage(nxt, nxt % STAGES);
         cp_async_commit();
-        const double* as = As + (c % STAGES) * TM * SP + (wm * 32 + g) * SP + q;
-        const double* bs = Bs + (c % STAGES) * TN * SP + (wn * 32 + g) * SP + q;
-        const double* dp = db + c * KC + q;
+        const double* as = As + (c % STAGES) * TM * PSP + (wm * 32 + g) * PSP + q;
+        const double* bs = Bs + (c % STAGES) * TN * PSP + (wn * 32 + g) * PSP + q;
+        double ndn[PKC / 4];
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-            const double nd = -__ldg(dp + kk);
+        for (int u = 0; u < PKC / 4; u++) ndn[u] = (c + 1 < nchunks) ? -__ldg(db + (c + 1) * PKC + 4 * u + q) : 0.0;
+#pragma unroll
+        for (int kk = 0; kk < PKC; kk += 4) {
             double a[4], bf[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * SP + kk] * nd;
+            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * PSP + kk] * nd[kk / 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * SP + kk];
+            for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * PSP + kk];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+        }
+#pragma unroll
+        for (int u = 0; u < PKC / 4; u++) nd[u] = ndn[u];
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // every warp is done with the pipeline buffers
+
+    // ---- epilogue: L[i,k] = (C X') D^{-1} with X = inv(L_kk) read from the diagonal block's upper triangle
+    double* Cs = sm;                 // TM x EP
+    double* Xs = sm + TM * EP;       // TN x EP : Xs[n][kk] = X[n][kk]
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const int r = wm * 32 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int c = wn * 32 + ni * 8 + 2 * q;
+            *reinterpret_cast<double2*>(Cs + r * EP + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int kk = e >> 6, n = e & 63;  // coalesced read of storage row j0 + kk
+        double v = 0.0;
+        if (n > kk) v = Kb[(size_t)(j0 + kk) * ld + j0 + n];
+        else if (n == kk) v = 1.0;
+        Xs[n * EP + kk] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    {
+        const double* as = Cs + (wm * 32 + g) * EP + q;
+        const double* bs = Xs + (wn * 32 + g) * EP + q;
+        const int kend = wn * 32 + 32;  // X[n][kk] = 0 for kk > n: this warp's columns need kk < kend only
+        for (int kk = 0; kk < kend; kk += 4) {
+            double a[4], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * EP + kk];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * EP + kk];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
         }
     }
-    cp_async_wait<0>();
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++) {
-        const int row = i0 + wm * 32 + mi * 8 + g;
-        if (row < Np) {
+    for (int ni = 0; ni < 4; ni++) {
+        const int col = j0 + wn * 32 + ni * 8 + 2 * q;
+        const double r0 = 1.0 / __ldg(db + col), r1 = 1.0 / __ldg(db + col + 1);
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
-                const int col = j0 + wn * 32 + ni * 8 + 2 * q;
-                *reinterpret_cast<double2*>(Kb + (size_t)row * ld + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-            }
+        for (int mi = 0; mi < 4; mi++) {
+            const int row = i0 + wm * 32 + mi * 8 + g;
+            if (row < Np)
+                *reinterpret_cast<double2*>(Kb + (size_t)row * ld + col) =
+                    make_double2(acc[mi][ni][0] * r0, acc[mi][ni][1] * r1);
         }
     }
 }
@@ -326,7 +527,8 @@ __global__ void __launch_bounds__(256) ldlt_solve_kernel(int ld, const int32_t* 
 }  // namespace
 
 extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, double* dvec, int32_t* info,
-                              int32_t* nneg, const int32_t* npos_expected, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream) {
+                              int32_t* nneg, const int32_t* npos_expected, const int32_t* work,
+                              const int32_t* nwork_dev, int nwork, void* stream) {
     if (B <= 0 || ld <= 0 || (ld % NB) != 0 || Nmax < 0 || Nmax > ld || !K || !dvec || !info || !nneg)
         return GF_ERR_ARG;
     if (nwork <= 0 || Nmax == 0) return GF_OK;
@@ -334,20 +536,14 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
     GfWork w{work, nwork_dev};
     const int Np = ((Nmax + NB - 1) / NB) * NB;
     const int nblk = Np / NB;
-    const size_t smem_trsm = (size_t)(NB * NB + NB + TR_ROWS * (NB + 1)) * sizeof(double);
-    const size_t smem_upd = (size_t)STAGES * (TM + TN) * SP * sizeof(double);
-    cudaFuncSetAttribute(ldlt_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_trsm);
-    cudaFuncSetAttribute(ldlt_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd);
+    cudaFuncSetAttribute(ldlt_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
+    cudaFuncSetAttribute(ldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PN_SMEM);
     for (int k = 0; k < nblk; k++) {
         const int j0 = k * NB;
-        if (k > 0) {
-            dim3 grid((Np - j0 + TM - 1) / TM, nwork);
-            ldlt_update_kernel<<<grid, 256, smem_upd, s>>>(ld, Nvec, Nmax, k, K, dvec, w);
-        }
-        ldlt_diag_kernel<<<nwork, 256, 0, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg, npos_expected, w);
+        ldlt_diag_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg, npos_expected, w);
         if (j0 + NB < Np) {
-            dim3 grid((Np - j0 - NB + TR_ROWS - 1) / TR_ROWS, nwork);
-            ldlt_trsm_kernel<<<grid, TR_ROWS, smem_trsm, s>>>(ld, Nvec, Nmax, k, K, dvec, w);
+            dim3 grid((Np - j0 - NB + TM - 1) / TM, nwork);
+            ldlt_panel_kernel<<<grid, 256, PN_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, w);
         }
     }
     return gf_launch_status();

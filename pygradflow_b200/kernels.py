@@ -39,9 +39,9 @@ def _w(work: WorkList):
     return (ptr(work.list), ptr(work.count_dev), work.nwork, _stream())
 
 
-def _call(name, *args):
+def _call(name, *args, launches: int = 1):
     global LAUNCHES
-    LAUNCHES += 1
+    LAUNCHES += launches
     native.call(name, *args)
 
 
@@ -109,8 +109,9 @@ def lu_solve(K, Nmax: int, Nvec, piv, rhs, trans: bool, work: WorkList):
 
 def ldlt_factor(K, Nmax: int, Nvec, dvec, info, nneg, npos_expected, work: WorkList):
     B, ld, _ = K.shape
+    nblk = (Nmax + 63) // 64
     _call("gf_ldlt_factor", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(dvec), ptr(info), ptr(nneg), ptr(npos_expected),
-          *_w(work))
+          *_w(work), launches=max(1, 3 * nblk - 2))
 
 
 def ldlt_solve(K, Nmax: int, Nvec, rhs, work: WorkList):
