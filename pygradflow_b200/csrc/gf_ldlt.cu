@@ -51,24 +51,25 @@ constexpr int DG_STAGES = 3;
 constexpr int DG_BW = 4;  // panel width of the in-shared-memory factorisation
 constexpr int XP = NB + 1;  // pitch of the inverse in shared memory
 constexpr int DG_OPS = (DG_STAGES * NB * SP > NB * XP) ? DG_STAGES * NB * SP : NB * XP;
-constexpr int DG_SMEM = (NB * (NB + 1) + DG_OPS) * (int)sizeof(double);
+constexpr int DG_SMEM = (NB * (NB + 1) + DG_OPS + NB + 32 * 33 + NB * (DG_BW + 1) + 2) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(256, 3) ldlt_diag_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k,
-                                                        double* __restrict__ K, double* __restrict__ dvec,
-                                                        int32_t* __restrict__ info, int32_t* __restrict__ nneg,
-                                                        const int32_t* __restrict__ npos_expected, GfWork work) {
-    const int b = gf_instance(work, blockIdx.x);
-    if (b < 0) return;
+__device__ __forceinline__ void ldlt_diag_body(double* sm, int b, int ld, const int32_t* __restrict__ Nvec,
+                                               int Nfixed, int k, double* __restrict__ K,
+                                               double* __restrict__ dvec, int32_t* __restrict__ info,
+                                               int32_t* __restrict__ nneg,
+                                               const int32_t* __restrict__ npos_expected) {
     const int Np = padded_order(Nvec, Nfixed, b, ld);
     const int j0 = k * NB;
     if (j0 >= Np) return;
-    extern __shared__ double sm[];
     double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);   // 64 x 65
     double* Ops = sm + NB * (NB + 1);                                 // DG_STAGES x 64 x SP, later X = inv(L)
-    __shared__ double rinv[NB];
-    __shared__ double T[32 * 33];
-    __shared__ double Wp[NB * (DG_BW + 1)];  // W = L D of the current panel
-    __shared__ int s_bad, s_neg, s_sign;
+    double* rinv = Ops + DG_OPS;                                      // 64
+    double* T = rinv + NB;                                            // 32 x 33
+    double* Wp = T + 32 * 33;                                         // 64 x (DG_BW + 1): W = L D of the current panel
+    int* flags = reinterpret_cast<int*>(Wp + NB * (DG_BW + 1));
+    int& s_bad = flags[0];
+    int& s_neg = flags[1];
+    int& s_sign = flags[2];
     double* Kb = K + (size_t)b * ld * ld;
     const double* db = dvec + (size_t)b * ld;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256, 3) ldlt_diag_kernel(int ld, const int32_t
     {
         const int wm = wid >> 1, wn = wid & 1;  // 4 x 2 warps, 16 x 32 each
         const int g = lane >> 2, q = lane & 3;
+        const bool upper_quadrant = (wn == 1) && (wm < 2);  // rows 0..31 x cols 32..63: never read
         double acc[2][4][2];
 #pragma unroll
         for (int mi = 0; mi < 2; mi++) {
@@ -124,10 +126,12 @@ __global__ void __launch_bounds__(256, 3) ldlt_diag_kernel(int ld, const int32_t
                 for (int mi = 0; mi < 2; mi++) a[mi] = as[mi * 8 * SP + kk] * nd;
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * SP + kk];
+                if (!upper_quadrant) {
 #pragma unroll
-                for (int mi = 0; mi < 2; mi++)
+                    for (int mi = 0; mi < 2; mi++)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+                        for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+                }
             }
         }
         cp_async_wait<0>();
@@ -303,66 +307,55 @@ constexpr int PN_SMEM_PIPE = STAGES * (TM + TN) * PSP * (int)sizeof(double);
 constexpr int PN_SMEM_EPI = (TM + TN) * EP * (int)sizeof(double);
 constexpr int PN_SMEM = PN_SMEM_PIPE > PN_SMEM_EPI ? PN_SMEM_PIPE : PN_SMEM_EPI;
 
-__global__ void __launch_bounds__(256, 2) ldlt_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
-                                                            int k, double* __restrict__ K,
-                                                            const double* __restrict__ dvec, GfWork work) {
-    const int b = gf_instance(work, blockIdx.y);
-    if (b < 0) return;
-    const int Np = padded_order(Nvec, Nfixed, b, ld);
-    const int j0 = k * NB;
-    const int i0 = j0 + NB + blockIdx.x * TM;
-    if (i0 >= Np) return;
-    extern __shared__ double sm[];
-    double* As = sm;                          // STAGES x TM x PSP
-    double* Bs = sm + STAGES * TM * PSP;      // STAGES x TN x PSP
-    double* Kb = K + (size_t)b * ld * ld;
-    const double* db = dvec + (size_t)b * ld;
+// One ROWS x 64 tile of block column k (rows i0.., all inside the padded order): update + triangular solve.
+// ROWS = 128: 4 x 2 warps of 32 x 32;  ROWS = 64 (odd remainder block): 2 x 4 warps of 32 x 16.
+template <int ROWS>
+__device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int ld, double* __restrict__ Kb,
+                                                const double* __restrict__ db) {
+    constexpr int WN = (ROWS == 128) ? 2 : 4;   // warps along the 64 columns
+    constexpr int NI = 8 / WN;                  // 8-column DMMA tiles per warp
+    constexpr int WC = NI * 8;                  // columns per warp
+    constexpr int AT = ROWS / 16;               // 16-byte pieces per thread per stage for the A rows
+    double* As = sm;                            // STAGES x TM x PSP (ROWS rows used)
+    double* Bs = sm + STAGES * TM * PSP;        // STAGES x TN x PSP
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm = wid >> 1, wn = wid & 1;    // 4 x 2 warps, 32 x 32 each
+    const int wm = wid / WN, wn = wid % WN;
     const int g = lane >> 2, q = lane & 3;
     const int nchunks = j0 / PKC;
 
+    // Each thread copies one 16-byte piece of AT A rows and 4 B rows per stage: row = (tid >> 4) + 16 t,
+    // piece = tid & 15; pointers advance by constants.
+    const int lrow = tid >> 4, lpart = (tid & 15) * 2;
+    const double* gA = Kb + (size_t)(i0 + lrow) * ld + lpart;
+    const double* gB = Kb + (size_t)(j0 + lrow) * ld + lpart;
+    const size_t gstride = (size_t)16 * ld;
+    double* sA = As + lrow * PSP + lpart;
+    double* sB = Bs + lrow * PSP + lpart;
     auto load_stage = [&](int chunk, int stage) {
-        const int p0 = chunk * PKC;
-        double* as = As + stage * TM * PSP;
-        double* bs = Bs + stage * TN * PSP;
+        const double* ga = gA + chunk * PKC;
+        const double* gb = gB + chunk * PKC;
+        double* sa = sA + stage * TM * PSP;
+        double* sb = sB + stage * TN * PSP;
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-            const int piece = tid + t * 256;          // 2048 pieces of 16 B: row = piece / 16, part = piece % 16
-            const int r = piece >> 4, part = piece & 15;
-            double* dst = as + r * PSP + part * 2;
-            if (i0 + r < Np) cp_async16(dst, Kb + (size_t)(i0 + r) * ld + p0 + part * 2);
-            else { dst[0] = 0.0; dst[1] = 0.0; }
-        }
+        for (int t = 0; t < AT; t++) cp_async16(sa + t * 16 * PSP, ga + t * gstride);
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int piece = tid + t * 256;          // 1024 pieces
-            const int r = piece >> 4, part = piece & 15;
-            cp_async16(bs + r * PSP + part * 2, Kb + (size_t)(j0 + r) * ld + p0 + part * 2);
-        }
+        for (int t = 0; t < 4; t++) cp_async16(sb + t * 16 * PSP, gb + t * gstride);
     };
-
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
         if (s < nchunks) load_stage(s, s);
         cp_async_commit();
     }
-    // accumulators start from the current A tile (these loads overlap the first pipeline stages)
-    double acc[4][4][2];
+    // accumulators start from the current A tile (these loads overlap the first pipeline stage)
+    double acc[4][NI][2];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
-        const int row = i0 + wm * 32 + mi * 8 + g;
+        const double* rowp = Kb + (size_t)(i0 + wm * 32 + mi * 8 + g) * ld + j0 + wn * WC + 2 * q;
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-            const int col = j0 + wn * 32 + ni * 8 + 2 * q;
-            if (row < Np) {
-                const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)row * ld + col);
-                acc[mi][ni][0] = v.x;
-                acc[mi][ni][1] = v.y;
-            } else {
-                acc[mi][ni][0] = 0.0;
-                acc[mi][ni][1] = 0.0;
-            }
+        for (int ni = 0; ni < NI; ni++) {
+            const double2 v = *reinterpret_cast<const double2*>(rowp + ni * 8);
+            acc[mi][ni][0] = v.x;
+            acc[mi][ni][1] = v.y;
         }
     }
     // -d of the first chunk; every later chunk's values are fetched one chunk ahead
@@ -376,21 +369,21 @@ __global__ void __launch_bounds__(256, 2) ldlt_panel_kernel(int ld, const int32_
         if (nxt < nchunks) load_stage(nxt, nxt % STAGES);
         cp_async_commit();
         const double* as = As + (c % STAGES) * TM * PSP + (wm * 32 + g) * PSP + q;
-        const double* bs = Bs + (c % STAGES) * TN * PSP + (wn * 32 + g) * PSP + q;
+        const double* bs = Bs + (c % STAGES) * TN * PSP + (wn * WC + g) * PSP + q;
         double ndn[PKC / 4];
 #pragma unroll
         for (int u = 0; u < PKC / 4; u++) ndn[u] = (c + 1 < nchunks) ? -__ldg(db + (c + 1) * PKC + 4 * u + q) : 0.0;
 #pragma unroll
         for (int kk = 0; kk < PKC; kk += 4) {
-            double a[4], bf[4];
+            double a[4], bf[NI];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * PSP + kk] * nd[kk / 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * PSP + kk];
+            for (int ni = 0; ni < NI; ni++) bf[ni] = bs[ni * 8 * PSP + kk];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+                for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
         }
 #pragma unroll
         for (int u = 0; u < PKC / 4; u++) nd[u] = ndn[u];
@@ -399,14 +392,14 @@ __global__ void __launch_bounds__(256, 2) ldlt_panel_kernel(int ld, const int32_
     __syncthreads();  // every warp is done with the pipeline buffers
 
     // ---- epilogue: L[i,k] = (C X') D^{-1} with X = inv(L_kk) read from the diagonal block's upper triangle
-    double* Cs = sm;                 // TM x EP
+    double* Cs = sm;                 // ROWS x EP
     double* Xs = sm + TM * EP;       // TN x EP : Xs[n][kk] = X[n][kk]
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
         const int r = wm * 32 + mi * 8 + g;
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-            const int c = wn * 32 + ni * 8 + 2 * q;
+        for (int ni = 0; ni < NI; ni++) {
+            const int c = wn * WC + ni * 8 + 2 * q;
             *reinterpret_cast<double2*>(Cs + r * EP + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
     }
@@ -421,35 +414,84 @@ __global__ void __launch_bounds__(256, 2) ldlt_panel_kernel(int ld, const int32_
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+        for (int ni = 0; ni < NI; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
     {
         const double* as = Cs + (wm * 32 + g) * EP + q;
-        const double* bs = Xs + (wn * 32 + g) * EP + q;
-        const int kend = wn * 32 + 32;  // X[n][kk] = 0 for kk > n: this warp's columns need kk < kend only
+        const double* bs = Xs + (wn * WC + g) * EP + q;
+        // X[n][kk] = 0 for kk > n: the 8 columns starting at n0 only need kk < n0 + 8
+        const int kend = wn * WC + WC;
         for (int kk = 0; kk < kend; kk += 4) {
-            double a[4], bf[4];
+            double a[4];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * EP + kk];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * EP + kk];
+            for (int ni = 0; ni < NI; ni++) {
+                if (kk < wn * WC + ni * 8 + 8) {
+                    const double bf = bs[ni * 8 * EP + kk];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+                    for (int mi = 0; mi < 4; mi++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++) {
-        const int col = j0 + wn * 32 + ni * 8 + 2 * q;
+    for (int ni = 0; ni < NI; ni++) {
+        const int col = j0 + wn * WC + ni * 8 + 2 * q;
         const double r0 = 1.0 / __ldg(db + col), r1 = 1.0 / __ldg(db + col + 1);
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
             const int row = i0 + wm * 32 + mi * 8 + g;
-            if (row < Np)
-                *reinterpret_cast<double2*>(Kb + (size_t)row * ld + col) =
-                    make_double2(acc[mi][ni][0] * r0, acc[mi][ni][1] * r1);
+            *reinterpret_cast<double2*>(Kb + (size_t)row * ld + col) =
+                make_double2(acc[mi][ni][0] * r0, acc[mi][ni][1] * r1);
         }
     }
+}
+
+__device__ __forceinline__ void ldlt_panel_body(double* sm, int b, int tile, int ld,
+                                                const int32_t* __restrict__ Nvec, int Nfixed, int k,
+                                                double* __restrict__ K, const double* __restrict__ dvec) {
+    const int Np = padded_order(Nvec, Nfixed, b, ld);
+    const int j0 = k * NB;
+    const int i0 = j0 + NB + tile * TM;
+    if (i0 >= Np) return;
+    double* Kb = K + (size_t)b * ld * ld;
+    const double* db = dvec + (size_t)b * ld;
+    if (Np - i0 >= TM) ldlt_panel_tile<128>(sm, i0, j0, ld, Kb, db);
+    else ldlt_panel_tile<64>(sm, i0, j0, ld, Kb, db);   // odd remainder block: Np - i0 == 64
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch wrappers.  `fused` interleaves, per matrix, the diag role of block column k+1 (blockIdx.x == 0) with
+// the panel tiles 1.. of block column k: the latency-bound factor / inverse phases of the diagonal block then
+// share an SM with a DMMA-bound panel CTA instead of idling the GPU between launches (look-ahead).
+__global__ void __launch_bounds__(256, 3) ldlt_diag_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k,
+                                                        double* __restrict__ K, double* __restrict__ dvec,
+                                                        int32_t* __restrict__ info, int32_t* __restrict__ nneg,
+                                                        const int32_t* __restrict__ npos_expected, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    ldlt_diag_body(sm, b, ld, Nvec, Nfixed, k, K, dvec, info, nneg, npos_expected);
+}
+
+__global__ void __launch_bounds__(256, 2) ldlt_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                            int k, int tile0, double* __restrict__ K,
+                                                            const double* __restrict__ dvec, GfWork work) {
+    const int b = gf_instance(work, blockIdx.y);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    ldlt_panel_body(sm, b, tile0 + blockIdx.x, ld, Nvec, Nfixed, k, K, dvec);
+}
+
+__global__ void __launch_bounds__(256, 2) ldlt_fused_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                            int k, double* __restrict__ K, double* __restrict__ dvec,
+                                                            int32_t* __restrict__ info, int32_t* __restrict__ nneg,
+                                                            const int32_t* __restrict__ npos_expected, GfWork work) {
+    const int b = gf_instance(work, blockIdx.y);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    if (blockIdx.x == 0) ldlt_diag_body(sm, b, ld, Nvec, Nfixed, k + 1, K, dvec, info, nneg, npos_expected);
+    else ldlt_panel_body(sm, b, blockIdx.x, ld, Nvec, Nfixed, k, K, dvec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -536,15 +578,18 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
     GfWork w{work, nwork_dev};
     const int Np = ((Nmax + NB - 1) / NB) * NB;
     const int nblk = Np / NB;
+    constexpr int FUSED_SMEM = PN_SMEM > DG_SMEM ? PN_SMEM : DG_SMEM;
     cudaFuncSetAttribute(ldlt_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
     cudaFuncSetAttribute(ldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PN_SMEM);
-    for (int k = 0; k < nblk; k++) {
+    cudaFuncSetAttribute(ldlt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+    ldlt_diag_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, 0, K, dvec, info, nneg, npos_expected, w);
+    for (int k = 0; k + 1 < nblk; k++) {
         const int j0 = k * NB;
-        ldlt_diag_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg, npos_expected, w);
-        if (j0 + NB < Np) {
-            dim3 grid((Np - j0 - NB + TM - 1) / TM, nwork);
-            ldlt_panel_kernel<<<grid, 256, PN_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, w);
-        }
+        const int tiles = (Np - j0 - NB + TM - 1) / TM;  // >= 1
+        // tile 0 holds the rows diag(k+1) needs; everything else of panel(k) runs beside diag(k+1)
+        ldlt_panel_kernel<<<dim3(1, nwork), 256, PN_SMEM, s>>>(ld, Nvec, Nmax, k, 0, K, dvec, w);
+        ldlt_fused_kernel<<<dim3(tiles, nwork), 256, FUSED_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
+                                                                      npos_expected, w);
     }
     return gf_launch_status();
 }
