@@ -33,7 +33,7 @@ CPU_SAMPLE = 128
 # ----------------------------------------------------------------------------------------------- data
 def make_batch_torch(B, n, m, device, seed):
     """cfg3 generator with the torch CUDA generator: H = sym(MM'/n) + 0.1 I, A ~ N(0,1),
-    b = -A x_f, g = 0.3 N(0,1), bounds [-1, 1]; state x = clip(1.3 U(-1,1)), y = 0.1 N(0,1)."""
+    b = -A x_f, g = 0.3 N(0,1), bounds [-1, 1]."""
     import torch
 
     gen = torch.Generator(device=device)
@@ -52,9 +52,7 @@ def make_batch_torch(B, n, m, device, seed):
     g = 0.3 * torch.randn((B, n), generator=gen, **f64)
     lb = torch.full((B, n), -1.0, **f64)
     ub = torch.full((B, n), 1.0, **f64)
-    x = torch.clamp(1.3 * (2 * torch.rand((B, n), generator=gen, **f64) - 1), -1.0, 1.0)
-    y = 0.1 * torch.randn((B, m), generator=gen, **f64)
-    return dict(H=H, A=A, g=g, b=b, lb=lb, ub=ub, x=x, y=y)
+    return dict(H=H, A=A, g=g, b=b, lb=lb, ub=ub)
 
 
 def make_sample_numpy(S, n, m):
@@ -63,8 +61,10 @@ def make_sample_numpy(S, n, m):
 
     d = synth.qp_batch(range(S), n, m)
     rng = np.random.default_rng(7)
-    d["x"] = np.clip(1.3 * rng.uniform(-1, 1, (S, n)), -1.0, 1.0)
+    d["x"] = np.clip(0.3 * rng.uniform(-1, 1, (S, n)), -1.0, 1.0)
     d["y"] = 0.1 * rng.standard_normal((S, m))
+    d["lamb"] = np.full(S, LAMB)
+    d["rho"] = np.full(S, RHO)
     return d
 
 
@@ -75,16 +75,17 @@ def _cpu_step(args):
 
     from oracle import gradflow_oracle as orc
 
-    H, A, g, b, lb, ub, x, y = args
+    H, A, g, b, lb, ub, x, y, lamb, rho = args
     with threadpool_limits(limits=1):
         t0 = time.perf_counter()
         prob = orc.DenseQP(H, A, g, b, lb, ub)
         prm = orc.OracleParams(newton_type="full", linear_solver="splu")
         it = orc.Iterate(prob, prm, x, y)
-        dt = 1.0 / LAMB
-        res = orc.newton_method(prob, prm, it, dt, RHO).step(it)
+        dt = 1.0 / float(np.asarray(lamb).reshape(()))
+        rho = float(np.asarray(rho).reshape(()))
+        res = orc.newton_method(prob, prm, it, dt, rho).step(it)
         nxt = res.iterate
-        fn = float(np.linalg.norm(orc.ImplicitFunc(prob, it, dt).value_at(nxt, RHO)))
+        fn = float(np.linalg.norm(orc.ImplicitFunc(prob, it, dt).value_at(nxt, rho)))
         t1 = time.perf_counter()
     return nxt.x, nxt.y, res.diff, fn, t1 - t0
 
@@ -95,7 +96,7 @@ def cpu_steps(sample, cores):
     import multiprocessing as mp
 
     S = sample["x"].shape[0]
-    tasks = [tuple(np.ascontiguousarray(sample[k][i]) for k in ("H", "A", "g", "b", "lb", "ub", "x", "y"))
+    tasks = [tuple(np.ascontiguousarray(sample[k][i]) for k in ("H", "A", "g", "b", "lb", "ub", "x", "y", "lamb", "rho"))
              for i in range(S)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
@@ -246,8 +247,21 @@ def run_gpu_arm(args):
     f64 = dict(dtype=torch.float64, device=device)
     lamb = torch.full((B,), LAMB, **f64)
     rho = torch.full((B,), RHO, **f64)
-    x, y = data["x"], data["y"]
     linear = LinearSolverType[args.linear]
+    # State of the timed step: every instance's iterate after `--state-iters` outer iterations of the batched
+    # solver from the cfg3 start (x0 = 0, y0 = 0, default Params) -- a mid-solve point with its own lambda, rho and
+    # a developed active set -- instead of an arbitrary random point.
+    from pygradflow_b200.params import Params
+    from pygradflow_b200.solver import BatchedSolver
+
+    bs = BatchedSolver(prob, Params(linear_solver_type=linear))
+    bs.solve(None, None, max_outer=args.state_iters)
+    x, y = bs.cur[0].clone(), bs.cur[1].clone()
+    lamb, rho = bs.lamb.clone(), bs.rho.clone()
+    running = int((bs.status == 0).sum().item())
+    del bs
+    torch.cuda.empty_cache()
+    data["x"], data["y"] = x, y
     stepper = NewtonKKTStepper(prob, linear)
 
     def barrier():
@@ -327,6 +341,7 @@ def run_gpu_arm(args):
         cores = host_cores()
         S = CPU_SAMPLE
         sample = {k: data[k][:S].cpu().numpy() for k in ("H", "A", "g", "b", "lb", "ub", "x", "y")}
+        sample["lamb"], sample["rho"] = lamb[:S].cpu().numpy(), rho[:S].cpu().numpy()
         res, wall = cpu_steps(sample, cores)
         cpu_value = S / wall
         xr = np.stack([r[0] for r in res])
@@ -353,9 +368,11 @@ def run_gpu_arm(args):
         nIbar = float(eng.nI.to(torch.float64).mean().item())
         Nbar = float(Nvec.mean().item())
         # algorithmic HBM bytes of the HBM-bound phases, per batched step
-        asm_bytes = float(((eng.nI.double() ** 2 + m * eng.nI.double()) * 8 + n + (Nvec ** 2) * 4).sum().item()) \
-            if linear != LinearSolverType.LU else \
-            float(((eng.nI.double() ** 2 + m * eng.nI.double()) * 8 + n + (Nvec ** 2) * 8).sum().item())
+        nId = eng.nI.double()
+        if eng.linear == LinearSolverType.LDLT:  # lower triangle only: half of H_II read, half of K written
+            asm_bytes = float(((nId ** 2 / 2 + m * nId) * 8 + n + (Nvec ** 2) * 4).sum().item())
+        else:
+            asm_bytes = float(((nId ** 2 + m * nId) * 8 + n + (Nvec ** 2) * 8).sum().item())
         solve_bytes = float(((Nvec ** 2) * 8 + 16 * Nvec).sum().item())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -364,12 +381,14 @@ def run_gpu_arm(args):
             "config": {"workload": "cfg3: batch of 4096 random dense convex QPs n=512 m=256 per GPU, equality + "
                                    "bound constraints (active-set KKT); one full Newton-KKT step per instance per "
                                    "step", "n": n, "m": m, "batch_per_gpu": B, "global_batch": B * world,
-                       "lamb": LAMB, "rho": RHO, "linear_solver": eng.linear.name,
+                       "state": f"iterates after {args.state_iters} outer iterations of the batched solver from x0=0, "
+                                f"y0=0 (per-instance lambda, rho); {running} of {B} instances still running",
+                       "linear_solver": eng.linear.name,
                        "mean_inactive": nIbar, "mean_kkt_order": Nbar, "lu_fallback_instances": n_fallback,
                        "failed_instances": nfail,
                        "l2": "inputs (13 GB of H, A per step) are far larger than the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "tensor", "kernel": "batched LDL' factorisation (ldlt_update_kernel DMMA + "
-                                                      "ldlt_diag_kernel + ldlt_trsm_kernel)",
+            "roofline": {"bound": "tensor", "kernel": "batched LDL' factorisation = gf_ldlt_factor: ldlt_panel_kernel + "
+                                                      "ldlt_fused_kernel (DMMA) + ldlt_diag_kernel",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "FP64 cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no "
@@ -406,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--linear", default="Auto", choices=["Auto", "LU", "LDLT"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--state-iters", type=int, default=6, help="outer iterations run to reach the timed state")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
