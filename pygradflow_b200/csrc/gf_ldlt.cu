@@ -303,7 +303,7 @@ __device__ __forceinline__ void ldlt_diag_body(double* sm, int b, int ld, const 
 constexpr int TM = 128, TN = 64, STAGES = 2;
 constexpr int PKC = 32;        // k-chunk per pipeline stage of the panel kernel
 constexpr int PSP = PKC + 4;   // its smem row pitch (== 4 mod 16: conflict-free fragment loads)
-constexpr int PN_SMEM_PIPE = STAGES * (TM + TN) * PSP * (int)sizeof(double);
+constexpr int PN_SMEM_PIPE = (STAGES * (TM + TN) * PSP + STAGES * PKC) * (int)sizeof(double);
 constexpr int PN_SMEM_EPI = (TM + TN) * EP * (int)sizeof(double);
 constexpr int PN_SMEM = PN_SMEM_PIPE > PN_SMEM_EPI ? PN_SMEM_PIPE : PN_SMEM_EPI;
 
@@ -318,13 +318,14 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     constexpr int AT = ROWS / 16;               // 16-byte pieces per thread per stage for the A rows
     double* As = sm;                            // STAGES x TM x PSP (ROWS rows used)
     double* Bs = sm + STAGES * TM * PSP;        // STAGES x TN x PSP
+    double* Ds = Bs + STAGES * TN * PSP;        // STAGES x PKC : d of the chunk
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm = wid / WN, wn = wid % WN;
     const int g = lane >> 2, q = lane & 3;
     const int nchunks = j0 / PKC;
 
     // Each thread copies one 16-byte piece of AT A rows and 4 B rows per stage: row = (tid >> 4) + 16 t,
-    // piece = tid & 15; pointers advance by constants.
+    // piece = tid & 15; pointers advance by constants.  Threads 0..15 also copy the chunk's 32 pivots.
     const int lrow = tid >> 4, lpart = (tid & 15) * 2;
     const double* gA = Kb + (size_t)(i0 + lrow) * ld + lpart;
     const double* gB = Kb + (size_t)(j0 + lrow) * ld + lpart;
@@ -340,6 +341,7 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
         for (int t = 0; t < AT; t++) cp_async16(sa + t * 16 * PSP, ga + t * gstride);
 #pragma unroll
         for (int t = 0; t < 4; t++) cp_async16(sb + t * 16 * PSP, gb + t * gstride);
+        if (tid < PKC / 2) cp_async16(Ds + stage * PKC + tid * 2, db + chunk * PKC + tid * 2);
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
@@ -358,10 +360,6 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
             acc[mi][ni][1] = v.y;
         }
     }
-    // -d of the first chunk; every later chunk's values are fetched one chunk ahead
-    double nd[PKC / 4];
-#pragma unroll
-    for (int u = 0; u < PKC / 4; u++) nd[u] = (nchunks > 0) ? -__ldg(db + 4 * u + q) : 0.0;
     for (int c = 0; c < nchunks; c++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -370,23 +368,38 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
         cp_async_commit();
         const double* as = As + (c % STAGES) * TM * PSP + (wm * 32 + g) * PSP + q;
         const double* bs = Bs + (c % STAGES) * TN * PSP + (wn * WC + g) * PSP + q;
-        double ndn[PKC / 4];
+        const double* ds = Ds + (c % STAGES) * PKC + q;
+        // software pipeline: the fragments of k-step kk+4 are fetched while the DMMAs of kk issue
+        double a[4], bf[NI], dcur;
 #pragma unroll
-        for (int u = 0; u < PKC / 4; u++) ndn[u] = (c + 1 < nchunks) ? -__ldg(db + (c + 1) * PKC + 4 * u + q) : 0.0;
+        for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * PSP];
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++) bf[ni] = bs[ni * 8 * PSP];
+        dcur = ds[0];
 #pragma unroll
         for (int kk = 0; kk < PKC; kk += 4) {
-            double a[4], bf[NI];
+            double an[4], bn[NI], dn = 0.0;
+            if (kk + 4 < PKC) {
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * PSP + kk] * nd[kk / 4];
+                for (int mi = 0; mi < 4; mi++) an[mi] = as[mi * 8 * PSP + kk + 4];
 #pragma unroll
-            for (int ni = 0; ni < NI; ni++) bf[ni] = bs[ni * 8 * PSP + kk];
+                for (int ni = 0; ni < NI; ni++) bn[ni] = bs[ni * 8 * PSP + kk + 4];
+                dn = ds[kk + 4];
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] *= -dcur;
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
-        }
+            if (kk + 4 < PKC) {
 #pragma unroll
-        for (int u = 0; u < PKC / 4; u++) nd[u] = ndn[u];
+                for (int mi = 0; mi < 4; mi++) a[mi] = an[mi];
+#pragma unroll
+                for (int ni = 0; ni < NI; ni++) bf[ni] = bn[ni];
+                dcur = dn;
+            }
+        }
     }
     cp_async_wait<0>();
     __syncthreads();  // every warp is done with the pipeline buffers
