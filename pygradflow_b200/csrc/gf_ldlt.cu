@@ -41,6 +41,7 @@ __device__ __forceinline__ void smem_neg_matmul(double* dst, int ldd, const doub
     for (int e = threadIdx.x; e < M * N; e += blockDim.x) {
         const int r = e / N, c = e - r * N;
         double acc = 0.0;
+#pragma unroll 8
         for (int p = 0; p < Kd; p++) acc = fma(A[r * lda + p], Bm[p * ldb + c], acc);
         dst[r * ldd + c] = -acc;
     }
@@ -195,6 +196,7 @@ __device__ __forceinline__ void ldlt_diag_body(double* sm, int b, int ld, const 
                 }
                 const int cbeg = jb + BW;
                 const int cstart = cbeg + ((cg - cbeg) & 3);
+#pragma unroll 4
                 for (int c = cstart; c <= i; c += 4) {
                     double acc = S[i][c];
 #pragma unroll
@@ -260,7 +262,8 @@ __device__ __forceinline__ void ldlt_diag_body(double* sm, int b, int ld, const 
         for (int e = tid; e < 16 * 16; e += blockDim.x) {  // T = L10 * X00
             const int r = e >> 4, c = e & 15;
             double acc = 0.0;
-            for (int p = c; p < 16; p++) acc = fma(S[h + 16 + r][h + p], X[(h + p) * XP + h + c], acc);
+#pragma unroll
+            for (int p = 0; p < 16; p++) acc = fma(S[h + 16 + r][h + p], X[(h + p) * XP + h + c], acc);
             T[r * 33 + c] = acc;
         }
         __syncthreads();
@@ -271,7 +274,8 @@ __device__ __forceinline__ void ldlt_diag_body(double* sm, int b, int ld, const 
     for (int e = tid; e < 32 * 32; e += blockDim.x) {
         const int r = e >> 5, c = e & 31;
         double acc = 0.0;
-        for (int p = c; p < 32; p++) acc = fma(S[32 + r][p], X[p * XP + c], acc);
+#pragma unroll 8
+        for (int p = 0; p < 32; p++) acc = fma(S[32 + r][p], X[p * XP + c], acc);
         T[r * 33 + c] = acc;
     }
     __syncthreads();
@@ -601,8 +605,12 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
         const int tiles = (Np - j0 - NB + TM - 1) / TM;  // >= 1
         // tile 0 holds the rows diag(k+1) needs; everything else of panel(k) runs beside diag(k+1)
         ldlt_panel_kernel<<<dim3(1, nwork), 256, PN_SMEM, s>>>(ld, Nvec, Nmax, k, 0, K, dvec, w);
-        ldlt_fused_kernel<<<dim3(tiles, nwork), 256, FUSED_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
-                                                                      npos_expected, w);
+        if (tiles > 1)
+            ldlt_fused_kernel<<<dim3(tiles, nwork), 256, FUSED_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
+                                                                          npos_expected, w);
+        else  // nothing to interleave with: the standalone diag kernel fits three CTAs per SM
+            ldlt_diag_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, k + 1, K, dvec, info, nneg, npos_expected,
+                                                         w);
     }
     return gf_launch_status();
 }
