@@ -170,6 +170,27 @@ int gf_commit(int B, int n, int m, const int32_t* phase, const double* lamb_next
               const double* of, double* x, double* y, double* grad, double* cons, double* obj, double* lamb,
               double* rho, int32_t* iters, int32_t* accepted, int32_t* status, void* stream);
 
+/* ---- globalized Newton (newton.py:242-304): merit gradient, trial point, fused residual-norm + Armijo ---- */
+
+/* res = 1/2 |F|^2 and inner = (F'^T F) . (dx, dy) (newton.py:254,262-271) without assembling F'
+ * (implicit_func.py:254-294): H is the Hessian of the Lagrangian at multiplier y + rho c, F the scaled residual at
+ * the current iterate, `active` its active set. */
+int gf_merit_grad(int B, int n, int m, const double* H, const double* J, const double* F, const uint8_t* active,
+                  const double* dt, const double* rho, const double* dx, const double* dy, double* res, double* inner,
+                  const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+/* xt = x - alpha dx, yt = y - alpha dy (newton.py:276-278) */
+int gf_ls_trial(int B, int n, int m, const double* x, const double* y, const double* dx, const double* dy,
+                const double* alpha, double* xt, double* yt, const int32_t* work, const int32_t* nwork_dev, int nwork,
+                void* stream);
+/* Scaled residual at the trial point, 1/2 |F|^2 (warp-shuffle reduction) and the Armijo test / step halving of
+ * newton.py:280-290 in one kernel.  state[B]: 0 searching, 1 accepted at alpha[B], 2 exhausted after max_trials
+ * (newton.py:294 raises). */
+int gf_armijo_residual(int B, int n, int m, const double* xt, const double* yt, const double* x0, const double* y0,
+                       const double* dL, const double* cons, const double* lb, const double* ub, const double* dt,
+                       const double* res, const double* inner, double newton_tol, int max_trials, double* alpha,
+                       int32_t* trials, int32_t* state, double* next_res, const int32_t* work,
+                       const int32_t* nwork_dev, int nwork, void* stream);
+
 /* helpers of the batched driver: ordered compaction of { b in parent (or 0..B-1) : (lo <= key[b] <= hi) != invert } */
 int gf_build_worklist(int B, const int32_t* key, int lo, int hi, int invert, const int32_t* parent,
                       const int32_t* parent_count, int32_t* list, int32_t* count, void* stream);

@@ -166,3 +166,25 @@ def build_worklist(key, lo: int, hi: int, out: WorkList, parent: Optional[WorkLi
 
 def dt_from_lamb(lamb, dt):
     _call("gf_dt_from_lamb", lamb.shape[0], ptr(lamb), ptr(dt), _stream())
+
+
+def merit_grad(H, J, F, active, dt, rho, dx, dy, res, inner, work: WorkList):
+    B, n, _ = H.shape
+    m = 0 if J is None else J.shape[1]
+    _call("gf_merit_grad", B, n, m, ptr(H), ptr(J), ptr(F), ptr(active), ptr(dt), ptr(rho), ptr(dx), ptr(dy),
+          ptr(res), ptr(inner), *_w(work))
+
+
+def ls_trial(x, y, dx, dy, alpha, xt, yt, work: WorkList):
+    B, n = x.shape
+    m = 0 if y is None else y.shape[1]
+    _call("gf_ls_trial", B, n, m, ptr(x), ptr(y), ptr(dx), ptr(dy), ptr(alpha), ptr(xt), ptr(yt), *_w(work))
+
+
+def armijo_residual(xt, yt, x0, y0, dL, cons, lb, ub, dt, res, inner, newton_tol, max_trials, alpha, trials, state,
+                    next_res, work: WorkList):
+    B, n = xt.shape
+    m = 0 if yt is None else yt.shape[1]
+    _call("gf_armijo_residual", B, n, m, ptr(xt), ptr(yt), ptr(x0), ptr(y0), ptr(dL), ptr(cons), ptr(lb), ptr(ub),
+          ptr(dt), ptr(res), ptr(inner), newton_tol, max_trials, ptr(alpha), ptr(trials), ptr(state), ptr(next_res),
+          *_w(work))

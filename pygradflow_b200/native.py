@@ -37,6 +37,9 @@ SIGNATURES = {
     "gf_dr_first": [_I, _P, _P, _P, _P, _P, _D, _D, _D, _P, _P, _P],
     "gf_dr_second": [_I, _P, _P, _P, _D, _D, _D, _D, _D, _D, _P, _P, _P, _P, _P],
     "gf_commit": [_I, _I, _I, _P, _P, _D, _I] + [_P] * 10 + [_P] * 10 + [_P],
+    "gf_merit_grad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_ls_trial": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_armijo_residual": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P] + _WORK,
     "gf_build_worklist": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "gf_dt_from_lamb": [_I, _P, _P, _P],
 }
