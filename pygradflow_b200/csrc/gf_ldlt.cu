@@ -9,24 +9,48 @@
 //
 // Layout: K[b] ld x ld row-major, only the lower triangle is read; the matrix is padded with an identity
 // block up to Np = roundup(N_b, 64) (gf_kkt_assemble does this) so no kernel has edge tiles inside a
-// 64-block.  d is kept on the diagonal of K and, contiguously, in dvec[b].  The strict upper triangle of
-// every 64x64 DIAGONAL block is scratch: it receives inv(L_kk)' for the panel kernel.
+// 64-block.  d is kept on the diagonal of K and, contiguously, in dvec[b].  The upper triangle of K is scratch:
+// the strict upper triangle of every 64x64 DIAGONAL block receives inv(L_kk)' for the triangular solves, and the
+// off-diagonal block (p, i), p < i, receives the block W'[i,p] = -(L[i,p] D_p) (not transposed), so the update
+// product sum_p W'[i,p] L[k,p]' needs no scaling inside the DMMA loop (a DMUL in that loop shares the FP64
+// pipe with the DMMAs and costs 8 % of its throughput, tools/dmma_loop_bench.cu).
 //
-// Left-looking by 64-wide block columns, two batched launches per block column k (j0 = 64 k):
-//   diag(k)   C = A[k,k] - sum_{p<k} (L[k,p] D_p) L[k,p]'  (DMMA, cp.async pipeline), then in shared memory
-//             C = L_kk D_k L_kk' and X = inv(L_kk) (blocked 16/32/64), one CTA per matrix;
-//   panel(k)  128x64 tiles below the diagonal: C = A[i,k] - sum_{p<k} (L[i,p] D_p) L[k,p]'  (DMMA),
-//             then the triangular solve as one more DMMA product L[i,k] = (C X') D_k^{-1}.
+// Left-looking by 64-wide block columns, ONE batched launch per block column k (j0 = 64 k) after the first
+// diagonal block; per matrix the launch has
+//   chain CTA   the 64 x 128 tile [ A[k+1,k] | A[k+1,k+1] ] minus the contributions of the block columns to
+//               its left in one DMMA main loop (the rows of block k+1 are both the A operand and the B operand of
+//               the diagonal tile, so it costs no extra loads), the triangular solve of L[k+1,k], the last
+//               rank-64 update of the diagonal tile, and then in shared memory C = L D L' and X = inv(L)
+//               (blocked 16/32/64) of diagonal block k+1  -- the critical path of the factorisation;
+//   panel CTAs  128x64 tiles further below: C = A[i,k] - sum_{p<k} (L[i,p] D_p) L[k,p]'  (DMMA), then the
+//               triangular solve as one more DMMA product L[i,k] = (C X') D_k^{-1}.
 // Every matrix entry is read and written once, operands stream once per block column
 // (~ 8 N^3 / (6*64) bytes per matrix), so the factorisation is bound by the FP64 pipe, not by HBM.
 #include "gf_common.cuh"
 #include "../../include/gradflow_b200.h"
 
+#ifdef GF_LDLT_TRACE
+// Developer instrumentation (tools/ldlt_trace.cu): per block column / CTA role, cycles spent per phase.
+__device__ unsigned long long g_ldlt_trace[64 * 2 * 16];
+#define TRACE_BEGIN(kk, role) long long t_prev_ = clock64(); const int t_slot_ = ((kk) * 2 + (role)) * 16;
+#define TRACE_MARK(i)                                                                    \
+    do {                                                                                 \
+        if (threadIdx.x == 0) {                                                          \
+            const long long t_now_ = clock64();                                          \
+            atomicAdd(&g_ldlt_trace[t_slot_ + (i)], (unsigned long long)(t_now_ - t_prev_)); \
+            t_prev_ = t_now_;                                                            \
+        }                                                                                \
+    } while (0)
+#define TRACE_COUNT() do { if (threadIdx.x == 0) atomicAdd(&g_ldlt_trace[t_slot_ + 15], 1ULL); } while (0)
+#else
+#define TRACE_BEGIN(kk, role)
+#define TRACE_MARK(i)
+#define TRACE_COUNT()
+#endif
+
 namespace {
 
 constexpr int NB = 64;
-constexpr int KC = 16;       // k-chunk per pipeline stage
-constexpr int SP = KC + 4;   // smem row pitch of a stage (bank-conflict-free DMMA fragment loads)
 constexpr int EP = NB + 4;   // smem row pitch of 64-wide tiles in the epilogues (same property)
 
 __device__ __forceinline__ int padded_order(const int32_t* Nvec, int Nfixed, int b, int ld) {
@@ -35,260 +59,201 @@ __device__ __forceinline__ int padded_order(const int32_t* Nvec, int Nfixed, int
     return Np < ld ? Np : ld;
 }
 
-// dst (M x N, pitch ldd) = -A (M x Kd, pitch lda) * Bm (Kd x N, pitch ldb), all in shared memory.
-__device__ __forceinline__ void smem_neg_matmul(double* dst, int ldd, const double* A, int lda, const double* Bm,
-                                                int ldb, int M, int N, int Kd) {
-    for (int e = threadIdx.x; e < M * N; e += blockDim.x) {
-        const int r = e / N, c = e - r * N;
-        double acc = 0.0;
-#pragma unroll 8
-        for (int p = 0; p < Kd; p++) acc = fma(A[r * lda + p], Bm[p * ldb + c], acc);
-        dst[r * ldd + c] = -acc;
-    }
+// Sign flip on the integer pipe (the FP64 pipe is the contended resource here).
+__device__ __forceinline__ double dneg(double x) {
+    return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ULL);
+}
+
+// 1 / d to ~1 ulp: MUFU seed + two Newton steps (4 dependent DFMAs; __drcp_rn is about twice as long, and this sits
+// on the pivot-to-pivot critical path of the factorisation).  d == 0 gives 0: the pivot is flagged separately.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return d != 0.0 ? r : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int DG_STAGES = 3;
-constexpr int DG_BW = 4;  // panel width of the in-shared-memory factorisation
-constexpr int XP = NB + 1;  // pitch of the inverse in shared memory
-constexpr int DG_OPS = (DG_STAGES * NB * SP > NB * XP) ? DG_STAGES * NB * SP : NB * XP;
-constexpr int DG_SMEM = (NB * (NB + 1) + DG_OPS + NB + 32 * 33 + NB * (DG_BW + 1) + 2) * (int)sizeof(double);
+// Diagonal block: S = L D L' and X = inv(L) for a 64 x 64 tile in shared memory.
+//
+// The FP64 FMA pipe is shared with the DMMAs of the CTA next door, so every dependent scalar FP64 instruction
+// here waits behind 16-cycle DMMAs.  The scheme therefore keeps scalar FP64 work to the unavoidable pivot
+// chain and does everything else as DMMA products:
+//   * 8 panels of 8 columns.  Warp 0 holds the 8 x 8 pivot block in registers (DMMA C layout: lane (g, q) owns
+//     P[g][2q], P[g][2q+1]) and eliminates it with warp shuffles: per pivot one reciprocal, one scale, and
+//     rank-1 updates of P and of Y = inv(L_pivot) -- 10 FP64 warp instructions;
+//   * panel below the pivot block: W = S_panel Y' (2 DMMAs per 8 rows), L = W D^{-1};
+//   * trailing update S += (-W) L' by 8 x 8 tiles (2 DMMAs each), the next pivot block first, by warp 0, which
+//     keeps it in registers and goes straight on to eliminate it while the other warps finish the update;
+//   * X = inv(L) from the Y blocks by block recursion 8 -> 16 -> 32 -> 64 (DMMA products).
+constexpr int DP = NB + 4;                   // pitch of S and X (== 4 mod 16: conflict-free DMMA fragment loads)
+constexpr int WNP = 12;                      // pitch of the -W panel (64 x 8)
+constexpr int TP = 36;                       // pitch of the 32 x 32 product scratch
+constexpr int DG_S = NB * DP;                // S: 64 x 68
+constexpr int DG_OPS = NB * DP;              // X = inv(L): 64 x 68
+constexpr int DG_MISC = NB * WNP + 32 * TP + NB + 2;  // -W panel, product scratch, 1/d, flags
+constexpr int DG_SMEM = (DG_S + DG_OPS + DG_MISC) * (int)sizeof(double);
 
-__device__ __forceinline__ void ldlt_diag_body(double* sm, int b, int ld, const int32_t* __restrict__ Nvec,
-                                               int Nfixed, int k, double* __restrict__ K,
-                                               double* __restrict__ dvec, int32_t* __restrict__ info,
-                                               int32_t* __restrict__ nneg,
-                                               const int32_t* __restrict__ npos_expected) {
-    const int Np = padded_order(Nvec, Nfixed, b, ld);
+// For every pair h < npair (o = 2 bs h): Out_h (bs x bs, at Out + oo_h) = +-A_h (at A + ao_h) * B_h (at Bm + bo_h), by
+// 8 x 8 output tiles round-robin over the 8 warps.  Offsets: *_row / *_col multiples of o plus constants.
+struct PairOperand {
+    double* base;
+    int pitch;
+    int pair_stride;  // offset between consecutive pairs
+};
+__device__ __forceinline__ void smem_pair_products(PairOperand Out, PairOperand A, PairOperand Bm, int npair, int tb,
+                                                   bool negate) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int per = tb * tb;
+    for (int e = wid; e < npair * per; e += 8) {
+        const int h = e / per, r = e - h * per, ti = r / tb, tj = r - ti * tb;
+        double c0 = 0.0, c1 = 0.0;
+        const double* ap = A.base + h * A.pair_stride + (ti * 8 + g) * A.pitch + q;
+        const double* bp = Bm.base + h * Bm.pair_stride + q * Bm.pitch + tj * 8 + g;
+        for (int kk = 0; kk < tb * 8; kk += 4) dmma884(c0, c1, ap[kk], bp[kk * Bm.pitch]);
+        if (negate) { c0 = dneg(c0); c1 = dneg(c1); }
+        *reinterpret_cast<double2*>(Out.base + h * Out.pair_stride + (ti * 8 + g) * Out.pitch + tj * 8 + 2 * q) =
+            make_double2(c0, c1);
+    }
+}
+
+// Factorise the updated diagonal tile of block k, held in shared memory S[64][DP] (lower triangle valid):
+// S = L D L', X = inv(L); writes L / d / inv(L)' to K, d to dvec, pivot diagnostics to info / nneg.
+// Xp (DG_OPS doubles) and misc (DG_MISC doubles) are scratch regions disjoint from S.
+__device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* misc, int b, int ld,
+                                                 const int32_t* __restrict__ Nvec, int Nfixed, int k,
+                                                 double* __restrict__ K, double* __restrict__ dvec,
+                                                 int32_t* __restrict__ info, int32_t* __restrict__ nneg,
+                                                 const int32_t* __restrict__ npos_expected) {
     const int j0 = k * NB;
-    if (j0 >= Np) return;
-    double(*S)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);   // 64 x 65
-    double* Ops = sm + NB * (NB + 1);                                 // DG_STAGES x 64 x SP, later X = inv(L)
-    double* rinv = Ops + DG_OPS;                                      // 64
-    double* T = rinv + NB;                                            // 32 x 33
-    double* Wp = T + 32 * 33;                                         // 64 x (DG_BW + 1): W = L D of the current panel
-    int* flags = reinterpret_cast<int*>(Wp + NB * (DG_BW + 1));
+    double* Wn = misc;                       // 64 x WNP : -W of the current panel
+    double* T = Wn + NB * WNP;               // 32 x TP
+    double* rinv = T + 32 * TP;              // 64
+    int* flags = reinterpret_cast<int*>(rinv + NB);
     int& s_bad = flags[0];
     int& s_neg = flags[1];
     int& s_sign = flags[2];
     double* Kb = K + (size_t)b * ld * ld;
-    const double* db = dvec + (size_t)b * ld;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    const int npos = npos_expected != nullptr ? npos_expected[b] : -1;
     if (tid == 0) { s_bad = 0x7fffffff; s_neg = 0; s_sign = 0; }
+    for (int e = tid; e < NB * NB; e += 256) X[(e >> 6) * DP + (e & 63)] = 0.0;
+    TRACE_BEGIN(k, 0);
 
-    // ---- phase A: diagonal tile minus the contributions of the block columns to its left (DMMA)
-    {
-        const int wm = wid >> 1, wn = wid & 1;  // 4 x 2 warps, 16 x 32 each
-        const int g = lane >> 2, q = lane & 3;
-        const bool upper_quadrant = (wn == 1) && (wm < 2);  // rows 0..31 x cols 32..63: never read
-        double acc[2][4][2];
+    // ---- factorisation
+    double p0 = 0.0, p1 = 0.0;  // warp 0: pivot block, lane (g, q) owns P[g][2q], P[g][2q + 1]
+    if (wid == 0) {
+        const double2 v = *reinterpret_cast<const double2*>(S + g * DP + 2 * q);
+        p0 = v.x;
+        p1 = v.y;
+    }
+    __syncthreads();  // X zeroed, flags initialised
+    for (int jb = 0; jb < 8; jb++) {
+        const int c0 = jb * 8;
+        if (wid == 0) {
+            // eliminate the 8 x 8 pivot block in registers
+            double y0 = (2 * q == g) ? 1.0 : 0.0, y1 = (2 * q + 1 == g) ? 1.0 : 0.0;
+            double rc0 = 0.0, rc1 = 0.0;
 #pragma unroll
-        for (int mi = 0; mi < 2; mi++) {
-            const int row = j0 + wm * 16 + mi * 8 + g;
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
-                const int col = j0 + wn * 32 + ni * 8 + 2 * q;
-                const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)row * ld + col);
-                acc[mi][ni][0] = v.x;
-                acc[mi][ni][1] = v.y;
-            }
-        }
-        const int nchunks = j0 / KC;
-        auto load_stage = [&](int chunk, int stage) {
-            const int p0 = chunk * KC;
-            double* os = Ops + stage * NB * SP;
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                const int piece = tid + t * 256;  // 512 pieces of 16 B
-                const int r = piece >> 3, part = piece & 7;
-                cp_async16(os + r * SP + part * 2, Kb + (size_t)(j0 + r) * ld + p0 + part * 2);
-            }
-        };
-#pragma unroll
-        for (int s = 0; s < DG_STAGES - 1; s++) {
-            if (s < nchunks) load_stage(s, s);
-            cp_async_commit();
-        }
-        for (int c = 0; c < nchunks; c++) {
-            cp_async_wait<DG_STAGES - 2>();
-            __syncthreads();
-            const int nxt = c + DG_STAGES - 1;
-            if (nxt < nchunks) load_stage(nxt, nxt % DG_STAGES);
-            cp_async_commit();
-            const double* os = Ops + (c % DG_STAGES) * NB * SP;
-            const double* as = os + (wm * 16 + g) * SP + q;
-            const double* bs = os + (wn * 32 + g) * SP + q;
-            const double* dp = db + c * KC + q;
-#pragma unroll
-            for (int kk = 0; kk < KC; kk += 4) {
-                const double nd = -__ldg(dp + kk);
-                double a[2], bf[4];
-#pragma unroll
-                for (int mi = 0; mi < 2; mi++) a[mi] = as[mi * 8 * SP + kk] * nd;
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * SP + kk];
-                if (!upper_quadrant) {
-#pragma unroll
-                    for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                        for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+            for (int j = 0; j < 8; j++) {
+                const double pj = (j & 1) ? p1 : p0;
+                const double dj = __shfl_sync(0xffffffffu, pj, j * 4 + (j >> 1));
+                const double wr = __shfl_sync(0xffffffffu, pj, g * 4 + (j >> 1));
+                const double wc0 = __shfl_sync(0xffffffffu, pj, (2 * q) * 4 + (j >> 1));
+                const double wc1 = __shfl_sync(0xffffffffu, pj, (2 * q + 1) * 4 + (j >> 1));
+                const double yj0 = __shfl_sync(0xffffffffu, y0, j * 4 + q);
+                const double yj1 = __shfl_sync(0xffffffffu, y1, j * 4 + q);
+                const double rj = fast_rcp(dj);
+                if (j == 2 * q) rc0 = rj;
+                if (j == 2 * q + 1) rc1 = rj;
+                const double lr = wr * rj;
+                if (g > j) {
+                    if (2 * q > j) p0 = fma(-lr, wc0, p0);
+                    if (2 * q + 1 > j) p1 = fma(-lr, wc1, p1);
+                    y0 = fma(-lr, yj0, y0);
+                    y1 = fma(-lr, yj1, y1);
                 }
             }
-        }
-        cp_async_wait<0>();
-#pragma unroll
-        for (int mi = 0; mi < 2; mi++) {
-            const int r = wm * 16 + mi * 8 + g;
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
-                const int c = wn * 32 + ni * 8 + 2 * q;
-                S[r][c] = acc[mi][ni][0];
-                S[r][c + 1] = acc[mi][ni][1];
+            // pivots: diagnostics, d, 1/d
+            if ((g >> 1) == q) {
+                const double d = (g & 1) ? p1 : p0;
+                const int jl = c0 + g, j = j0 + jl;
+                if (!(isfinite(d)) || d == 0.0) atomicMin(&s_bad, jl + 1);
+                if (d < 0.0 && j < N) atomicAdd(&s_neg, 1);
+                // quasi-definite sign pattern: the first npos pivots positive, the remaining (up to N) negative
+                if (npos >= 0 && j < N && ((j < npos) != (d > 0.0))) s_sign = 1;
+                dvec[(size_t)b * ld + j] = d;
+                rinv[jl] = (g & 1) ? rc1 : rc0;
             }
+            // L (strict lower, scaled), d on the diagonal; Y = inv(L_pivot) into the diagonal block of X
+            const double l0 = (2 * q < g) ? p0 * rc0 : p0, l1 = (2 * q + 1 < g) ? p1 * rc1 : p1;
+            if (2 * q + 1 <= g) *reinterpret_cast<double2*>(S + (c0 + g) * DP + c0 + 2 * q) = make_double2(l0, l1);
+            else if (2 * q == g) S[(c0 + g) * DP + c0 + 2 * q] = l0;
+            *reinterpret_cast<double2*>(X + (c0 + g) * DP + c0 + 2 * q) = make_double2(y0, y1);
         }
-    }
-    __syncthreads();
-
-    // ---- phase B: C = L D L' in place, right-looking in panels of DG_BW columns on W = L D (scaled to L
-    // afterwards).  Every thread factors the small diagonal block redundantly in registers, so a panel
-    // costs two barriers instead of DG_BW.
-    {
-        const int i = tid & 63, cg = tid >> 6;
-        constexpr int BW = DG_BW;
-        for (int jb = 0; jb < NB; jb += BW) {
-            double Dg[BW][BW], rj[BW];
-#pragma unroll
-            for (int r = 0; r < BW; r++)
-#pragma unroll
-                for (int c = 0; c <= r; c++) Dg[r][c] = S[jb + r][jb + c];
-#pragma unroll
-            for (int j = 0; j < BW; j++) {
-                const double d = Dg[j][j];
-                rj[j] = (d != 0.0) ? __drcp_rn(d) : 0.0;
-#pragma unroll
-                for (int i2 = j + 1; i2 < BW; i2++) {
-                    const double l = Dg[i2][j] * rj[j];
-#pragma unroll
-                    for (int c = j + 1; c <= i2; c++) Dg[i2][c] = fma(-l, Dg[c][j], Dg[i2][c]);
-                }
+        __syncthreads();  // pivot block published; all trailing updates of the previous panel are done
+        if (jb == 7) break;
+        // panel below the pivot block: row tile t = jb + 1 + wid
+        {
+            const int t = jb + 1 + wid;
+            if (t < 8) {
+                const double* ap = S + (t * 8 + g) * DP + c0 + q;
+                const double* bp = X + (c0 + g) * DP + c0 + q;  // B[kk][n] = Y[n][kk]
+                double w0 = 0.0, w1 = 0.0;
+                const double a0 = ap[0], a1 = ap[4];
+                dmma884(w0, w1, a0, bp[0]);
+                dmma884(w0, w1, a1, bp[4]);
+                __syncwarp();
+                const double2 rv = *reinterpret_cast<const double2*>(rinv + c0 + 2 * q);
+                *reinterpret_cast<double2*>(S + (t * 8 + g) * DP + c0 + 2 * q) = make_double2(w0 * rv.x, w1 * rv.y);
+                *reinterpret_cast<double2*>(Wn + (t * 8 + g) * WNP + 2 * q) = make_double2(dneg(w0), dneg(w1));
             }
-            double l[BW], w[BW];
-            const bool below = i >= jb + BW;
-            if (below) {
-#pragma unroll
-                for (int c = 0; c < BW; c++) w[c] = S[i][jb + c];
-#pragma unroll
-                for (int c = 0; c < BW; c++) {
-#pragma unroll
-                    for (int p = 0; p < c; p++) w[c] = fma(-l[p], Dg[c][p], w[c]);
-                    l[c] = w[c] * rj[c];
-                }
-                if (cg == 0) {
-#pragma unroll
-                    for (int c = 0; c < BW; c++) Wp[i * (BW + 1) + c] = w[c];
-                }
-            }
-            __syncthreads();  // Wp complete; nobody reads S[., jb..jb+7] below this line any more
-            if (below) {
-                if (cg == 0) {
-#pragma unroll
-                    for (int c = 0; c < BW; c++) S[i][jb + c] = w[c];
-                }
-                const int cbeg = jb + BW;
-                const int cstart = cbeg + ((cg - cbeg) & 3);
-#pragma unroll 4
-                for (int c = cstart; c <= i; c += 4) {
-                    double acc = S[i][c];
-#pragma unroll
-                    for (int p = 0; p < BW; p++) acc = fma(-l[p], Wp[c * (BW + 1) + p], acc);
-                    S[i][c] = acc;
-                }
-            } else if (i >= jb && cg == 0) {
-                const int r = i - jb;
-#pragma unroll
-                for (int rr = 0; rr < BW; rr++)
-                    if (rr == r) {
-#pragma unroll
-                        for (int c = 0; c <= rr; c++) S[i][jb + c] = Dg[rr][c];
-                    }
-            }
-            __syncthreads();
-        }
-    }
-    if (tid < NB) {
-        const double d = S[tid][tid];
-        if (!(isfinite(d)) || d == 0.0) atomicMin(&s_bad, tid + 1);
-        const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
-        const int j = j0 + tid;
-        if (d < 0.0 && j < N) atomicAdd(&s_neg, 1);
-        // quasi-definite sign pattern: the first npos pivots positive, the remaining (up to N) negative
-        if (npos_expected != nullptr && j < N && ((j < npos_expected[b]) != (d > 0.0))) s_sign = 1;
-        dvec[(size_t)b * ld + j] = d;
-        rinv[tid] = 1.0 / d;
-    }
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += blockDim.x) {
-        const int r = e >> 6, c = e & 63;
-        if (c < r) S[r][c] *= rinv[c];  // W -> L
-    }
-    __syncthreads();
-
-    // ---- phase C: X = inv(L) (unit lower), blocked 16 -> 32 -> 64; X and the scratch T live in Ops
-    double* X = Ops;                    // 64 x XP
-    for (int e = tid; e < NB * NB; e += blockDim.x) {
-        const int r = e >> 6, c = e & 63;
-        X[r * XP + c] = (r == c) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    if (tid < NB) {  // the four 16x16 diagonal blocks, one thread per column
-        const int blk = tid >> 4, j = tid & 15, o = blk * 16;
-        double x[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) x[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int i = 1; i < 16; i++) {
-            double s = 0.0;
-#pragma unroll
-            for (int p = 0; p < i; p++) s = fma(S[o + i][o + p], x[p], s);
-            if (i > j) x[i] = -s;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++)
-            if (i > j) X[(o + i) * XP + o + j] = x[i];
-    }
-    __syncthreads();
-    // 32-level: X[h+16:h+32, h:h+16] = -X11' * (L10 * X00), h in {0, 32}
-    for (int h = 0; h < NB; h += 32) {
-        for (int e = tid; e < 16 * 16; e += blockDim.x) {  // T = L10 * X00
-            const int r = e >> 4, c = e & 15;
-            double acc = 0.0;
-#pragma unroll
-            for (int p = 0; p < 16; p++) acc = fma(S[h + 16 + r][h + p], X[(h + p) * XP + h + c], acc);
-            T[r * 33 + c] = acc;
         }
         __syncthreads();
-        smem_neg_matmul(X + (h + 16) * XP + h, XP, X + (h + 16) * XP + h + 16, XP, T, 33, 16, 16, 16);
+        // trailing update by 8 x 8 tiles (ti, tj), jb < tj <= ti < 8: warp 0 takes the next pivot block and keeps
+        // it in registers, warps 1..7 share the rest
+        {
+            const int m = 7 - jb;                      // tile rows / cols left
+            const int ntile = m * (m + 1) / 2;
+            for (int e = (wid == 0 ? 0 : wid); e < ntile; e += (wid == 0 ? ntile : 7)) {
+                // e -> (ti, tj) in row-major order of the lower triangle: e = ti' (ti' + 1) / 2 + tj'
+                int tr = 0;
+                while ((tr + 1) * (tr + 2) / 2 <= e) tr++;
+                const int tc = e - tr * (tr + 1) / 2;
+                const int ti = jb + 1 + tr, tj = jb + 1 + tc;
+                double* cp = S + (ti * 8 + g) * DP + tj * 8 + 2 * q;
+                double2 cv = *reinterpret_cast<const double2*>(cp);
+                const double* ap = Wn + (ti * 8 + g) * WNP + q;
+                const double* bp = S + (tj * 8 + g) * DP + c0 + q;
+                dmma884(cv.x, cv.y, ap[0], bp[0]);
+                dmma884(cv.x, cv.y, ap[4], bp[4]);
+                if (wid == 0) { p0 = cv.x; p1 = cv.y; }
+                else *reinterpret_cast<double2*>(cp) = cv;
+            }
+        }
+        // (no barrier: warp 0 goes on with the pivot block in registers; the others wait at the next barrier)
+    }
+    TRACE_MARK(8);
+
+    // ---- X = inv(L) (unit lower) by block recursion: X[hi, lo] = -X[hi, hi] (L[hi, lo] X[lo, lo]) for the pairs of
+    // diagonal blocks of size bs = 8, 16, 32 (the pairs of one level are independent)
+    for (int bs = 8; bs < NB; bs *= 2) {
+        const int tb = bs / 8, npair = NB / (2 * bs), ps = 2 * bs * (DP + 1);
+        smem_pair_products({T, TP, bs}, {S + bs * DP, DP, ps}, {X, DP, ps}, npair, tb, false);
+        __syncthreads();
+        smem_pair_products({X + bs * DP, DP, ps}, {X + bs * (DP + 1), DP, ps}, {T, TP, bs}, npair, tb, true);
         __syncthreads();
     }
-    // 64-level: X[32:64, 0:32] = -X[32:64, 32:64] * (L[32:64, 0:32] * X[0:32, 0:32])
-    for (int e = tid; e < 32 * 32; e += blockDim.x) {
-        const int r = e >> 5, c = e & 31;
-        double acc = 0.0;
-#pragma unroll 8
-        for (int p = 0; p < 32; p++) acc = fma(S[32 + r][p], X[p * XP + c], acc);
-        T[r * 33 + c] = acc;
-    }
-    __syncthreads();
-    smem_neg_matmul(X + 32 * XP, XP, X + 32 * XP + 32, XP, T, 33, 32, 32, 32);
-    __syncthreads();
+    TRACE_MARK(9);
 
     // ---- write back: L (strict lower), d (diagonal), inv(L)' (strict upper)
     for (int e = tid; e < NB * NB; e += blockDim.x) {
         const int r = e >> 6, c = e & 63;
-        double v;
-        if (c < r) v = S[r][c];
-        else if (c == r) v = S[r][r];
-        else v = X[c * XP + r];  // K[j0 + r][j0 + c] = X[c][r], c > r
+        const double v = (c <= r) ? S[r * DP + c] : X[c * DP + r];  // K[j0 + r][j0 + c] = X[c][r], c > r
         Kb[(size_t)(j0 + r) * ld + j0 + c] = v;
     }
     if (tid == 0) {
@@ -301,15 +266,47 @@ __device__ __forceinline__ void ldlt_diag_body(double* sm, int b, int ld, const 
             if (bad != 0 && info[b] == 0) info[b] = bad;
         }
     }
+    TRACE_MARK(10);
+    TRACE_COUNT();
 }
 
 // ------------------------------------------------------------------------------------------------
 constexpr int TM = 128, TN = 64, STAGES = 2;
-constexpr int PKC = 32;        // k-chunk per pipeline stage of the panel kernel
+constexpr int PKC = 32;        // k-chunk per pipeline stage
 constexpr int PSP = PKC + 4;   // its smem row pitch (== 4 mod 16: conflict-free fragment loads)
-constexpr int PN_SMEM_PIPE = (STAGES * (TM + TN) * PSP + STAGES * PKC) * (int)sizeof(double);
-constexpr int PN_SMEM_EPI = (TM + TN) * EP * (int)sizeof(double);
-constexpr int PN_SMEM = PN_SMEM_PIPE > PN_SMEM_EPI ? PN_SMEM_PIPE : PN_SMEM_EPI;
+constexpr int STAGE_ROWS = TM + TN;  // rows of a stage: panel 128 A + 64 B, chain 64 A + 64 B1 + 64 B2
+constexpr int PN_SMEM = STAGES * STAGE_ROWS * PSP * (int)sizeof(double);
+static_assert(PKC * 2 == NB, "two chunks per block column: the chunk count is even, the last chunk sits in stage 1");
+// epilogue regions (doubles from the start of the dynamic shared memory); Xs must fit into stage 0, which is idle
+// while the last chunk (always in stage 1) is computed and receives the diagonal block of column k meanwhile
+constexpr int EPI_XS = 0;                       // 64 x EP : storage rows of diagonal block k (inv(L_kk)' above its diagonal)
+static_assert(NB * EP <= STAGE_ROWS * PSP, "Xs must fit into one pipeline stage");
+constexpr int PN_CS = NB * EP;                  // panel: C tile, 128 x EP (written after the main loop)
+constexpr int PN_RINV = PN_CS + TM * EP;        // 64 reciprocal pivots
+static_assert((PN_RINV + NB) * (int)sizeof(double) <= PN_SMEM, "panel epilogue must fit");
+constexpr int CH_S = NB * EP;                   // chain: S (64 x DP), C / W' (64 x EP), rinv; factor scratch over C
+constexpr int CH_CS = CH_S + DG_S;
+constexpr int CH_RINV = CH_CS + NB * EP;
+static_assert((CH_RINV + NB) * (int)sizeof(double) <= PN_SMEM, "chain epilogue must fit");
+static_assert(DG_MISC <= NB * EP, "the factor's scratch reuses the C / W' region");
+static_assert(DG_OPS <= NB * EP, "inv(L) scratch reuses the Xs region");
+
+// 16-byte asynchronous copy of the 64 x 64 diagonal block of column k (storage layout) into Xs
+__device__ __forceinline__ void load_diag_block(double* Xs, const double* __restrict__ Kb, int j0, int ld) {
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int piece = threadIdx.x + t * 256;
+        const int r = piece >> 5, c2 = (piece & 31) * 2;
+        cp_async16(Xs + r * EP + c2, Kb + (size_t)(j0 + r) * ld + j0 + c2);
+    }
+}
+
+// B fragment of X' for the triangular solve, read from the storage layout G[kk][n] (X[n][kk] for n > kk):
+// unit diagonal and zeros below it are supplied here.
+__device__ __forceinline__ double xt_fragment(const double* Xs, int kq, int n) {
+    const double v = Xs[kq * EP + n];
+    return n > kq ? v : (n == kq ? 1.0 : 0.0);
+}
 
 // One ROWS x 64 tile of block column k (rows i0.., all inside the padded order): update + triangular solve.
 // ROWS = 128: 4 x 2 warps of 32 x 32;  ROWS = 64 (odd remainder block): 2 x 4 warps of 32 x 16.
@@ -320,38 +317,36 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     constexpr int NI = 8 / WN;                  // 8-column DMMA tiles per warp
     constexpr int WC = NI * 8;                  // columns per warp
     constexpr int AT = ROWS / 16;               // 16-byte pieces per thread per stage for the A rows
-    double* As = sm;                            // STAGES x TM x PSP (ROWS rows used)
-    double* Bs = sm + STAGES * TM * PSP;        // STAGES x TN x PSP
-    double* Ds = Bs + STAGES * TN * PSP;        // STAGES x PKC : d of the chunk
+    double* As = sm;                            // stage s: A rows at s * STAGE_ROWS * PSP, B rows TM rows later
+    double* Bs = sm + TM * PSP;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm = wid / WN, wn = wid % WN;
     const int g = lane >> 2, q = lane & 3;
     const int nchunks = j0 / PKC;
+    TRACE_BEGIN(j0 / NB, 1);
 
     // Each thread copies one 16-byte piece of AT A rows and 4 B rows per stage: row = (tid >> 4) + 16 t,
-    // piece = tid & 15; pointers advance by constants.  Threads 0..15 also copy the chunk's 32 pivots.
+    // piece = tid & 15.  A = W'[tile rows, chunk] from the mirrored blocks (p, i): tile row r of block i, depth
+    // 64 p + c sits at K[64 p + (r & 63)][64 i + c];  B = L[block k rows, chunk] from the lower triangle.
     const int lrow = tid >> 4, lpart = (tid & 15) * 2;
-    const double* gA = Kb + (size_t)(i0 + lrow) * ld + lpart;
+    const double* gA = Kb + (size_t)lrow * ld + i0 + lpart;
     const double* gB = Kb + (size_t)(j0 + lrow) * ld + lpart;
     const size_t gstride = (size_t)16 * ld;
     double* sA = As + lrow * PSP + lpart;
     double* sB = Bs + lrow * PSP + lpart;
     auto load_stage = [&](int chunk, int stage) {
-        const double* ga = gA + chunk * PKC;
+        const double* ga = gA + (size_t)(chunk >> 1) * NB * ld + (chunk & 1) * PKC;
         const double* gb = gB + chunk * PKC;
-        double* sa = sA + stage * TM * PSP;
-        double* sb = sB + stage * TN * PSP;
+        double* sa = sA + stage * STAGE_ROWS * PSP;
+        double* sb = sB + stage * STAGE_ROWS * PSP;
 #pragma unroll
-        for (int t = 0; t < AT; t++) cp_async16(sa + t * 16 * PSP, ga + t * gstride);
+        for (int t = 0; t < AT; t++) cp_async16(sa + t * 16 * PSP, ga + (t & 3) * gstride + (t >> 2) * NB);
 #pragma unroll
         for (int t = 0; t < 4; t++) cp_async16(sb + t * 16 * PSP, gb + t * gstride);
-        if (tid < PKC / 2) cp_async16(Ds + stage * PKC + tid * 2, db + chunk * PKC + tid * 2);
     };
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nchunks) load_stage(s, s);
-        cp_async_commit();
-    }
+    if (nchunks > 0) load_stage(0, 0);
+    else load_diag_block(sm + EPI_XS, Kb, j0, ld);
+    cp_async_commit();
     // accumulators start from the current A tile (these loads overlap the first pipeline stage)
     double acc[4][NI][2];
 #pragma unroll
@@ -364,53 +359,36 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
             acc[mi][ni][1] = v.y;
         }
     }
+    TRACE_MARK(0);
     for (int c = 0; c < nchunks; c++) {
-        cp_async_wait<STAGES - 2>();
+        cp_async_wait<0>();
         __syncthreads();
-        const int nxt = c + STAGES - 1;
-        if (nxt < nchunks) load_stage(nxt, nxt % STAGES);
+        if (c + 1 < nchunks) load_stage(c + 1, (c + 1) & 1);
+        else load_diag_block(sm + EPI_XS, Kb, j0, ld);   // stage 0 is idle during the last chunk
         cp_async_commit();
-        const double* as = As + (c % STAGES) * TM * PSP + (wm * 32 + g) * PSP + q;
-        const double* bs = Bs + (c % STAGES) * TN * PSP + (wn * WC + g) * PSP + q;
-        const double* ds = Ds + (c % STAGES) * PKC + q;
-        // software pipeline: the fragments of k-step kk+4 are fetched while the DMMAs of kk issue
-        double a[4], bf[NI], dcur;
-#pragma unroll
-        for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * PSP];
-#pragma unroll
-        for (int ni = 0; ni < NI; ni++) bf[ni] = bs[ni * 8 * PSP];
-        dcur = ds[0];
+        const double* as = As + (c & 1) * STAGE_ROWS * PSP + (wm * 32 + g) * PSP + q;
+        const double* bs = Bs + (c & 1) * STAGE_ROWS * PSP + (wn * WC + g) * PSP + q;
 #pragma unroll
         for (int kk = 0; kk < PKC; kk += 4) {
-            double an[4], bn[NI], dn = 0.0;
-            if (kk + 4 < PKC) {
+            double a[4], bf[NI];
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) an[mi] = as[mi * 8 * PSP + kk + 4];
+            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * PSP + kk];
 #pragma unroll
-                for (int ni = 0; ni < NI; ni++) bn[ni] = bs[ni * 8 * PSP + kk + 4];
-                dn = ds[kk + 4];
-            }
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] *= -dcur;
+            for (int ni = 0; ni < NI; ni++) bf[ni] = bs[ni * 8 * PSP + kk];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
                 for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
-            if (kk + 4 < PKC) {
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++) a[mi] = an[mi];
-#pragma unroll
-                for (int ni = 0; ni < NI; ni++) bf[ni] = bn[ni];
-                dcur = dn;
-            }
         }
     }
     cp_async_wait<0>();
-    __syncthreads();  // every warp is done with the pipeline buffers
+    __syncthreads();  // every warp is done with the pipeline buffers; the diagonal block has landed in Xs
+    TRACE_MARK(1);
 
-    // ---- epilogue: L[i,k] = (C X') D^{-1} with X = inv(L_kk) read from the diagonal block's upper triangle
-    double* Cs = sm;                 // ROWS x EP
-    double* Xs = sm + TM * EP;       // TN x EP : Xs[n][kk] = X[n][kk]
+    // ---- epilogue: W = C X' (DMMA), L[i,k] = W D^{-1} -> lower triangle, W' = -W -> mirrored block
+    const double* Xs = sm + EPI_XS;
+    double* Cs = sm + PN_CS;
+    double* rinv = sm + PN_RINV;
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
         const int r = wm * 32 + mi * 8 + g;
@@ -420,21 +398,15 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
             *reinterpret_cast<double2*>(Cs + r * EP + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
     }
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int kk = e >> 6, n = e & 63;  // coalesced read of storage row j0 + kk
-        double v = 0.0;
-        if (n > kk) v = Kb[(size_t)(j0 + kk) * ld + j0 + n];
-        else if (n == kk) v = 1.0;
-        Xs[n * EP + kk] = v;
-    }
+    if (tid < NB) rinv[tid] = 1.0 / db[j0 + tid];
     __syncthreads();
+    TRACE_MARK(2);
 #pragma unroll
     for (int mi = 0; mi < 4; mi++)
 #pragma unroll
         for (int ni = 0; ni < NI; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
     {
         const double* as = Cs + (wm * 32 + g) * EP + q;
-        const double* bs = Xs + (wn * WC + g) * EP + q;
         // X[n][kk] = 0 for kk > n: the 8 columns starting at n0 only need kk < n0 + 8
         const int kend = wn * WC + WC;
         for (int kk = 0; kk < kend; kk += 4) {
@@ -444,7 +416,7 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
 #pragma unroll
             for (int ni = 0; ni < NI; ni++) {
                 if (kk < wn * WC + ni * 8 + 8) {
-                    const double bf = bs[ni * 8 * EP + kk];
+                    const double bf = xt_fragment(Xs, kk + q, wn * WC + ni * 8 + g);
 #pragma unroll
                     for (int mi = 0; mi < 4; mi++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf);
                 }
@@ -453,62 +425,275 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     }
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) {
-        const int col = j0 + wn * WC + ni * 8 + 2 * q;
-        const double r0 = 1.0 / __ldg(db + col), r1 = 1.0 / __ldg(db + col + 1);
+        const int c = wn * WC + ni * 8 + 2 * q;
+        const double r0 = rinv[c], r1 = rinv[c + 1];
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
-            const int row = i0 + wm * 32 + mi * 8 + g;
-            *reinterpret_cast<double2*>(Kb + (size_t)row * ld + col) =
-                make_double2(acc[mi][ni][0] * r0, acc[mi][ni][1] * r1);
+            const int r = wm * 32 + mi * 8 + g;
+            const double w0 = acc[mi][ni][0], w1 = acc[mi][ni][1];
+            *reinterpret_cast<double2*>(Kb + (size_t)(i0 + r) * ld + j0 + c) = make_double2(w0 * r0, w1 * r1);
+            *reinterpret_cast<double2*>(Kb + (size_t)(j0 + (r & 63)) * ld + i0 + (r >> 6) * NB + c) =
+                make_double2(-w0, -w1);
         }
     }
+    TRACE_MARK(3);
+    TRACE_COUNT();
 }
 
-__device__ __forceinline__ void ldlt_panel_body(double* sm, int b, int tile, int ld,
-                                                const int32_t* __restrict__ Nvec, int Nfixed, int k,
-                                                double* __restrict__ K, const double* __restrict__ dvec) {
+// ------------------------------------------------------------------------------------------------
+// Chain CTA of block column k: rows of block k+1 (i0 = j0 + 64).  One DMMA main loop over the block columns
+// p < k produces the 64 x 128 tile [ A[k+1,k] | A[k+1,k+1] ] + sum_p W'[k+1,p] [ L[k,p] | L[k+1,p] ]'
+// (8 warps of 32 x 32), then
+//   W = C X_k' (DMMA), L[k+1,k] = W D_k^{-1} -> global, W' = -W -> mirror;  S = A[k+1,k+1]-part + W' L[k+1,k]';
+//   ldlt_diag_factor(S) for block k+1.
+__device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const int32_t* __restrict__ Nvec,
+                                                int Nfixed, int k, double* __restrict__ K,
+                                                double* __restrict__ dvec, int32_t* __restrict__ info,
+                                                int32_t* __restrict__ nneg,
+                                                const int32_t* __restrict__ npos_expected) {
+    const int Np = padded_order(Nvec, Nfixed, b, ld);
+    const int j0 = k * NB, i0 = j0 + NB;
+    if (i0 >= Np) return;
+    double* Kb = K + (size_t)b * ld * ld;
+    const double* db = dvec + (size_t)b * ld;
+    double* As = sm;                    // per stage: 64 rows W'[k+1, chunk], 64 rows L[k, chunk], 64 rows L[k+1, chunk]
+    double* B1s = sm + NB * PSP;
+    double* B2s = sm + 2 * NB * PSP;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm = wid >> 2, wn = wid & 3;      // 2 x 4 warps of 32 x 32
+    const int g = lane >> 2, q = lane & 3;
+    const bool diag_part = wn >= 2;             // columns 64..127 of the tile = diagonal tile of block k+1
+    const bool skip = (wm == 0) && (wn == 3);   // its strictly upper 32 x 32 quadrant is never read
+    const int nchunks = j0 / PKC;
+    TRACE_BEGIN(k + 1, 0);
+
+    const int lrow = tid >> 4, lpart = (tid & 15) * 2;
+    const double* gA = Kb + (size_t)lrow * ld + i0 + lpart;
+    const double* gB1 = Kb + (size_t)(j0 + lrow) * ld + lpart;
+    const double* gB2 = Kb + (size_t)(i0 + lrow) * ld + lpart;
+    const size_t gstride = (size_t)16 * ld;
+    auto load_stage = [&](int chunk, int stage) {
+        const double* ga = gA + (size_t)(chunk >> 1) * NB * ld + (chunk & 1) * PKC;
+        const double* gb1 = gB1 + chunk * PKC;
+        const double* gb2 = gB2 + chunk * PKC;
+        double* sa = As + stage * STAGE_ROWS * PSP + lrow * PSP + lpart;
+#pragma unroll
+        for (int t = 0; t < 4; t++) cp_async16(sa + t * 16 * PSP, ga + t * gstride);
+#pragma unroll
+        for (int t = 0; t < 4; t++) cp_async16(sa + (NB + t * 16) * PSP, gb1 + t * gstride);
+#pragma unroll
+        for (int t = 0; t < 4; t++) cp_async16(sa + (2 * NB + t * 16) * PSP, gb2 + t * gstride);
+    };
+    if (nchunks > 0) load_stage(0, 0);
+    else load_diag_block(sm + EPI_XS, Kb, j0, ld);
+    cp_async_commit();
+    double acc[4][4][2];
+    {
+        const int colbase = (diag_part ? i0 + (wn - 2) * 32 : j0 + wn * 32) + 2 * q;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const double* rowp = Kb + (size_t)(i0 + wm * 32 + mi * 8 + g) * ld + colbase;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                double2 v = make_double2(0.0, 0.0);
+                if (!skip) v = *reinterpret_cast<const double2*>(rowp + ni * 8);
+                acc[mi][ni][0] = v.x;
+                acc[mi][ni][1] = v.y;
+            }
+        }
+    }
+    TRACE_MARK(0);
+    for (int c = 0; c < nchunks; c++) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (c + 1 < nchunks) load_stage(c + 1, (c + 1) & 1);
+        else load_diag_block(sm + EPI_XS, Kb, j0, ld);
+        cp_async_commit();
+        const int so = (c & 1) * STAGE_ROWS * PSP;
+        const double* as = As + so + (wm * 32 + g) * PSP + q;
+        const double* bs = (diag_part ? B2s + so + ((wn - 2) * 32 + g) * PSP : B1s + so + (wn * 32 + g) * PSP) + q;
+        if (!skip) {
+#pragma unroll
+            for (int kk = 0; kk < PKC; kk += 4) {
+                double a[4], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * PSP + kk];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * PSP + kk];
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // every warp is done with the pipeline buffers; the diagonal block has landed in Xs
+    TRACE_MARK(1);
+
+    // ---- epilogue 1: panel half -> Cs, diagonal half -> S
+    double* Xs = sm + EPI_XS;                                          // 64 x EP, later L[k+1,k]
+    double(*S)[DP] = reinterpret_cast<double(*)[DP]>(sm + CH_S);           // 64 x DP
+    double* Cs = sm + CH_CS;                                           // 64 x EP, later W' = -C X'
+    double* rinv = sm + CH_RINV;                                       // 64
+    if (!diag_part) {
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int r = wm * 32 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int c = wn * 32 + ni * 8 + 2 * q;
+                *reinterpret_cast<double2*>(Cs + r * EP + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            }
+        }
+    } else if (!skip) {
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int r = wm * 32 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int c = (wn - 2) * 32 + ni * 8 + 2 * q;
+                S[r][c] = acc[mi][ni][0];
+                S[r][c + 1] = acc[mi][ni][1];
+            }
+        }
+    }
+    if (tid < NB) rinv[tid] = 1.0 / db[j0 + tid];
+    __syncthreads();
+    TRACE_MARK(2);
+
+    // ---- epilogue 2: W = C X' (2 x 4 warps of 32 x 16), L = W D^{-1}
+    {
+        double w2[4][2][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) { w2[mi][ni][0] = 0.0; w2[mi][ni][1] = 0.0; }
+        const double* as = Cs + (wm * 32 + g) * EP + q;
+        const int kend = wn * 16 + 16;  // X[n][kk] = 0 for kk > n
+        for (int kk = 0; kk < kend; kk += 4) {
+            double a[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * EP + kk];
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) {
+                if (kk < wn * 16 + ni * 8 + 8) {
+                    const double bf = xt_fragment(Xs, kk + q, wn * 16 + ni * 8 + g);
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++) dmma884(w2[mi][ni][0], w2[mi][ni][1], a[mi], bf);
+                }
+            }
+        }
+        __syncthreads();  // all reads of Cs / Xs are done: overwrite them with W' and L
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) {
+            const int c = wn * 16 + ni * 8 + 2 * q;
+            const double r0 = rinv[c], r1 = rinv[c + 1];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) {
+                const int r = wm * 32 + mi * 8 + g;
+                const double2 wv = make_double2(-w2[mi][ni][0], -w2[mi][ni][1]);
+                const double2 lv = make_double2(w2[mi][ni][0] * r0, w2[mi][ni][1] * r1);
+                *reinterpret_cast<double2*>(Cs + r * EP + c) = wv;
+                *reinterpret_cast<double2*>(Xs + r * EP + c) = lv;
+                *reinterpret_cast<double2*>(Kb + (size_t)(i0 + r) * ld + j0 + c) = lv;
+                *reinterpret_cast<double2*>(Kb + (size_t)(j0 + r) * ld + i0 + c) = wv;
+            }
+        }
+    }
+    __syncthreads();
+    TRACE_MARK(3);
+
+    // ---- epilogue 3: S += W' L'  (4 x 2 warps of 16 x 32, strictly upper quadrant skipped)
+    {
+        const int wm2 = wid >> 1, wn2 = wid & 1;
+        if (!((wn2 == 1) && (wm2 < 2))) {
+            double s2[2][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm2 * 16 + mi * 8 + g;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    const int c = wn2 * 32 + ni * 8 + 2 * q;
+                    s2[mi][ni][0] = S[r][c];
+                    s2[mi][ni][1] = S[r][c + 1];
+                }
+            }
+            const double* as = Cs + (wm2 * 16 + g) * EP + q;
+            const double* bs = Xs + (wn2 * 32 + g) * EP + q;
+#pragma unroll 4
+            for (int kk = 0; kk < NB; kk += 4) {
+                double a[2], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) a[mi] = as[mi * 8 * EP + kk];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * EP + kk];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(s2[mi][ni][0], s2[mi][ni][1], a[mi], bf[ni]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm2 * 16 + mi * 8 + g;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    const int c = wn2 * 32 + ni * 8 + 2 * q;
+                    S[r][c] = s2[mi][ni][0];
+                    S[r][c + 1] = s2[mi][ni][1];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    TRACE_MARK(4);
+    ldlt_diag_factor(sm + CH_S, sm + EPI_XS, sm + CH_CS, b, ld, Nvec, Nfixed, k + 1, K, dvec, info, nneg,
+                     npos_expected);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch wrappers.
+__global__ void __launch_bounds__(256, 3) ldlt_diag0_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                             double* __restrict__ K, double* __restrict__ dvec,
+                                                             int32_t* __restrict__ info, int32_t* __restrict__ nneg,
+                                                             const int32_t* __restrict__ npos_expected, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    if (padded_order(Nvec, Nfixed, b, ld) <= 0) return;
+    double(*S)[DP] = reinterpret_cast<double(*)[DP]>(sm);
+    const double* Kb = K + (size_t)b * ld * ld;
+    for (int e = threadIdx.x; e < NB * NB / 2; e += blockDim.x) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)r * ld + c);
+        S[r][c] = v.x;
+        S[r][c + 1] = v.y;
+    }
+    __syncthreads();
+    ldlt_diag_factor(sm, sm + DG_S, sm + DG_S + DG_OPS, b, ld, Nvec, Nfixed, 0, K, dvec, info, nneg, npos_expected);
+}
+
+// Block column k: blockIdx.x == 0 is the chain CTA (rows of block k+1 + diagonal block k+1), blockIdx.x >= 1 the
+// 128-row panel tiles from row j0 + 128 on.  No CTA depends on another CTA of the same launch.
+__global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                             int k, double* __restrict__ K, double* __restrict__ dvec,
+                                                             int32_t* __restrict__ info, int32_t* __restrict__ nneg,
+                                                             const int32_t* __restrict__ npos_expected, GfWork work) {
+    const int b = gf_instance(work, blockIdx.y);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    if (blockIdx.x == 0) {
+        ldlt_chain_body(sm, b, ld, Nvec, Nfixed, k, K, dvec, info, nneg, npos_expected);
+        return;
+    }
     const int Np = padded_order(Nvec, Nfixed, b, ld);
     const int j0 = k * NB;
-    const int i0 = j0 + NB + tile * TM;
+    const int i0 = j0 + 2 * NB + (blockIdx.x - 1) * TM;
     if (i0 >= Np) return;
     double* Kb = K + (size_t)b * ld * ld;
     const double* db = dvec + (size_t)b * ld;
     if (Np - i0 >= TM) ldlt_panel_tile<128>(sm, i0, j0, ld, Kb, db);
     else ldlt_panel_tile<64>(sm, i0, j0, ld, Kb, db);   // odd remainder block: Np - i0 == 64
-}
-
-// ------------------------------------------------------------------------------------------------
-// Launch wrappers.  `fused` interleaves, per matrix, the diag role of block column k+1 (blockIdx.x == 0) with
-// the panel tiles 1.. of block column k: the latency-bound factor / inverse phases of the diagonal block then
-// share an SM with a DMMA-bound panel CTA instead of idling the GPU between launches (look-ahead).
-__global__ void __launch_bounds__(256, 3) ldlt_diag_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k,
-                                                        double* __restrict__ K, double* __restrict__ dvec,
-                                                        int32_t* __restrict__ info, int32_t* __restrict__ nneg,
-                                                        const int32_t* __restrict__ npos_expected, GfWork work) {
-    const int b = gf_instance(work, blockIdx.x);
-    if (b < 0) return;
-    extern __shared__ double sm[];
-    ldlt_diag_body(sm, b, ld, Nvec, Nfixed, k, K, dvec, info, nneg, npos_expected);
-}
-
-__global__ void __launch_bounds__(256, 2) ldlt_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
-                                                            int k, int tile0, double* __restrict__ K,
-                                                            const double* __restrict__ dvec, GfWork work) {
-    const int b = gf_instance(work, blockIdx.y);
-    if (b < 0) return;
-    extern __shared__ double sm[];
-    ldlt_panel_body(sm, b, tile0 + blockIdx.x, ld, Nvec, Nfixed, k, K, dvec);
-}
-
-__global__ void __launch_bounds__(256, 2) ldlt_fused_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
-                                                            int k, double* __restrict__ K, double* __restrict__ dvec,
-                                                            int32_t* __restrict__ info, int32_t* __restrict__ nneg,
-                                                            const int32_t* __restrict__ npos_expected, GfWork work) {
-    const int b = gf_instance(work, blockIdx.y);
-    if (b < 0) return;
-    extern __shared__ double sm[];
-    if (blockIdx.x == 0) ldlt_diag_body(sm, b, ld, Nvec, Nfixed, k + 1, K, dvec, info, nneg, npos_expected);
-    else ldlt_panel_body(sm, b, blockIdx.x, ld, Nvec, Nfixed, k, K, dvec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -595,22 +780,19 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
     GfWork w{work, nwork_dev};
     const int Np = ((Nmax + NB - 1) / NB) * NB;
     const int nblk = Np / NB;
-    constexpr int FUSED_SMEM = PN_SMEM > DG_SMEM ? PN_SMEM : DG_SMEM;
-    cudaFuncSetAttribute(ldlt_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
-    cudaFuncSetAttribute(ldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PN_SMEM);
-    cudaFuncSetAttribute(ldlt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
-    ldlt_diag_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, 0, K, dvec, info, nneg, npos_expected, w);
+#ifdef GF_LDLT_COL_SMEM_MIN  // developer experiment: force the occupancy of the column kernel
+    constexpr int COL_SMEM = GF_LDLT_COL_SMEM_MIN;
+#else
+    constexpr int COL_SMEM = PN_SMEM;
+#endif
+    cudaFuncSetAttribute(ldlt_diag0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
+    cudaFuncSetAttribute(ldlt_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM);
+    ldlt_diag0_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w);
     for (int k = 0; k + 1 < nblk; k++) {
-        const int j0 = k * NB;
-        const int tiles = (Np - j0 - NB + TM - 1) / TM;  // >= 1
-        // tile 0 holds the rows diag(k+1) needs; everything else of panel(k) runs beside diag(k+1)
-        ldlt_panel_kernel<<<dim3(1, nwork), 256, PN_SMEM, s>>>(ld, Nvec, Nmax, k, 0, K, dvec, w);
-        if (tiles > 1)
-            ldlt_fused_kernel<<<dim3(tiles, nwork), 256, FUSED_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
-                                                                          npos_expected, w);
-        else  // nothing to interleave with: the standalone diag kernel fits three CTAs per SM
-            ldlt_diag_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, k + 1, K, dvec, info, nneg, npos_expected,
-                                                         w);
+        const int below = Np - (k + 2) * NB;              // rows under block k+1
+        const int tiles = 1 + (below + TM - 1) / TM;      // chain CTA + 128-row panel tiles
+        ldlt_column_kernel<<<dim3(tiles, nwork), 256, COL_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
+                                                                     npos_expected, w);
     }
     return gf_launch_status();
 }

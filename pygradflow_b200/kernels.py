@@ -111,7 +111,7 @@ def ldlt_factor(K, Nmax: int, Nvec, dvec, info, nneg, npos_expected, work: WorkL
     B, ld, _ = K.shape
     nblk = (Nmax + 63) // 64
     _call("gf_ldlt_factor", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(dvec), ptr(info), ptr(nneg), ptr(npos_expected),
-          *_w(work), launches=max(1, 2 * nblk - 1))
+          *_w(work), launches=max(1, nblk))
 
 
 def ldlt_solve(K, Nmax: int, Nvec, rhs, work: WorkList):
