@@ -28,6 +28,8 @@
 // (~ 8 N^3 / (6*64) bytes per matrix), so the factorisation is bound by the FP64 pipe, not by HBM.
 #include "gf_common.cuh"
 #include "../../include/gradflow_b200.h"
+#include <cstdlib>
+#include <mutex>
 
 #ifdef GF_LDLT_TRACE
 // Developer instrumentation (tools/ldlt_trace.cu): per block column / CTA role, cycles spent per phase.
@@ -401,39 +403,43 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     if (tid < NB) rinv[tid] = 1.0 / db[j0 + tid];
     __syncthreads();
     TRACE_MARK(2);
-#pragma unroll
-    for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-        for (int ni = 0; ni < NI; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    // every warp solves ROWS / 8 full rows (all 64 columns), so the triangular pruning of the k range loads all
+    // warps -- and with them the four SM sub-partitions -- equally
     {
-        const double* as = Cs + (wm * 32 + g) * EP + q;
-        // X[n][kk] = 0 for kk > n: the 8 columns starting at n0 only need kk < n0 + 8
-        const int kend = wn * WC + WC;
-        for (int kk = 0; kk < kend; kk += 4) {
-            double a[4];
+        constexpr int TMI = ROWS / 64;           // 8-row DMMA tiles per warp
+        constexpr int WR = ROWS / 8;             // rows per warp
+        double t[TMI][8][2];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * EP + kk];
+        for (int mi = 0; mi < TMI; mi++)
 #pragma unroll
-            for (int ni = 0; ni < NI; ni++) {
-                if (kk < wn * WC + ni * 8 + 8) {
-                    const double bf = xt_fragment(Xs, kk + q, wn * WC + ni * 8 + g);
+            for (int ni = 0; ni < 8; ni++) { t[mi][ni][0] = 0.0; t[mi][ni][1] = 0.0; }
+        const double* as = Cs + (wid * WR + g) * EP + q;
 #pragma unroll
-                    for (int mi = 0; mi < 4; mi++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf);
+        for (int kk = 0; kk < NB; kk += 4) {
+            double a[TMI];
+#pragma unroll
+            for (int mi = 0; mi < TMI; mi++) a[mi] = as[mi * 8 * EP + kk];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) {
+                if (kk < ni * 8 + 8) {  // X[n][kk] = 0 for kk > n
+                    const double bf = xt_fragment(Xs, kk + q, ni * 8 + g);
+#pragma unroll
+                    for (int mi = 0; mi < TMI; mi++) dmma884(t[mi][ni][0], t[mi][ni][1], a[mi], bf);
                 }
             }
         }
-    }
 #pragma unroll
-    for (int ni = 0; ni < NI; ni++) {
-        const int c = wn * WC + ni * 8 + 2 * q;
-        const double r0 = rinv[c], r1 = rinv[c + 1];
+        for (int ni = 0; ni < 8; ni++) {
+            const int c = ni * 8 + 2 * q;
+            const double r0 = rinv[c], r1 = rinv[c + 1];
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++) {
-            const int r = wm * 32 + mi * 8 + g;
-            const double w0 = acc[mi][ni][0], w1 = acc[mi][ni][1];
-            *reinterpret_cast<double2*>(Kb + (size_t)(i0 + r) * ld + j0 + c) = make_double2(w0 * r0, w1 * r1);
-            *reinterpret_cast<double2*>(Kb + (size_t)(j0 + (r & 63)) * ld + i0 + (r >> 6) * NB + c) =
-                make_double2(-w0, -w1);
+            for (int mi = 0; mi < TMI; mi++) {
+                const int r = wid * WR + mi * 8 + g;
+                const double w0 = t[mi][ni][0], w1 = t[mi][ni][1];
+                *reinterpret_cast<double2*>(Kb + (size_t)(i0 + r) * ld + j0 + c) = make_double2(w0 * r0, w1 * r1);
+                *reinterpret_cast<double2*>(Kb + (size_t)(j0 + (r & 63)) * ld + i0 + (r >> 6) * NB + c) =
+                    make_double2(-w0, -w1);
+            }
         }
     }
     TRACE_MARK(3);
@@ -562,43 +568,32 @@ __device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const
     __syncthreads();
     TRACE_MARK(2);
 
-    // ---- epilogue 2: W = C X' (2 x 4 warps of 32 x 16), L = W D^{-1}
+    // ---- epilogue 2: W = C X' (every warp 8 full rows), L = W D^{-1}
     {
-        double w2[4][2][2];
+        double t[8][2];
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++)
+        for (int ni = 0; ni < 8; ni++) { t[ni][0] = 0.0; t[ni][1] = 0.0; }
+        const double* as = Cs + (wid * 8 + g) * EP + q;
 #pragma unroll
-            for (int ni = 0; ni < 2; ni++) { w2[mi][ni][0] = 0.0; w2[mi][ni][1] = 0.0; }
-        const double* as = Cs + (wm * 32 + g) * EP + q;
-        const int kend = wn * 16 + 16;  // X[n][kk] = 0 for kk > n
-        for (int kk = 0; kk < kend; kk += 4) {
-            double a[4];
+        for (int kk = 0; kk < NB; kk += 4) {
+            const double a = as[kk];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = as[mi * 8 * EP + kk];
-#pragma unroll
-            for (int ni = 0; ni < 2; ni++) {
-                if (kk < wn * 16 + ni * 8 + 8) {
-                    const double bf = xt_fragment(Xs, kk + q, wn * 16 + ni * 8 + g);
-#pragma unroll
-                    for (int mi = 0; mi < 4; mi++) dmma884(w2[mi][ni][0], w2[mi][ni][1], a[mi], bf);
-                }
+            for (int ni = 0; ni < 8; ni++) {
+                if (kk < ni * 8 + 8) dmma884(t[ni][0], t[ni][1], a, xt_fragment(Xs, kk + q, ni * 8 + g));
             }
         }
         __syncthreads();  // all reads of Cs / Xs are done: overwrite them with W' and L
+        const int r = wid * 8 + g;
 #pragma unroll
-        for (int ni = 0; ni < 2; ni++) {
-            const int c = wn * 16 + ni * 8 + 2 * q;
+        for (int ni = 0; ni < 8; ni++) {
+            const int c = ni * 8 + 2 * q;
             const double r0 = rinv[c], r1 = rinv[c + 1];
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++) {
-                const int r = wm * 32 + mi * 8 + g;
-                const double2 wv = make_double2(-w2[mi][ni][0], -w2[mi][ni][1]);
-                const double2 lv = make_double2(w2[mi][ni][0] * r0, w2[mi][ni][1] * r1);
-                *reinterpret_cast<double2*>(Cs + r * EP + c) = wv;
-                *reinterpret_cast<double2*>(Xs + r * EP + c) = lv;
-                *reinterpret_cast<double2*>(Kb + (size_t)(i0 + r) * ld + j0 + c) = lv;
-                *reinterpret_cast<double2*>(Kb + (size_t)(j0 + r) * ld + i0 + c) = wv;
-            }
+            const double2 wv = make_double2(-t[ni][0], -t[ni][1]);
+            const double2 lv = make_double2(t[ni][0] * r0, t[ni][1] * r1);
+            *reinterpret_cast<double2*>(Cs + r * EP + c) = wv;
+            *reinterpret_cast<double2*>(Xs + r * EP + c) = lv;
+            *reinterpret_cast<double2*>(Kb + (size_t)(i0 + r) * ld + j0 + c) = lv;
+            *reinterpret_cast<double2*>(Kb + (size_t)(j0 + r) * ld + i0 + c) = wv;
         }
     }
     __syncthreads();
@@ -656,8 +651,9 @@ __device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const
 __global__ void __launch_bounds__(256, 3) ldlt_diag0_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                              double* __restrict__ K, double* __restrict__ dvec,
                                                              int32_t* __restrict__ info, int32_t* __restrict__ nneg,
-                                                             const int32_t* __restrict__ npos_expected, GfWork work) {
-    const int b = gf_instance(work, blockIdx.x);
+                                                             const int32_t* __restrict__ npos_expected, GfWork work,
+                                                             int woff) {
+    const int b = gf_instance(work, woff + blockIdx.x);
     if (b < 0) return;
     extern __shared__ double sm[];
     if (padded_order(Nvec, Nfixed, b, ld) <= 0) return;
@@ -678,8 +674,9 @@ __global__ void __launch_bounds__(256, 3) ldlt_diag0_kernel(int ld, const int32_
 __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                              int k, double* __restrict__ K, double* __restrict__ dvec,
                                                              int32_t* __restrict__ info, int32_t* __restrict__ nneg,
-                                                             const int32_t* __restrict__ npos_expected, GfWork work) {
-    const int b = gf_instance(work, blockIdx.y);
+                                                             const int32_t* __restrict__ npos_expected, GfWork work,
+                                                             int woff) {
+    const int b = gf_instance(work, woff + blockIdx.y);
     if (b < 0) return;
     extern __shared__ double sm[];
     if (blockIdx.x == 0) {
@@ -770,6 +767,36 @@ __global__ void __launch_bounds__(256) ldlt_solve_kernel(int ld, const int32_t* 
 
 }  // namespace
 
+// Two internal streams per device: a large batch is factorised in two halves whose block-column launches
+// interleave, so the tail of one half's launch (few long chain CTAs left) is filled by the other half's CTAs.
+namespace {
+struct LdltLanes {
+    cudaStream_t s[2];
+    cudaEvent_t fork, join[2];
+    bool ok;
+};
+LdltLanes* ldlt_lanes() {
+    static std::mutex mu;
+    static LdltLanes lanes[64];
+    static bool made[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    LdltLanes& L = lanes[dev];
+    if (!made[dev]) {
+        made[dev] = true;
+        L.ok = true;
+        for (int i = 0; i < 2; i++) {
+            L.ok = L.ok && cudaStreamCreateWithFlags(&L.s[i], cudaStreamNonBlocking) == cudaSuccess;
+            L.ok = L.ok && cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        L.ok = L.ok && cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) == cudaSuccess;
+    }
+    return L.ok ? &L : nullptr;
+}
+constexpr int LDLT_SPLIT_MIN = 1024;  // below this many matrices a launch has no tail worth hiding
+}  // namespace
+
 extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, double* dvec, int32_t* info,
                               int32_t* nneg, const int32_t* npos_expected, const int32_t* work,
                               const int32_t* nwork_dev, int nwork, void* stream) {
@@ -787,12 +814,33 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
 #endif
     cudaFuncSetAttribute(ldlt_diag0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
     cudaFuncSetAttribute(ldlt_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM);
-    ldlt_diag0_kernel<<<nwork, 256, DG_SMEM, s>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w);
+    static const bool lanes_on = [] { const char* e = getenv("GF_LDLT_LANES"); return e == nullptr || e[0] != '0'; }();
+    LdltLanes* L = (lanes_on && nwork >= LDLT_SPLIT_MIN && nblk > 2) ? ldlt_lanes() : nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (L != nullptr && (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) L = nullptr;
+    const int nlane = L != nullptr ? 2 : 1;
+    const int half = (nwork + 1) / 2;
+    const int off[2] = {0, L != nullptr ? half : 0}, cnt[2] = {L != nullptr ? half : nwork, nwork - half};
+    cudaStream_t st[2] = {L != nullptr ? L->s[0] : s, L != nullptr ? L->s[1] : s};
+    if (L != nullptr) {
+        cudaEventRecord(L->fork, s);
+        for (int i = 0; i < 2; i++) cudaStreamWaitEvent(L->s[i], L->fork, 0);
+    }
+    // issue order interleaves the lanes launch by launch
+    for (int i = 0; i < nlane; i++)
+        ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i]);
     for (int k = 0; k + 1 < nblk; k++) {
         const int below = Np - (k + 2) * NB;              // rows under block k+1
         const int tiles = 1 + (below + TM - 1) / TM;      // chain CTA + 128-row panel tiles
-        ldlt_column_kernel<<<dim3(tiles, nwork), 256, COL_SMEM, s>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
-                                                                     npos_expected, w);
+        for (int i = 0; i < nlane; i++)
+            ldlt_column_kernel<<<dim3(tiles, cnt[i]), 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
+                                                                              npos_expected, w, off[i]);
+    }
+    if (L != nullptr) {
+        for (int i = 0; i < 2; i++) {
+            cudaEventRecord(L->join[i], L->s[i]);
+            cudaStreamWaitEvent(s, L->join[i], 0);
+        }
     }
     return gf_launch_status();
 }
