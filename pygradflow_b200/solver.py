@@ -50,12 +50,15 @@ class BatchedResult:
 class BatchedSolver:
     """``Solver(problem, params).solve(x0, y0)`` for a whole batch on one GPU."""
 
-    def __init__(self, problem: BatchedProblem, params: Optional[Params] = None, sync_every: int = 1):
+    def __init__(self, problem: BatchedProblem, params: Optional[Params] = None, sync_every: int = 1,
+                 use_graph: bool = True, graph_steps: int = 8):
         self.problem = problem
         self.params = params if params is not None else Params()
         if self.params.newton_type == NewtonType.Globalized:
             raise NotImplementedError("Globalized Newton runs through pygradflow_b200.globalized.GlobalizedStepper")
         self.sync_every = max(1, int(sync_every))
+        self.use_graph = bool(use_graph)
+        self.graph_steps = max(1, int(graph_steps))  # captured units replayed between two reads of the running count
         p = problem
         B, n, m, dev = p.B, p.n, p.m, p.device
         self.engine = KKTEngine(B, n, m, dev, self.params.linear_solver_type)
@@ -105,7 +108,7 @@ class BatchedSolver:
 
     def solve(self, x0=None, y0=None, on_iteration: Optional[Callable] = None,
               max_outer: Optional[int] = None) -> BatchedResult:
-        prm, prob, eng = self.params, self.problem, self.engine
+        prm, prob = self.params, self.problem
         B, n, m = prob.B, prob.n, prob.m
         dev = prob.device
         x, y, grad, cons, obj = self.cur
@@ -130,93 +133,128 @@ class BatchedSolver:
         prob.eval(x, grad, cons, obj, allw)
 
         run, second = self.run, self.second
-        run.nwork = B
+        run.nwork = second.nwork = B
+        # One unit of the loop = one outer iteration of every running instance (`_step`) followed by the termination
+        # test of the new iterates (`_top`, solver.py:306-308).  The unit is launch-bound once most instances have
+        # finished (cfg2: a few stragglers run for 20 000 more iterations), so after the first eager unit it is
+        # replayed from a CUDA graph: every kernel takes its instance list and count from device memory, hence one
+        # captured unit is valid for any state, and a unit with nobody running changes nothing.  The captured grid
+        # size (an upper bound of the running count) is re-captured when the count has halved.
+        use_graph = self.use_graph and on_iteration is None and max_outer is None
+        graph, graph_nwork = None, 0
+        self._top(allw)
         outer = 0
-        full = prm.newton_type == NewtonType.Full
-        active_set_newton = prm.newton_type == NewtonType.ActiveSet
-        dual_norm = prm.penalty_update == PenaltyUpdate.DualNorm
-        lb, ub = prob.var_lb, prob.var_ub
-
         while True:
-            # ---- top of the loop: termination test on the current iterate (solver.py:306-308)
-            J0 = prob.jac(x, self.Jbuf[0], run if outer > 0 else allw) if m > 0 else None
-            wtop = run if outer > 0 else allw
-            self._aug_grad(J0, self.cur, self.dL0, self.jty if m > 0 else None, self.jtc if m > 0 else None, wtop)
-            K.check_terminate(x, grad, self._cons(self.cur), self.jty if m > 0 else None,
-                              self.jtc if m > 0 else None, obj, lb, ub, prm.opt_tol, prm.active_tol,
-                              prm.local_infeas_tol, prm.obj_lower_limit, prm.iteration_limit, self.iters,
-                              self.status, self.total_res, wtop)
-            K.build_worklist(self.status, 0, 0, run)
-            if outer % self.sync_every == 0:
-                nrun = int(run.count_dev.item())  # the only host sync of the loop
-                if nrun == 0:
-                    break
-                run.nwork = nrun
+            nrun = int(run.count_dev.item())  # the only host sync of the loop
+            if nrun == 0:
+                break
             if max_outer is not None and outer >= max_outer:
                 break
-            K.dt_from_lamb(self.lamb, self.dt)
-
-            # ---- first Newton step from (x^, y^) = current iterate
-            K.residual(x, self._y(self.cur), x, self._y(self.cur), self.dL0, self._cons(self.cur), lb, ub, self.dt,
-                       True, 0, eng.active, self.F, None, run)
-            H0 = prob.lag_hess(x, self._y(self.cur), self.Hbuf[0], run)
-            eng.update_active_set(run)
-            eng.factor(H0, J0, self.dt, self.rho, run)
-            xm, ym, gm, cm, om = self.mid
-            eng.step(H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
-                     ym if m > 0 else None, self.diff1, run)
-            prob.eval(xm, gm, cm, om, run)
-            Jm = prob.jac(xm, self.Jbuf[1], run) if m > 0 else None
-            self._aug_grad(Jm, self.mid, self.dLm, None, None, run)
-            # ||F_unscaled(mid)|| with the active set recomputed at mid (distance_ratio_control.py:34)
-            K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub, self.dt,
-                       False, 0, None, None, self.mid_norm, run)
-            K.dr_first(self.status, eng.info, self.dt, self.mid_norm, self.diff1, prm.newton_tol, prm.lamb_red,
-                       prm.lamb_min, self.phase, self.lamb_next)
-            K.build_worklist(self.phase, PHASE_SECOND, PHASE_SECOND, second, parent=run)
-            second.nwork = run.nwork
-
-            # ---- second Newton step from mid
-            Hs, Js = H0, J0
-            if full or active_set_newton:
-                # Full: active set + derivatives at mid (newton.py:83-89); ActiveSet: active set at mid,
-                # derivatives frozen (newton.py:205-215).  Refactoring with an unchanged active set
-                # reproduces the same factor, so it is done unconditionally.
-                K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub,
-                           self.dt, True, 0, eng.active, self.F, None, second)
-                if full:
-                    Hs = prob.lag_hess(xm, self._y(self.mid), self.Hbuf[1], second)
-                    Js = Jm
-                eng.update_active_set(second)
-                eng.factor(Hs, Js, self.dt, self.rho, second)
-                # a failed refactorisation rejects the step like the first one would (step_control.py:102-104)
+            if use_graph and outer >= 1:
+                bucket = min(B, max(64, 1 << (nrun - 1).bit_length()))
+                if graph is None or bucket < graph_nwork:
+                    run.nwork = second.nwork = graph_nwork = bucket
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._step(None, 0)
+                        self._top(run)
+                for _ in range(self.graph_steps):
+                    graph.replay()
+                outer += self.graph_steps
             else:
-                K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub,
-                           self.dt, True, 1, eng.active, self.F, None, second)
-            xf, yf, gf, cf, of = self.fin
-            eng.step(Hs, Js, xm, self._y(self.mid), self.F, self.dt, self.rho, lb, ub, xf,
-                     yf if m > 0 else None, self.diff2, second)
-            if full or active_set_newton:
-                self._mark_failed_second(eng)
-            K.dr_second(self.dt, self.diff1, self.diff2, prm.theta_max, prm.log_theta_ref, prm.K_P, prm.K_I,
-                        prm.lamb_min, prm.lamb_inc, self.err_sum, self.phase, self.lamb_next, self.theta)
-            prob.eval(xf, gf, cf, of, second)
-
-            if on_iteration is not None:
-                on_iteration(outer, self)
-            # ---- accept / reject, penalty, counters (solver.py:318-378)
-            ph = self.phase
-            self.newton_step_count += ((ph >= 2) & (ph <= 4)).sum() + ((ph == 3) | (ph == 4)).sum()
-            K.commit(self.phase, self.lamb_next, prm.lamb_max, dual_norm, self.mid, self.fin, self.cur, self.lamb,
-                     self.rho, self.iters, self.accepted, self.status)
-            outer += 1
+                run.nwork = second.nwork = nrun
+                self._step(on_iteration, outer)
+                self._top(run)
+                outer += 1
 
         return BatchedResult(
             x=x.clone(), y=y.clone(), status=self.status.clone(), iterations=self.iters.clone(),
             accepted_steps=self.accepted.clone(), lamb=self.lamb.clone(), rho=self.rho.clone(),
-            total_res=self.total_res.clone(), outer_iterations=outer,
+            total_res=self.total_res.clone(), outer_iterations=int(self.iters.max().item()),
             newton_steps=int(self.newton_step_count.item()),
         )
+
+    def _top(self, wtop: WorkList):
+        """Termination test on the current iterates (solver.py:180-205,306-308) and the list of running instances."""
+        prm, prob = self.params, self.problem
+        m = prob.m
+        x, y, grad, cons, obj = self.cur
+        self._J0 = prob.jac(x, self.Jbuf[0], wtop) if m > 0 else None
+        self._aug_grad(self._J0, self.cur, self.dL0, self.jty if m > 0 else None, self.jtc if m > 0 else None, wtop)
+        K.check_terminate(x, grad, self._cons(self.cur), self.jty if m > 0 else None,
+                          self.jtc if m > 0 else None, obj, prob.var_lb, prob.var_ub, prm.opt_tol, prm.active_tol,
+                          prm.local_infeas_tol, prm.obj_lower_limit, prm.iteration_limit, self.iters,
+                          self.status, self.total_res, wtop)
+        nw = self.run.nwork
+        K.build_worklist(self.status, 0, 0, self.run)
+        self.run.nwork = nw
+
+    def _step(self, on_iteration, outer):
+        """One outer iteration of every running instance: two Newton steps, step-size control, commit."""
+        prm, prob, eng = self.params, self.problem, self.engine
+        m = prob.m
+        run, second = self.run, self.second
+        x, y, grad, cons, obj = self.cur
+        J0 = self._J0
+        full = prm.newton_type == NewtonType.Full
+        active_set_newton = prm.newton_type == NewtonType.ActiveSet
+        dual_norm = prm.penalty_update == PenaltyUpdate.DualNorm
+        lb, ub = prob.var_lb, prob.var_ub
+        K.dt_from_lamb(self.lamb, self.dt)
+
+        # ---- first Newton step from (x^, y^) = current iterate
+        K.residual(x, self._y(self.cur), x, self._y(self.cur), self.dL0, self._cons(self.cur), lb, ub, self.dt,
+                   True, 0, eng.active, self.F, None, run)
+        H0 = prob.lag_hess(x, self._y(self.cur), self.Hbuf[0], run)
+        eng.update_active_set(run)
+        eng.factor(H0, J0, self.dt, self.rho, run)
+        xm, ym, gm, cm, om = self.mid
+        eng.step(H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
+                 ym if m > 0 else None, self.diff1, run)
+        prob.eval(xm, gm, cm, om, run)
+        Jm = prob.jac(xm, self.Jbuf[1], run) if m > 0 else None
+        self._aug_grad(Jm, self.mid, self.dLm, None, None, run)
+        # ||F_unscaled(mid)|| with the active set recomputed at mid (distance_ratio_control.py:34)
+        K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub, self.dt,
+                   False, 0, None, None, self.mid_norm, run)
+        K.dr_first(self.status, eng.info, self.dt, self.mid_norm, self.diff1, prm.newton_tol, prm.lamb_red,
+                   prm.lamb_min, self.phase, self.lamb_next)
+        K.build_worklist(self.phase, PHASE_SECOND, PHASE_SECOND, second, parent=run)
+        second.nwork = run.nwork
+
+        # ---- second Newton step from mid
+        Hs, Js = H0, J0
+        if full or active_set_newton:
+            # Full: active set + derivatives at mid (newton.py:83-89); ActiveSet: active set at mid,
+            # derivatives frozen (newton.py:205-215).  Refactoring with an unchanged active set
+            # reproduces the same factor, so it is done unconditionally.
+            K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub,
+                       self.dt, True, 0, eng.active, self.F, None, second)
+            if full:
+                Hs = prob.lag_hess(xm, self._y(self.mid), self.Hbuf[1], second)
+                Js = Jm
+            eng.update_active_set(second)
+            eng.factor(Hs, Js, self.dt, self.rho, second)
+            # a failed refactorisation rejects the step like the first one would (step_control.py:102-104)
+        else:
+            K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub,
+                       self.dt, True, 1, eng.active, self.F, None, second)
+        xf, yf, gf, cf, of = self.fin
+        eng.step(Hs, Js, xm, self._y(self.mid), self.F, self.dt, self.rho, lb, ub, xf,
+                 yf if m > 0 else None, self.diff2, second)
+        if full or active_set_newton:
+            self._mark_failed_second(eng)
+        K.dr_second(self.dt, self.diff1, self.diff2, prm.theta_max, prm.log_theta_ref, prm.K_P, prm.K_I,
+                    prm.lamb_min, prm.lamb_inc, self.err_sum, self.phase, self.lamb_next, self.theta)
+        prob.eval(xf, gf, cf, of, second)
+
+        if on_iteration is not None:
+            on_iteration(outer, self)
+        # ---- accept / reject, penalty, counters (solver.py:318-378)
+        ph = self.phase
+        self.newton_step_count += ((ph >= 2) & (ph <= 4)).sum() + ((ph == 3) | (ph == 4)).sum()
+        K.commit(self.phase, self.lamb_next, prm.lamb_max, dual_norm, self.mid, self.fin, self.cur, self.lamb,
+                 self.rho, self.iters, self.accepted, self.status)
 
     def _mark_failed_second(self, eng):
         """Solver failure during the second step's refactorisation: reject, lambda <- 2 lambda."""
