@@ -74,6 +74,20 @@ int gf_rosen_eval(int B, int n, const double* a, const double* b, const double* 
 int gf_rosen_hess(int B, int n, const double* a, const double* b, const double* x, double* H,
                   const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 
+/* discretised optimal-control family (cfg4 of the baseline; synthetic, the reference ships no OCP -- the callbacks
+ * it replaces are Problem.obj / obj_grad / cons / cons_jac / lag_hess, problem.py:112-192): variables
+ * z = (x_1, u_0, ..., x_S, u_{S-1}), c_j = x_{j+1} - x_j - h (A_j x_j + B_j u_j + 0.1 sin x_j), x_0 = xinit,
+ * cost 1/2 sum (x'Qx + u'Ru) with diagonal Q [B,S,nx], R [B,S,nu]; A [B,S,nx,nx], Bm [B,S,nx,nu].
+ * gf_ocp_jac / gf_ocp_hess write only the non-zero blocks / the diagonal of dense J [B,m,n] / H [B,n,n]
+ * (zero elsewhere); c1 = 0.1 h. */
+int gf_ocp_eval(int B, int S, int nx, int nu, double h, const double* A, const double* Bm, const double* Q,
+                const double* R, const double* xinit, const double* z, double* grad, double* cons, double* obj,
+                const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+int gf_ocp_jac(int B, int S, int nx, int nu, double h, const double* A, const double* Bm, const double* z, double* J,
+               const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+int gf_ocp_hess(int B, int S, int nx, int nu, double c1, const double* Q, const double* R, const double* z,
+                const double* y, double* H, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
 /* Iterate.aug_lag_deriv_x (iterate.py:91-94): dL = grad + J'(rho c + y); optionally J'y (iterate.py:138,171)
  * and J'c (iterate.py:125) from the same pass over J.  dL / jty / jtc may be NULL. */
 int gf_aug_lag_grad(int B, int n, int m, const double* J, const double* grad, const double* cons, const double* y,

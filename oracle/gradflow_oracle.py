@@ -207,6 +207,79 @@ class ChainedRosenbrock(OracleProblem):
         return H
 
 
+class OCP(OracleProblem):
+    """Discretised nonlinear optimal-control problem (synthetic family, the reference ships no OCP).
+
+    Variables z = (x_1, u_0, x_2, u_1, ..., x_S, u_{S-1}) stage-interleaved, n = S (nx + nu); x_0 fixed.
+    Dynamics c_j = x_{j+1} - x_j - h (A_j x_j + B_j u_j + 0.1 sin(x_j)) = 0, j = 0..S-1  (m = S nx);
+    cost sum_j 1/2 (x_{j+1}' Q_j x_{j+1} + u_j' R_j u_j) with diagonal Q, R; |u| <= umax, states free.
+    All sums are accumulated sequentially in index order so that the CUDA evaluators reproduce them.
+    """
+
+    def __init__(self, A, Bm, Q, R, xinit, umax, h):
+        self.A = np.asarray(A, dtype=np.float64)
+        self.Bm = np.asarray(Bm, dtype=np.float64)
+        self.Q = np.asarray(Q, dtype=np.float64)
+        self.R = np.asarray(R, dtype=np.float64)
+        self.xinit = np.asarray(xinit, dtype=np.float64)
+        self.h = float(h)
+        self.S, self.nx, _ = self.A.shape
+        self.nu = self.Bm.shape[2]
+        S, nx, nu = self.S, self.nx, self.nu
+        lb = np.tile(np.concatenate([np.full(nx, -np.inf), np.full(nu, -float(umax))]), S)
+        ub = np.tile(np.concatenate([np.full(nx, np.inf), np.full(nu, float(umax))]), S)
+        super().__init__(lb, ub, num_cons=S * nx)
+
+    def _split(self, z):
+        Z = np.asarray(z, dtype=np.float64).reshape(self.S, self.nx + self.nu)
+        X1, U = Z[:, : self.nx], Z[:, self.nx:]
+        Xprev = np.vstack([self.xinit[None, :], X1[:-1]])
+        return X1, U, Xprev
+
+    def obj(self, z):
+        X1, U, _ = self._split(z)
+        return float(0.5 * np.sum(self.Q * X1 * X1) + 0.5 * np.sum(self.R * U * U))
+
+    def obj_grad(self, z):
+        X1, U, _ = self._split(z)
+        return np.concatenate([self.Q * X1, self.R * U], axis=1).reshape(-1)
+
+    def cons(self, z):
+        X1, U, Xprev = self._split(z)
+        ax = np.zeros((self.S, self.nx))
+        for k in range(self.nx):
+            ax = ax + self.A[:, :, k] * Xprev[:, k : k + 1]
+        bu = np.zeros((self.S, self.nx))
+        for k in range(self.nu):
+            bu = bu + self.Bm[:, :, k] * U[:, k : k + 1]
+        f = (ax + bu) + 0.1 * np.sin(Xprev)
+        return ((X1 - Xprev) - self.h * f).reshape(-1)
+
+    def cons_jac(self, z):
+        X1, U, Xprev = self._split(z)
+        S, nx, nu = self.S, self.nx, self.nu
+        w = nx + nu
+        J = np.zeros((S * nx, S * w))
+        eye = np.eye(nx)
+        for j in range(S):
+            rows = slice(j * nx, (j + 1) * nx)
+            J[rows, j * w : j * w + nx] = eye
+            J[rows, j * w + nx : (j + 1) * w] = -(self.h * self.Bm[j])
+            if j >= 1:
+                e = self.h * (self.A[j] + eye * (0.1 * np.cos(Xprev[j]))[None, :])
+                J[rows, (j - 1) * w : (j - 1) * w + nx] = -(eye + e)
+        return J
+
+    def lag_hess(self, z, y):
+        X1, U, _ = self._split(z)
+        S, nx = self.S, self.nx
+        Y = np.asarray(y, dtype=np.float64).reshape(S, nx)
+        c1 = 0.1 * self.h
+        dx = self.Q.copy()
+        dx[:-1] = self.Q[:-1] + (Y[1:] * c1) * np.sin(X1[:-1])
+        return np.diag(np.concatenate([dx, self.R], axis=1).reshape(-1))
+
+
 class Tame(OracleProblem):
     """f=(x0-x1)^2, c = x0+x1-1 (tests/pygradflow/tame.py:7-36)."""
 

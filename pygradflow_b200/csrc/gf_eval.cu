@@ -171,6 +171,107 @@ __global__ void rosen_hess_kernel(int n, const double* __restrict__ a, const dou
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// OCP family (cfg4): z = (x_1, u_0, ..., x_S, u_{S-1}), dynamics c_j = x_{j+1} - x_j - h (A_j x_j + B_j u_j +
+// 0.1 sin x_j), cost 1/2 sum (x'Qx + u'Ru).  Same accumulation order as the oracle's OCP class (sequential in k).
+__global__ void ocp_eval_kernel(int S, int nx, int nu, double h, const double* __restrict__ A,
+                                const double* __restrict__ Bm, const double* __restrict__ Q,
+                                const double* __restrict__ R, const double* __restrict__ xinit,
+                                const double* __restrict__ z, double* __restrict__ grad, double* __restrict__ cons,
+                                double* __restrict__ obj, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    __shared__ double red[32];
+    const int w = nx + nu, n = S * w, m = S * nx;
+    const double* zb = z + (size_t)b * n;
+    const double* Ab = A + (size_t)b * S * nx * nx;
+    const double* Bb = Bm + (size_t)b * S * nx * nu;
+    const double* Qb = Q + (size_t)b * S * nx;
+    const double* Rb = R + (size_t)b * S * nu;
+    const double* x0 = xinit + (size_t)b * nx;
+    double objp = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int j = i / w, c = i - j * w;
+        const double v = zb[i];
+        const double wgt = c < nx ? Qb[j * nx + c] : Rb[j * nu + (c - nx)];
+        const double gi = __dmul_rn(wgt, v);
+        grad[(size_t)b * n + i] = gi;
+        objp += 0.5 * gi * v;
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int j = i / nx, r = i - j * nx;
+        const double* xp = j == 0 ? x0 : zb + (size_t)(j - 1) * w;  // x_j
+        const double* uj = zb + (size_t)j * w + nx;
+        const double* Ar = Ab + ((size_t)j * nx + r) * nx;
+        const double* Br = Bb + ((size_t)j * nx + r) * nu;
+        double ax = 0.0, bu = 0.0;
+        for (int k = 0; k < nx; k++) ax = __dadd_rn(ax, __dmul_rn(Ar[k], xp[k]));
+        for (int k = 0; k < nu; k++) bu = __dadd_rn(bu, __dmul_rn(Br[k], uj[k]));
+        const double f = __dadd_rn(__dadd_rn(ax, bu), __dmul_rn(0.1, sin(xp[r])));
+        cons[(size_t)b * m + i] = __dsub_rn(__dsub_rn(zb[(size_t)j * w + r], xp[r]), __dmul_rn(h, f));
+    }
+    if (obj != nullptr) {
+        const double o = block_sum(objp, red);
+        if (threadIdx.x == 0) obj[b] = o;
+    }
+}
+
+// The non-zero blocks of the dense Jacobian J[b] (m x n, zero elsewhere): d c_j / d x_{j+1} = I,
+// d c_j / d u_j = -h B_j, d c_j / d x_j = -(I + h (A_j + 0.1 diag cos x_j)).
+__global__ void ocp_jac_kernel(int S, int nx, int nu, double h, const double* __restrict__ A,
+                               const double* __restrict__ Bm, const double* __restrict__ z,
+                               double* __restrict__ J, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    const int w = nx + nu, n = S * w, m = S * nx;
+    const double* zb = z + (size_t)b * n;
+    const double* Ab = A + (size_t)b * S * nx * nx;
+    const double* Bb = Bm + (size_t)b * S * nx * nu;
+    double* Jb = J + (size_t)b * m * n;
+    const int per = nx * (2 * nx + nu);  // entries per stage: [x_j | x_{j+1} | u_j] columns of nx rows
+    for (int e = threadIdx.x; e < S * per; e += blockDim.x) {
+        const int j = e / per, t = e - j * per, r = t / (2 * nx + nu), c = t - r * (2 * nx + nu);
+        double* row = Jb + (size_t)(j * nx + r) * n;
+        if (c < nx) {  // d / d x_j (previous stage block), j >= 1
+            if (j >= 1) {
+                const double d = (r == c) ? 1.0 : 0.0;
+                const double xe = zb[(size_t)(j - 1) * w + c];
+                const double ee = __dmul_rn(h, __dadd_rn(Ab[((size_t)j * nx + r) * nx + c],
+                                                        __dmul_rn(d, __dmul_rn(0.1, cos(xe)))));
+                row[(size_t)(j - 1) * w + c] = -__dadd_rn(d, ee);
+            }
+        } else if (c < 2 * nx) {
+            row[(size_t)j * w + (c - nx)] = (r == c - nx) ? 1.0 : 0.0;
+        } else {
+            row[(size_t)j * w + nx + (c - 2 * nx)] = -__dmul_rn(h, Bb[((size_t)j * nx + r) * nu + (c - 2 * nx)]);
+        }
+    }
+}
+
+// Diagonal of the Hessian of the Lagrangian (H must be zero elsewhere):
+// x_{j+1}: Q_j + (y_{j+1} * 0.1 h) sin(x_{j+1}) (no dynamics term for x_S), u_j: R_j.
+__global__ void ocp_hess_kernel(int S, int nx, int nu, double c1, const double* __restrict__ Q,
+                                const double* __restrict__ R, const double* __restrict__ z,
+                                const double* __restrict__ y, double* __restrict__ H, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    const int w = nx + nu, n = S * w, m = S * nx;
+    const double* zb = z + (size_t)b * n;
+    const double* yb = y + (size_t)b * m;
+    double* Hb = H + (size_t)b * n * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int j = i / w, c = i - j * w;
+        double v;
+        if (c < nx) {
+            v = Q[((size_t)b * S + j) * nx + c];
+            if (j + 1 < S) v = __dadd_rn(v, __dmul_rn(__dmul_rn(yb[(size_t)(j + 1) * nx + c], c1), sin(zb[i])));
+        } else {
+            v = R[((size_t)b * S + j) * nu + (c - nx)];
+        }
+        Hb[(size_t)i * n + i] = v;
+    }
+}
+
 inline int pick_threads(int n) {
     int t = ((n + 31) / 32) * 32;
     if (t < 64) t = 64;
@@ -221,5 +322,34 @@ extern "C" int gf_rosen_hess(int B, int n, const double* a, const double* b, con
     if (B <= 0 || n < 2 || !a || !b || !x || !H) return GF_ERR_ARG;
     if (nwork <= 0) return GF_OK;
     rosen_hess_kernel<<<nwork, pick_threads(n), 0, (cudaStream_t)stream>>>(n, a, b, x, H, GfWork{work, nwork_dev});
+    return gf_launch_status();
+}
+
+extern "C" int gf_ocp_eval(int B, int S, int nx, int nu, double h, const double* A, const double* Bm, const double* Q,
+                           const double* R, const double* xinit, const double* z, double* grad, double* cons,
+                           double* obj, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream) {
+    if (B <= 0 || S <= 0 || nx <= 0 || nu <= 0 || !A || !Bm || !Q || !R || !xinit || !z || !grad || !cons)
+        return GF_ERR_ARG;
+    if (nwork <= 0) return GF_OK;
+    ocp_eval_kernel<<<nwork, pick_threads(S * (nx + nu)), 0, (cudaStream_t)stream>>>(
+        S, nx, nu, h, A, Bm, Q, R, xinit, z, grad, cons, obj, GfWork{work, nwork_dev});
+    return gf_launch_status();
+}
+
+extern "C" int gf_ocp_jac(int B, int S, int nx, int nu, double h, const double* A, const double* Bm, const double* z,
+                          double* J, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream) {
+    if (B <= 0 || S <= 0 || nx <= 0 || nu <= 0 || !A || !Bm || !z || !J) return GF_ERR_ARG;
+    if (nwork <= 0) return GF_OK;
+    ocp_jac_kernel<<<nwork, 512, 0, (cudaStream_t)stream>>>(S, nx, nu, h, A, Bm, z, J, GfWork{work, nwork_dev});
+    return gf_launch_status();
+}
+
+extern "C" int gf_ocp_hess(int B, int S, int nx, int nu, double c1, const double* Q, const double* R, const double* z,
+                           const double* y, double* H, const int32_t* work, const int32_t* nwork_dev, int nwork,
+                           void* stream) {
+    if (B <= 0 || S <= 0 || nx <= 0 || nu <= 0 || !Q || !R || !z || !y || !H) return GF_ERR_ARG;
+    if (nwork <= 0) return GF_OK;
+    ocp_hess_kernel<<<nwork, pick_threads(S * (nx + nu)), 0, (cudaStream_t)stream>>>(S, nx, nu, c1, Q, R, z, y, H,
+                                                                                       GfWork{work, nwork_dev});
     return gf_launch_status();
 }

@@ -61,6 +61,19 @@ def rosen_hess(a, b, x, H, work: WorkList):
     _call("gf_rosen_hess", B, n, ptr(a), ptr(b), ptr(x), ptr(H), *_w(work))
 
 
+def ocp_eval(S, nx, nu, h, A, Bm, Q, R, xinit, z, grad, cons, obj, work: WorkList):
+    _call("gf_ocp_eval", z.shape[0], S, nx, nu, h, ptr(A), ptr(Bm), ptr(Q), ptr(R), ptr(xinit), ptr(z), ptr(grad),
+          ptr(cons), ptr(obj), *_w(work))
+
+
+def ocp_jac(S, nx, nu, h, A, Bm, z, J, work: WorkList):
+    _call("gf_ocp_jac", z.shape[0], S, nx, nu, h, ptr(A), ptr(Bm), ptr(z), ptr(J), *_w(work))
+
+
+def ocp_hess(S, nx, nu, c1, Q, R, z, y, H, work: WorkList):
+    _call("gf_ocp_hess", z.shape[0], S, nx, nu, c1, ptr(Q), ptr(R), ptr(z), ptr(y), ptr(H), *_w(work))
+
+
 def aug_lag_grad(J, grad, cons, y, rho, dL, jty, jtc, work: WorkList):
     B, n = grad.shape
     m = 0 if cons is None else cons.shape[1]

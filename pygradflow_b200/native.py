@@ -23,6 +23,9 @@ SIGNATURES = {
     "gf_qp_eval": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_rosen_eval": [_I, _I, _P, _P, _P, _P, _P] + _WORK,
     "gf_rosen_hess": [_I, _I, _P, _P, _P, _P] + _WORK,
+    "gf_ocp_eval": [_I, _I, _I, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_ocp_jac": [_I, _I, _I, _I, _D, _P, _P, _P, _P] + _WORK,
+    "gf_ocp_hess": [_I, _I, _I, _I, _D, _P, _P, _P, _P, _P] + _WORK,
     "gf_aug_lag_grad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_residual": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P] + _WORK,
     "gf_index_sets": [_I, _I, _I, _P, _P, _P, _P] + _WORK,

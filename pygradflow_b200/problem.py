@@ -118,6 +118,54 @@ class BatchedRosenbrock(BatchedProblem):
         return q
 
 
+class BatchedOCP(BatchedProblem):
+    """Discretised nonlinear optimal-control problems (cfg4): stage-interleaved variables
+    z = (x_1, u_0, ..., x_S, u_{S-1}), equality dynamics, bounds on the controls only.
+
+    Device twin of the oracle's ``OCP`` class; J and H are kept dense (block-banded J, diagonal H), only their
+    non-zero entries are rewritten per evaluation."""
+
+    def __init__(self, A, Bm, Q, R, xinit, umax, h, device="cuda"):
+        A, Bm, Q, R, xinit = (_dev(t, device) for t in (A, Bm, Q, R, xinit))
+        B, S, nx, _ = A.shape
+        nu = Bm.shape[3]
+        f64 = dict(dtype=torch.float64)
+        lb1 = torch.cat([torch.full((nx,), -float("inf"), **f64), torch.full((nu,), -float(umax), **f64)]).repeat(S)
+        lb = lb1.to(device).expand(B, -1).contiguous()
+        super().__init__(lb, -lb, S * nx)
+        self.A, self.Bm, self.Q, self.R, self.xinit = A, Bm, Q, R, xinit
+        self.S, self.nx, self.nu, self.h, self.umax = S, nx, nu, float(h), float(umax)
+        self._zeroed = set()
+
+    def _zero_once(self, out):
+        if out.data_ptr() not in self._zeroed:  # the kernels write the non-zero pattern only
+            out.zero_()
+            self._zeroed.add(out.data_ptr())
+
+    def eval(self, x, grad, cons, obj, work):
+        K.ocp_eval(self.S, self.nx, self.nu, self.h, self.A, self.Bm, self.Q, self.R, self.xinit, x, grad, cons, obj,
+                   work)
+
+    def jac(self, x, out, work):
+        self._zero_once(out)
+        K.ocp_jac(self.S, self.nx, self.nu, self.h, self.A, self.Bm, x, out, work)
+        return out
+
+    def lag_hess(self, x, y, out, work):
+        self._zero_once(out)
+        K.ocp_hess(self.S, self.nx, self.nu, 0.1 * self.h, self.Q, self.R, x, y, out, work)
+        return out
+
+    def select(self, idx):
+        q = object.__new__(BatchedOCP)
+        BatchedProblem.__init__(q, self.var_lb[idx].contiguous(), self.var_ub[idx].contiguous(), self.m)
+        for name in ("A", "Bm", "Q", "R", "xinit"):
+            setattr(q, name, getattr(self, name)[idx].contiguous())
+        q.S, q.nx, q.nu, q.h, q.umax = self.S, self.nx, self.nu, self.h, self.umax
+        q._zeroed = set()
+        return q
+
+
 class BatchedDense(BatchedProblem):
     """Problem whose derivatives are supplied as dense device tensors by the caller (the batch = 1
     plug-in path evaluates a Python ``Problem`` on the host and uploads grad / cons / J / H here)."""

@@ -91,4 +91,14 @@ def ocp_instance(k: int, stages: int = 128, nx: int = 8, nu: int = 8, h: float =
     R = rng.uniform(0.1, 0.5, (stages, nu))
     xinit = rng.uniform(-1.0, 1.0, nx)
     umax = 0.4
-    return dict(A=Aj, B=Bj, Q=Q, R=R, xinit=xinit, umax=umax, h=h, stages=stages, nx=nx, nu=nu)
+    n = stages * (nx + nu)
+    return dict(A=Aj, B=Bj, Q=Q, R=R, xinit=xinit, umax=umax, h=h, stages=stages, nx=nx, nu=nu,
+                x0=np.zeros(n), y0=np.zeros(stages * nx))
+
+
+def ocp_batch(ks, stages: int = 128, nx: int = 8, nu: int = 8, h: float = 0.05):
+    """Stack ocp_instance over ``ks`` -> dict of [B, ...] arrays (scalars umax, h, stages, nx, nu unchanged)."""
+    items = [ocp_instance(int(k), stages, nx, nu, h) for k in ks]
+    out = {key: np.stack([it[key] for it in items]) for key in ("A", "B", "Q", "R", "xinit", "x0", "y0")}
+    out.update({key: items[0][key] for key in ("umax", "h", "stages", "nx", "nu")})
+    return out

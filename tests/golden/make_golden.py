@@ -95,6 +95,32 @@ class RefChainedRosenbrock(Problem):
         return sps.diags([off, main, off], [-1, 0, 1], format="csc")
 
 
+class RefOCP(Problem):
+    """cfg4 family as a reference Problem: the formulas of the oracle's OCP class (identical arithmetic), returned
+    as scipy.sparse matrices like the reference's own fixtures."""
+
+    def __init__(self, d):
+        from oracle import gradflow_oracle as orc
+
+        self.p = orc.OCP(d["A"], d["B"], d["Q"], d["R"], d["xinit"], d["umax"], d["h"])
+        super().__init__(self.p.var_lb, self.p.var_ub, num_cons=self.p.num_cons)
+
+    def obj(self, x):
+        return self.p.obj(x)
+
+    def obj_grad(self, x):
+        return self.p.obj_grad(x)
+
+    def cons(self, x):
+        return self.p.cons(x)
+
+    def cons_jac(self, x):
+        return sps.csr_matrix(self.p.cons_jac(x))
+
+    def lag_hess(self, x, y):
+        return sps.csc_matrix(self.p.lag_hess(x, y))
+
+
 STATUS_CODE = {s: s.value for s in SolverStatus}
 
 
@@ -304,12 +330,24 @@ def golden_full_size_qp():
     np.savez_compressed(os.path.join(HERE, "qp512.npz"), **flat("qp_n512_m256_k0/Simplified", res))
 
 
+def golden_ocp():
+    """cfg4-style discretised optimal-control problems (small): full traces of the real reference."""
+    out = {}
+    for (S, nx, nu, k) in [(6, 3, 2, 0), (16, 4, 3, 1)]:
+        d = synth.ocp_instance(k, stages=S, nx=nx, nu=nu)
+        for newton in ("Simplified", "Full"):
+            res = trace_solve(RefOCP(d), params_for(newton), d["x0"], d["y0"], keep_every=4 if S > 6 else 1)
+            out.update(flat(f"ocp_S{S}_nx{nx}_nu{nu}_k{k}/{newton}", res))
+    np.savez_compressed(os.path.join(HERE, "ocp.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_linear_solver()
     golden_newton()
     golden_globalized()
     golden_solves()
     golden_full_size_qp()
+    golden_ocp()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -154,6 +154,19 @@ def test_solve_rosenbrock_docs_example(golden):
     assert np.array2string(res.x, precision=8) == "[0.99999959 0.99999917]"
 
 
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("S,nx,nu,k", [(6, 3, 2, 0), (16, 4, 3, 1)])
+def test_solve_ocp(golden, S, nx, nu, k, newton):
+    """cfg4 family (nonlinear equality constraints, bounds on the controls) against the real reference."""
+    d = synth.ocp_instance(k, stages=S, nx=nx, nu=nu)
+    p = orc.OCP(d["A"], d["B"], d["Q"], d["R"], d["xinit"], d["umax"], d["h"])
+    # the 56-iteration trajectory of the larger instance amplifies the last-bit differences of the linear solves
+    # (SuperLU's ordering on the sparse vs the dense matrix) to ~1e-10 by iteration 20: compared at 1e-8
+    res = _check_solve(golden("ocp"), f"ocp_S{S}_nx{nx}_nu{nu}_k{k}/{newton}", p, d["x0"], d["y0"], newton=newton,
+                       tol=RTOL if S == 6 else 1e-8)
+    assert res.status == 1
+
+
 def test_solve_tame(golden):
     res = _check_solve(golden("solves"), "tame", orc.Tame(), np.zeros(2), np.zeros(1))
     assert np.allclose(res.x, [0.5, 0.5], atol=1e-6)  # tests/pygradflow/instances.py:57-68

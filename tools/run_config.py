@@ -18,7 +18,7 @@ import torch
 
 from pygradflow_b200 import synth
 from pygradflow_b200.params import LinearSolverType, NewtonType, Params
-from pygradflow_b200.problem import BatchedQP, BatchedRosenbrock
+from pygradflow_b200.problem import BatchedOCP, BatchedQP, BatchedRosenbrock
 from pygradflow_b200.solver import BatchedSolver
 
 
@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--B", type=int, default=4096)
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--m", type=int, default=None)
+    ap.add_argument("--stages", type=int, default=128)
     ap.add_argument("--linear", default="Auto")
     ap.add_argument("--newton", default="Simplified")
     ap.add_argument("--check", type=int, default=4)
@@ -41,6 +42,11 @@ def main():
         d = synth.rosenbrock_batch(range(B), n)
         prob = BatchedRosenbrock(d["a"], d["b"], d["lb"], d["ub"])
         x0, y0 = d["x0"], None
+    elif args.cfg == 4:
+        d = synth.ocp_batch(range(B), stages=args.stages)
+        prob = BatchedOCP(d["A"], d["B"], d["Q"], d["R"], d["xinit"], d["umax"], d["h"])
+        n, m = prob.n, prob.m
+        x0, y0 = d["x0"], d["y0"]
     else:
         n, m = args.n or 512, args.m if args.m is not None else 256
         d = synth.qp_batch(range(B), n, m)
@@ -67,7 +73,11 @@ def main():
 
         chk = []
         for b in range(min(args.check, B)):
-            if args.cfg == 2:
+            if args.cfg == 4:
+                p = orc.OCP(d["A"][b], d["B"][b], d["Q"][b], d["R"][b], d["xinit"][b], d["umax"], d["h"])
+                t1 = time.perf_counter()
+                ref = orc.Solver(p, orc.OracleParams()).solve(d["x0"][b], d["y0"][b])
+            elif args.cfg == 2:
                 p = orc.ChainedRosenbrock(d["a"][b], d["b"][b], d["lb"][b], d["ub"][b])
                 t1 = time.perf_counter()
                 ref = orc.Solver(p, orc.OracleParams()).solve(d["x0"][b], np.zeros(0))

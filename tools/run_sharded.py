@@ -1,0 +1,57 @@
+"""NCCL check of the sharded solve (torchrun, one rank per GPU): every rank solves its block, one all-gather at the
+end; rank 0 also solves the whole batch alone and compares bit for bit.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/run_sharded.py [--B 64] [--n 128] [--m 64]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from pygradflow_b200 import synth
+from pygradflow_b200.dist import solve_sharded
+from pygradflow_b200.problem import BatchedQP
+from pygradflow_b200.solver import BatchedSolver
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--B", type=int, default=64)
+ap.add_argument("--n", type=int, default=128)
+ap.add_argument("--m", type=int, default=64)
+args = ap.parse_args()
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local_rank = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+d = synth.qp_batch(range(args.B), args.n, args.m)
+
+
+def factory(lo, hi):
+    return BatchedQP(d["H"][lo:hi], d["A"][lo:hi], d["g"][lo:hi], d["b"][lo:hi], d["lb"][lo:hi], d["ub"][lo:hi], device=dev)
+
+
+x0 = torch.as_tensor(d["x0"], device=dev)
+y0 = torch.as_tensor(d["y0"], device=dev)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+res = solve_sharded(args.B, factory, None, x0, y0)
+torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+if rank == 0:
+    full = BatchedSolver(factory(0, args.B)).solve(x0, y0)
+    out = dict(world=world, B=args.B, n=args.n, m=args.m, wall_s=wall, backend=dist.get_backend() if world > 1 else None,
+               x_equal=bool(torch.equal(res.x, full.x)), y_equal=bool(torch.equal(res.y, full.y)),
+               status_equal=bool(torch.equal(res.status, full.status)),
+               iterations_equal=bool(torch.equal(res.iterations, full.iterations)),
+               optimal=int((res.status == 1).sum().item()))
+    print(json.dumps(out))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
