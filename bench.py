@@ -218,6 +218,16 @@ def measure_fp64_peak(device):
     return 2 * N ** 3 / best * 1e-9  # TFLOP/s
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of one whole factorisation of the bench batch, summed over its launches, from the
+    committed ncu capture (profiles/r01_ncu_ldlt_factor_dram.json); None when the capture is not at hand."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_ldlt_factor_dram.json")) as f:
+            return float(json.load(f)["dram_bytes_per_factorisation"])
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -387,10 +397,11 @@ def run_gpu_arm(args):
                        "mean_inactive": nIbar, "mean_kkt_order": Nbar, "lu_fallback_instances": n_fallback,
                        "failed_instances": nfail,
                        "l2": "inputs (13 GB of H, A per step) are far larger than the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "tensor", "kernel": "batched LDL' factorisation = gf_ldlt_factor: ldlt_panel_kernel + "
-                                                      "ldlt_fused_kernel (DMMA) + ldlt_diag_kernel",
+            "roofline": {"bound": "tensor", "kernel": "batched LDL' factorisation = gf_ldlt_factor: ldlt_diag0_kernel + one "
+                                                      "ldlt_column_kernel (DMMA) per 64-wide block column, issued as "
+                                                      "two interleaved half-batches",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": ncu_traffic(),
                          "peak_source": "FP64 cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no "
                                         "FP64 entry; profiles/r01_fp64_peak.json: 35.4 TFLOP/s)",
                          "algorithmic_flops_per_step": flops_ldlt if linear != LinearSolverType.LU else 2 * flops_ldlt,

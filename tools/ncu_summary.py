@@ -7,6 +7,8 @@ KEYS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
