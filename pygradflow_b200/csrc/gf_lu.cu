@@ -114,21 +114,26 @@ __global__ void lu_smem_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfi
 template <int NB>
 __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                        double* __restrict__ K, int32_t* __restrict__ piv,
-                                                       int32_t* __restrict__ info, GfWork work) {
+                                                       int32_t* __restrict__ info, GfWork work, int jstart,
+                                                       int one_column) {
+    // one_column = 0: the whole factorisation (FMA trailing update in this kernel);
+    // one_column = 1: block column jstart only -- panel, interchanges, U12; the trailing update is lu_update_kernel
     const int b = gf_instance(work, blockIdx.x);
     if (b < 0) return;
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
-    extern __shared__ double P[];              // NB * N doubles (panel), then 8*NB doubles (U strip)
-    double* Us = P + (size_t)NB * (Nfixed | 1);  // Nfixed = batch-wide Nmax (launch_panel)
+    if (jstart >= N) return;
+    extern __shared__ double P[];              // NB * rows doubles (panel), then 8*NB doubles (U strip)
+    double* Us = P + (size_t)NB * ((Nfixed - jstart) | 1);  // Nfixed = batch-wide Nmax (launch_panel)
     __shared__ MaxLoc scratch[32];
     __shared__ int32_t spiv[NB];
     __shared__ int32_t sinfo;
     double* Kb = K + (size_t)b * ld * ld;
     int32_t* pb = piv + (size_t)b * ld;
     const int T = blockDim.x;
-    if (threadIdx.x == 0) sinfo = 0;
+    if (threadIdx.x == 0) sinfo = jstart == 0 ? 0 : info[b];
     __syncthreads();
-    for (int j0 = 0; j0 < N; j0 += NB) {
+    const int jend = one_column ? min(N, jstart + NB) : N;
+    for (int j0 = jstart; j0 < jend; j0 += NB) {
         const int jb = min(NB, N - j0);
         const int rows = N - j0;
         const int pitch = rows | 1;
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
         __syncthreads();
         // ---- trailing update M22 -= L21 U12, strips of 8 storage rows, 4 x 8 register tile per thread
         const int tr = rows - jb;  // trailing extent
-        if (tr > 0) {
+        if (tr > 0 && !one_column) {
             for (int c0 = j0 + jb; c0 < N; c0 += 8) {
                 const int nc = min(8, N - c0);
                 for (int e = threadIdx.x; e < 8 * NB; e += T) {
@@ -391,14 +396,104 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
     for (int i = threadIdx.x; i < N; i += blockDim.x) rb[i] = v[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Right-looking trailing update on the FP64 tensor pipe: M22 -= L21 U12 for block column j0 (width NB).  In storage
+// terms (storage row c = column c of M): C[c][i] -= sum_k U[c][k] L[k][i] with U[c][k] = K[c][j0 + k] (row-major, the
+// A operand) and L[k][i] = K[j0 + k][i] (the B operand).  One CTA per 64 (c) x 128 (i) tile, 2 x 4 warps of 32 x 32.
+__device__ __forceinline__ double lu_dneg(double x) {
+    return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ULL);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256, 2) lu_update_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int j0,
+                                                            double* __restrict__ K, GfWork work) {
+    const int b = gf_instance(work, blockIdx.z);
+    if (b < 0) return;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    const int t0 = j0 + NB;
+    const int c0 = t0 + blockIdx.y * 64, i0 = t0 + blockIdx.x * 128;
+    if (c0 >= N || i0 >= N) return;
+    constexpr int AP = NB + 4;   // pitch of the A tile (== 4 or 12 mod 16: conflict-free fragment loads)
+    constexpr int BP = 128 + 4;  // pitch of the B tile
+    extern __shared__ double usm[];
+    double* As = usm;             // 64 x AP
+    double* Bs = usm + 64 * AP;   // NB x BP
+    double* Kb = K + (size_t)b * ld * ld;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm = wid >> 2, wn = wid & 3, g = lane >> 2, q = lane & 3;
+    for (int e = tid; e < 64 * NB; e += 256) {
+        const int c = e / NB, k = e - c * NB;
+        As[c * AP + k] = (c0 + c < N) ? Kb[(size_t)(c0 + c) * ld + j0 + k] : 0.0;
+    }
+    for (int e = tid; e < NB * 128; e += 256) {
+        const int k = e >> 7, i = e & 127;
+        Bs[k * BP + i] = (i0 + i < N) ? Kb[(size_t)(j0 + k) * ld + i0 + i] : 0.0;
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const int c = c0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int i = i0 + wn * 32 + ni * 8 + 2 * q;
+            const double* cp = Kb + (size_t)c * ld + i;
+            acc[mi][ni][0] = (c < N && i < N) ? cp[0] : 0.0;
+            acc[mi][ni][1] = (c < N && i + 1 < N) ? cp[1] : 0.0;
+        }
+    }
+    __syncthreads();
+    const double* as = As + (wm * 32 + g) * AP + q;
+    const double* bs = Bs + q * BP + wn * 32 + g;
+#pragma unroll
+    for (int kk = 0; kk < NB; kk += 4) {
+        double a[4], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) a[mi] = lu_dneg(as[mi * 8 * AP + kk]);
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) bf[ni] = bs[kk * BP + ni * 8];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const int c = c0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int i = i0 + wn * 32 + ni * 8 + 2 * q;
+            double* cp = Kb + (size_t)c * ld + i;
+            if (c < N && i < N) cp[0] = acc[mi][ni][0];
+            if (c < N && i + 1 < N) cp[1] = acc[mi][ni][1];
+        }
+    }
+}
+
 template <int NB>
 int launch_panel(int ld, int Nmax, const int32_t* Nvec, int Nfixed, double* K, int32_t* piv, int32_t* info,
-                 GfWork w, int nwork, cudaStream_t s) {
-    const size_t smem = ((size_t)NB * (Nmax | 1) + 8 * NB) * sizeof(double);
+                 GfWork w, int nwork, cudaStream_t s, int jstart = 0, int one_column = 0) {
+    const size_t smem = ((size_t)NB * ((Nmax - jstart) | 1) + 8 * NB) * sizeof(double);
     if (smem > 227 * 1024) return GF_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(lu_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lu_panel_kernel<NB><<<nwork, 256, smem, s>>>(ld, Nvec, Nfixed, K, piv, info, w);
+    lu_panel_kernel<NB><<<nwork, 256, smem, s>>>(ld, Nvec, Nfixed, K, piv, info, w, jstart, one_column);
     return gf_launch_status();
+}
+
+// One block column of the multi-launch factorisation: pivoted panel (one CTA per matrix), then the DMMA update.
+template <int NB>
+int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info, GfWork w, int nwork,
+                  cudaStream_t s, int j0) {
+    int rc = launch_panel<NB>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s, j0, 1);
+    if (rc != GF_OK) return rc;
+    const int tr = Nmax - j0 - NB;
+    if (tr > 0) {
+        dim3 grid((tr + 127) / 128, (tr + 63) / 64, nwork);
+        constexpr int USMEM = (64 * (NB + 4) + NB * 132) * (int)sizeof(double);
+        cudaFuncSetAttribute(lu_update_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, USMEM);
+        lu_update_kernel<NB><<<grid, 256, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w);
+        rc = gf_launch_status();
+    }
+    return rc;
 }
 
 }  // namespace
@@ -416,10 +511,19 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
         lu_smem_kernel<<<nwork, threads, full, s>>>(ld, Nvec, Nmax, K, piv, info, w);
         return gf_launch_status();
     }
-    if (Nmax <= 830) return launch_panel<32>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
-    if (Nmax <= 1700) return launch_panel<16>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
-    if (Nmax <= 3500) return launch_panel<8>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
-    return GF_ERR_UNSUPPORTED;
+    if (Nmax > 3500 || nwork > 65535) return GF_ERR_UNSUPPORTED;
+    // Multi-launch right-looking factorisation: per block column a pivoted panel kernel (panel resident in shared
+    // memory, so its width follows the rows that are left) and the DMMA trailing update.
+    int j0 = 0;
+    while (j0 < Nmax) {
+        const int rows = Nmax - j0;
+        int rc;
+        if (rows <= 830) { rc = launch_column<32>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 32; }
+        else if (rows <= 1700) { rc = launch_column<16>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 16; }
+        else { rc = launch_column<8>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 8; }
+        if (rc != GF_OK) return rc;
+    }
+    return GF_OK;
 }
 
 extern "C" int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, const int32_t* piv,
