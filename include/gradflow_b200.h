@@ -205,6 +205,14 @@ int gf_armijo_residual(int B, int n, int m, const double* xt, const double* yt, 
                        int32_t* trials, int32_t* state, double* next_res, const int32_t* work,
                        const int32_t* nwork_dev, int nwork, void* stream);
 
+/* ---- host-buffer entry (the reference hands its step solver host arrays: scaled_step_solver.py:76-79) ---- */
+
+/* H [cnt, n, n] is symmetric (problem.py:174-192): copy only its lower block triangle (row blocks of `blk` rows,
+ * columns up to the end of the diagonal block) from pinned host memory with one strided copy per row block, and
+ * rebuild the blocks above the diagonal on the device (blk a multiple of 32). */
+int gf_h2d_sym_lower(double* dst, const double* src_host, int cnt, int n, int blk, void* stream);
+int gf_symmetrize_lower(double* H, int cnt, int n, int blk, void* stream);
+
 /* helpers of the batched driver: ordered compaction of { b in parent (or 0..B-1) : (lo <= key[b] <= hi) != invert } */
 int gf_build_worklist(int B, const int32_t* key, int lo, int hi, int invert, const int32_t* parent,
                       const int32_t* parent_count, int32_t* list, int32_t* count, void* stream);

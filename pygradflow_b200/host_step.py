@@ -13,6 +13,7 @@ from typing import Dict
 
 import torch
 
+from . import kernels as K
 from .newton import NewtonKKTStepper
 from .params import LinearSolverType
 from .problem import BatchedQP
@@ -58,8 +59,9 @@ class HostNewtonKKT:
         return out
 
     def bytes_per_step(self, B: int):
+        """Bytes that cross PCIe per step (H: lower block triangle only, it is symmetric)."""
         n, m = self.n, self.m
-        h2d = 8 * B * (n * n + m * n + 4 * n + 2 * m + 2)
+        h2d = K.h2d_sym_lower_bytes(B, n) + 8 * B * (m * n + 4 * n + 2 * m + 2)
         d2h = 8 * B * (n + m + 2) + 4 * B
         return h2d, d2h
 
@@ -78,8 +80,8 @@ class HostNewtonKKT:
             with torch.cuda.stream(sc):
                 sc.wait_event(s.done)  # the slot's previous chunk has been consumed
                 q = s.qp
-                pairs = [(q.H, "H"), (q.g, "g"), (q.var_lb, "lb"), (q.var_ub, "ub"), (s.x, "x"), (s.lamb, "lamb"),
-                         (s.rho, "rho")]
+                K.h2d_sym_lower(q.H, host["H"][lo:hi], cnt)
+                pairs = [(q.g, "g"), (q.var_lb, "lb"), (q.var_ub, "ub"), (s.x, "x"), (s.lamb, "lamb"), (s.rho, "rho")]
                 if m > 0:
                     pairs += [(q.A, "A"), (q.b, "b"), (s.y, "y")]
                 for dst, key in pairs:
@@ -87,6 +89,7 @@ class HostNewtonKKT:
                 s.ready.record(sc)
             with torch.cuda.stream(sk):
                 sk.wait_event(s.ready)
+                K.symmetrize_lower(s.qp.H, cnt)
                 s.stepper.work.nwork = cnt
                 xn, yn, diff, fnorm, info = s.stepper.step(s.x, s.y, s.lamb, s.rho)
                 out["xn"][lo:hi].copy_(xn[:cnt], non_blocking=True)

@@ -201,3 +201,26 @@ def armijo_residual(xt, yt, x0, y0, dL, cons, lb, ub, dt, res, inner, newton_tol
     _call("gf_armijo_residual", B, n, m, ptr(xt), ptr(yt), ptr(x0), ptr(y0), ptr(dL), ptr(cons), ptr(lb), ptr(ub),
           ptr(dt), ptr(res), ptr(inner), newton_tol, max_trials, ptr(alpha), ptr(trials), ptr(state), ptr(next_res),
           *_w(work))
+
+
+SYM_BLOCK = 64  # row-block height of the symmetric transfer
+
+
+def h2d_sym_lower(dst, src_host, cnt: int):
+    """dst[:cnt] (device, [*, n, n]) <- lower block triangle of the pinned host tensor src_host[:cnt]."""
+    n = dst.shape[1]
+    assert src_host.is_pinned() and src_host.is_contiguous() and dst.is_contiguous()
+    _call("gf_h2d_sym_lower", ptr(dst), src_host.data_ptr(), cnt, n, SYM_BLOCK, _stream(), launches=0)
+
+
+def h2d_sym_lower_bytes(cnt: int, n: int) -> int:
+    tot = 0
+    for r0 in range(0, n, SYM_BLOCK):
+        r1 = min(n, r0 + SYM_BLOCK)
+        tot += r1 * (r1 - r0) * 8
+    return tot * cnt
+
+
+def symmetrize_lower(H, cnt: int):
+    """Rebuild the blocks above the diagonal of H[:cnt] from the transferred lower block triangle."""
+    _call("gf_symmetrize_lower", ptr(H), cnt, H.shape[1], SYM_BLOCK, _stream())
