@@ -44,7 +44,14 @@ __device__ unsigned long long g_ldlt_trace[64 * 2 * 16];
         }                                                                                \
     } while (0)
 #define TRACE_COUNT() do { if (threadIdx.x == 0) atomicAdd(&g_ldlt_trace[t_slot_ + 15], 1ULL); } while (0)
+__device__ unsigned long long g_ldlt_fine[8];
+#define FINE_DECL __shared__ long long fine_ts_[80]; int fine_n_ = 0;
+#define FINE_MARK() do { if (threadIdx.x == 0 && fine_n_ < 80) fine_ts_[fine_n_] = clock64(); fine_n_++; } while (0)
+#define FINE_FLUSH() do { if (threadIdx.x == 0) { for (int i_ = 1; i_ < fine_n_ && i_ < 80; i_++) atomicAdd(&g_ldlt_fine[(i_ - 1) % 5], (unsigned long long)(fine_ts_[i_] - fine_ts_[i_ - 1])); } } while (0)
 #else
+#define FINE_DECL
+#define FINE_MARK()
+#define FINE_FLUSH()
 #define TRACE_BEGIN(kk, role)
 #define TRACE_MARK(i)
 #define TRACE_COUNT()
@@ -154,6 +161,8 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
         p1 = v.y;
     }
     __syncthreads();  // X zeroed, flags initialised
+    FINE_DECL
+    FINE_MARK();
     for (int jb = 0; jb < 8; jb++) {
         const int c0 = jb * 8;
         if (wid == 0) {
@@ -169,13 +178,21 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 const double wc1 = __shfl_sync(0xffffffffu, pj, (2 * q + 1) * 4 + (j >> 1));
                 const double yj0 = __shfl_sync(0xffffffffu, y0, j * 4 + q);
                 const double yj1 = __shfl_sync(0xffffffffu, y1, j * 4 + q);
-                const double rj = fast_rcp(dj);
+                // 1 / dj = r0 (1 + e + e^2) with e = 1 - dj r0 (cubic: the MUFU seed has ~20 bits).  The pivot-to-pivot
+                // chain is shfl -> MUFU -> e -> s -> fma: the products with r0 and the subtraction run beside it.
+                double r0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(dj));
+                if (dj == 0.0) r0 = 0.0;
+                const double e = fma(-dj, r0, 1.0);
+                const double sc = fma(e, e, e);
+                const double u0 = (wr * wc0) * r0, u1 = (wr * wc1) * r0;
+                const double rj = fma(r0, sc, r0);
                 if (j == 2 * q) rc0 = rj;
                 if (j == 2 * q + 1) rc1 = rj;
                 const double lr = wr * rj;
                 if (g > j) {
-                    if (2 * q > j) p0 = fma(-lr, wc0, p0);
-                    if (2 * q + 1 > j) p1 = fma(-lr, wc1, p1);
+                    if (2 * q > j) p0 = fma(-u0, sc, p0 - u0);
+                    if (2 * q + 1 > j) p1 = fma(-u1, sc, p1 - u1);
                     y0 = fma(-lr, yj0, y0);
                     y1 = fma(-lr, yj1, y1);
                 }
@@ -197,7 +214,9 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
             else if (2 * q == g) S[(c0 + g) * DP + c0 + 2 * q] = l0;
             *reinterpret_cast<double2*>(X + (c0 + g) * DP + c0 + 2 * q) = make_double2(y0, y1);
         }
+        FINE_MARK();  // [0] pivot block
         __syncthreads();  // pivot block published; all trailing updates of the previous panel are done
+        FINE_MARK();  // [1] barrier
         if (jb == 7) break;
         // panel below the pivot block: row tile t = jb + 1 + wid
         {
@@ -215,7 +234,9 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 *reinterpret_cast<double2*>(Wn + (t * 8 + g) * WNP + 2 * q) = make_double2(dneg(w0), dneg(w1));
             }
         }
+        FINE_MARK();  // [2] panel
         __syncthreads();
+        FINE_MARK();  // [3] barrier
         // trailing update by 8 x 8 tiles (ti, tj), jb < tj <= ti < 8: warp 0 takes the next pivot block and keeps
         // it in registers, warps 1..7 share the rest
         {
@@ -238,7 +259,9 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
             }
         }
         // (no barrier: warp 0 goes on with the pivot block in registers; the others wait at the next barrier)
+        FINE_MARK();  // [4] update (warp 0: the next pivot block only)
     }
+    FINE_FLUSH();
     TRACE_MARK(8);
 
     // ---- X = inv(L) (unit lower) by block recursion: X[hi, lo] = -X[hi, hi] (L[hi, lo] X[lo, lo]) for the pairs of
@@ -675,17 +698,21 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
                                                              int k, double* __restrict__ K, double* __restrict__ dvec,
                                                              int32_t* __restrict__ info, int32_t* __restrict__ nneg,
                                                              const int32_t* __restrict__ npos_expected, GfWork work,
-                                                             int woff) {
-    const int b = gf_instance(work, woff + blockIdx.y);
+                                                             int woff, int cnt, int tiles) {
+    // 1-D grid of cnt * tiles CTAs: the cnt chain CTAs (the long ones) come first, then the panel tiles
+    const int lin = blockIdx.x;
+    const int wi = lin < cnt ? lin : (lin - cnt) / (tiles - 1);
+    const int tile = lin < cnt ? 0 : 1 + (lin - cnt) % (tiles - 1);
+    const int b = gf_instance(work, woff + wi);
     if (b < 0) return;
     extern __shared__ double sm[];
-    if (blockIdx.x == 0) {
+    if (tile == 0) {
         ldlt_chain_body(sm, b, ld, Nvec, Nfixed, k, K, dvec, info, nneg, npos_expected);
         return;
     }
     const int Np = padded_order(Nvec, Nfixed, b, ld);
     const int j0 = k * NB;
-    const int i0 = j0 + 2 * NB + (blockIdx.x - 1) * TM;
+    const int i0 = j0 + 2 * NB + (tile - 1) * TM;
     if (i0 >= Np) return;
     double* Kb = K + (size_t)b * ld * ld;
     const double* db = dvec + (size_t)b * ld;
@@ -833,8 +860,8 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
         const int below = Np - (k + 2) * NB;              // rows under block k+1
         const int tiles = 1 + (below + TM - 1) / TM;      // chain CTA + 128-row panel tiles
         for (int i = 0; i < nlane; i++)
-            ldlt_column_kernel<<<dim3(tiles, cnt[i]), 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
-                                                                              npos_expected, w, off[i]);
+            ldlt_column_kernel<<<tiles * cnt[i], 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
+                                                                         npos_expected, w, off[i], cnt[i], tiles);
     }
     if (L != nullptr) {
         for (int i = 0; i < 2; i++) {

@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
         fill_kernel<<<B, 256>>>(K, ld, N, npos);
         unsigned long long zero[64 * 2 * 16] = {0};
         cudaMemcpyToSymbol(g_ldlt_trace, zero, sizeof(zero));
+        cudaMemcpyToSymbol(g_ldlt_fine, zero, 8 * sizeof(unsigned long long));
         cudaEventRecord(e0);
         int rc = gf_ldlt_factor(B, ld, N, nullptr, K, dvec, info, nneg, nullptr, nullptr, nullptr, B, nullptr);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
@@ -44,6 +45,10 @@ int main(int argc, char** argv) {
     int bad = 0; for (int i = 0; i < B; i++) bad += h[i] != 0;
     printf("B=%d N=%d factor %.3f ms  %.2f TFLOP/s  bad=%d  err=%s\n", B, N, best, B * (double)N * N * N / 3 / best * 1e-9, bad,
            cudaGetErrorString(cudaGetLastError()));
+    unsigned long long fine[8];
+    cudaMemcpyFromSymbol(fine, g_ldlt_fine, sizeof(fine));
+    printf("factor detail, thread 0, summed over all diagonal blocks and CTAs [Mcycles]: pivot block %.1f  barrier %.1f  panel %.1f  barrier %.1f  update %.1f\n",
+           fine[0] * 1e-6, fine[1] * 1e-6, fine[2] * 1e-6, fine[3] * 1e-6, fine[4] * 1e-6);
     static unsigned long long t[64 * 2 * 16];
     cudaMemcpyFromSymbol(t, g_ldlt_trace, sizeof(t));
     printf("mean cycles per CTA.  chain(k): prologue mainloop epi-load trsm S-update | factor inverse writeback ; panel(k): prologue mainloop epi-load trsm\n");
