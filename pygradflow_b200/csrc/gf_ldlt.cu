@@ -185,17 +185,18 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 if (dj == 0.0) r0 = 0.0;
                 const double e = fma(-dj, r0, 1.0);
                 const double sc = fma(e, e, e);
-                const double u0 = (wr * wc0) * r0, u1 = (wr * wc1) * r0;
+                // branch-free: entries outside the trailing block get a zero update (r0, sc are finite)
+                const bool below = g > j;
+                const double u0 = (below && 2 * q > j) ? (wr * wc0) * r0 : 0.0;
+                const double u1 = (below && 2 * q + 1 > j) ? (wr * wc1) * r0 : 0.0;
                 const double rj = fma(r0, sc, r0);
                 if (j == 2 * q) rc0 = rj;
                 if (j == 2 * q + 1) rc1 = rj;
-                const double lr = wr * rj;
-                if (g > j) {
-                    if (2 * q > j) p0 = fma(-u0, sc, p0 - u0);
-                    if (2 * q + 1 > j) p1 = fma(-u1, sc, p1 - u1);
-                    y0 = fma(-lr, yj0, y0);
-                    y1 = fma(-lr, yj1, y1);
-                }
+                const double lr = below ? wr * rj : 0.0;
+                p0 = fma(-u0, sc, p0 - u0);
+                p1 = fma(-u1, sc, p1 - u1);
+                y0 = fma(-lr, yj0, y0);
+                y1 = fma(-lr, yj1, y1);
             }
             // pivots: diagnostics, d, 1/d
             if ((g >> 1) == q) {

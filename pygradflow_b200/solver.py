@@ -54,8 +54,6 @@ class BatchedSolver:
                  use_graph: bool = True, graph_steps: int = 8):
         self.problem = problem
         self.params = params if params is not None else Params()
-        if self.params.newton_type == NewtonType.Globalized:
-            raise NotImplementedError("Globalized Newton runs through pygradflow_b200.globalized.GlobalizedStepper")
         self.sync_every = max(1, int(sync_every))
         self.use_graph = bool(use_graph)
         self.graph_steps = max(1, int(graph_steps))  # captured units replayed between two reads of the running count
@@ -95,6 +93,13 @@ class BatchedSolver:
         if not p.hess_constant:
             self.Hbuf = [torch.zeros((B, n, n), **f64) for _ in range(2)]
         self.newton_step_count = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.globalized = None
+        if self.params.newton_type == NewtonType.Globalized:
+            from .globalized import GlobalizedStepper
+
+            # newton.py:218-304; the line search reads its state back per trial, so this mode runs eagerly
+            self.globalized = GlobalizedStepper(problem, self.engine, self.params.newton_tol)
+            self.use_graph = False
 
     # ------------------------------------------------------------------------------------------
     def _y(self, pt):
@@ -205,12 +210,20 @@ class BatchedSolver:
         # ---- first Newton step from (x^, y^) = current iterate
         K.residual(x, self._y(self.cur), x, self._y(self.cur), self.dL0, self._cons(self.cur), lb, ub, self.dt,
                    True, 0, eng.active, self.F, None, run)
-        H0 = prob.lag_hess(x, self._y(self.cur), self.Hbuf[0], run)
-        eng.update_active_set(run)
-        eng.factor(H0, J0, self.dt, self.rho, run)
         xm, ym, gm, cm, om = self.mid
-        eng.step(H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
-                 ym if m > 0 else None, self.diff1, run)
+        ls_failed = None
+        if self.globalized is not None:
+            # GlobalizedNewtonMethod.step(orig_iterate): derivatives, active set, Newton direction, Armijo search
+            st = self.globalized.step(self.cur, self.dL0, self.cur, self.dt, self.rho, xm, ym if m > 0 else None,
+                                      self.diff1, run)
+            ls_failed = (st == 2) & (eng.info == 0)  # a failed factorisation is a rejected step, not a failed search
+            H0 = None
+        else:
+            H0 = prob.lag_hess(x, self._y(self.cur), self.Hbuf[0], run)
+            eng.update_active_set(run)
+            eng.factor(H0, J0, self.dt, self.rho, run)
+            eng.step(H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
+                     ym if m > 0 else None, self.diff1, run)
         prob.eval(xm, gm, cm, om, run)
         Jm = prob.jac(xm, self.Jbuf[1], run) if m > 0 else None
         self._aug_grad(Jm, self.mid, self.dLm, None, None, run)
@@ -219,6 +232,8 @@ class BatchedSolver:
                    False, 0, None, None, self.mid_norm, run)
         K.dr_first(self.status, eng.info, self.dt, self.mid_norm, self.diff1, prm.newton_tol, prm.lamb_red,
                    prm.lamb_min, self.phase, self.lamb_next)
+        if ls_failed is not None:  # the reference raises out of Solver.solve (newton.py:294): the instance stops here
+            self._line_search_failed(ls_failed)
         K.build_worklist(self.phase, PHASE_SECOND, PHASE_SECOND, second, parent=run)
         second.nwork = run.nwork
 
@@ -236,12 +251,19 @@ class BatchedSolver:
             eng.update_active_set(second)
             eng.factor(Hs, Js, self.dt, self.rho, second)
             # a failed refactorisation rejects the step like the first one would (step_control.py:102-104)
-        else:
+        elif self.globalized is None:
             K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub,
                        self.dt, True, 1, eng.active, self.F, None, second)
         xf, yf, gf, cf, of = self.fin
-        eng.step(Hs, Js, xm, self._y(self.mid), self.F, self.dt, self.rho, lb, ub, xf,
-                 yf if m > 0 else None, self.diff2, second)
+        if self.globalized is not None:
+            # second step: derivatives / active set at mid, direction from the residual at the ORIGINAL iterate
+            st = self.globalized.step(self.cur, self.dL0, self.mid, self.dt, self.rho, xf, yf if m > 0 else None,
+                                      self.diff2, second)
+            self._mark_failed_second(eng)
+            self._line_search_failed((st == 2) & (self.phase == PHASE_SECOND))
+        else:
+            eng.step(Hs, Js, xm, self._y(self.mid), self.F, self.dt, self.rho, lb, ub, xf,
+                     yf if m > 0 else None, self.diff2, second)
         if full or active_set_newton:
             self._mark_failed_second(eng)
         K.dr_second(self.dt, self.diff1, self.diff2, prm.theta_max, prm.log_theta_ref, prm.K_P, prm.K_I,
@@ -255,6 +277,12 @@ class BatchedSolver:
         self.newton_step_count += ((ph >= 2) & (ph <= 4)).sum() + ((ph == 3) | (ph == 4)).sum()
         K.commit(self.phase, self.lamb_next, prm.lamb_max, dual_norm, self.mid, self.fin, self.cur, self.lamb,
                  self.rho, self.iters, self.accepted, self.status)
+
+    def _line_search_failed(self, mask):
+        """Armijo search exhausted (newton.py:294 raises a bare Exception that ends Solver.solve): the instance
+        terminates with GF_STATUS_LINE_SEARCH_FAILED and is not committed."""
+        self.status.copy_(torch.where(mask & (self.status == 0), torch.full_like(self.status, 7), self.status))
+        self.phase.copy_(torch.where(mask, torch.zeros_like(self.phase), self.phase))
 
     def _mark_failed_second(self, eng):
         """Solver failure during the second step's refactorisation: reject, lambda <- 2 lambda."""
