@@ -9,7 +9,8 @@
 //   K' x = r  <=>  L z = P r, U x = z                  (trans = 1; row-contiguous axpys)
 // For the symmetric KKT matrix of the Symmetric step solver M = K.
 //
-//   lu_smem_kernel   N <= ~150: whole matrix resident in shared memory, one CTA per matrix (cfg2, n=64).
+//   lu_warp_kernel   N <= 32: one warp per matrix, matrix resident in registers, pivoting by warp shuffles.
+//   lu_smem_kernel   N <= ~110: whole matrix resident in shared memory, one CTA per matrix (cfg2, n=64).
 //   lu_panel_kernel  larger N: right-looking blocked, NB-wide pivoted panel in shared memory, TRSM +
 //                    register-tiled trailing update streamed through L2/HBM.  Robust general path; the
 //                    throughput path for quasi-definite K is the LDL' in gf_ldlt.cu.
@@ -108,6 +109,84 @@ __global__ void lu_smem_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfi
         Kb[(size_t)c * ld + i] = S[c * pitch + i];
     }
     if (threadIdx.x == 0) info[b] = sinfo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// N <= 32: one WARP per matrix, the matrix resident in registers (lane i holds row i of M, 32 doubles), eight
+// matrices per CTA, no shared memory and no block barriers.  Pivot search = warp arg-max by shuffles (ties to the
+// smaller row, NaN never wins: same rule as block_maxloc); rows are not moved between lanes -- every lane tracks
+// the logical position of its row and the factors are written back permuted; the pivot row is broadcast by
+// shuffles.  Same arithmetic (division by the pivot, fused multiply-subtract) as lu_smem_kernel.
+// The column loop is a real loop over a ROTATING register file: the current column is always a[0]; after the
+// elimination step every lane stages its (final) entry of that column in shared memory and shifts its registers
+// down by one, so register indices stay static while the code stays a compact loop (a fully unrolled N = 32
+// elimination is ~100 KB of straight-line code executed once per warp: instruction-fetch bound).
+template <int NMAX>
+__global__ void __launch_bounds__(256) lu_warp_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                      double* __restrict__ K, int32_t* __restrict__ piv,
+                                                      int32_t* __restrict__ info, GfWork work, int nwork) {
+    extern __shared__ double wstage[];  // 8 warps x NMAX columns x 32 lanes
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + wid;
+    if (slot >= nwork) return;
+    const int b = gf_instance(work, slot);
+    if (b < 0) return;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    double* Kb = K + (size_t)b * ld * ld;
+    int32_t* pb = piv + (size_t)b * ld;
+    double* stage = wstage + (size_t)wid * NMAX * 32;
+    const bool row = lane < N;
+    double a[NMAX];
+#pragma unroll
+    for (int c = 0; c < NMAX; c++) a[c] = (row && c < N) ? Kb[(size_t)c * ld + lane] : 0.0;
+    int pos = lane;      // logical row of PM held by this lane (rows never change lanes)
+    int32_t sinfo = 0;
+    constexpr int NONE = 1 << 20;
+    for (int j = 0; j < N; j++) {
+        double v = fabs(a[0]);
+        int idx = pos;
+        if (!(row && pos >= j && v >= 0.0)) { v = -1.0; idx = NONE; }  // excluded rows and NaN entries
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        const int p = idx < NONE ? idx : j;
+        record_pivot(v, j, &sinfo);
+        const int lp = __ffs(__ballot_sync(0xffffffffu, pos == p)) - 1;  // lane that holds the pivot row
+        const int lj = __ffs(__ballot_sync(0xffffffffu, pos == j)) - 1;
+        if (lane == lp) pos = j;
+        else if (lane == lj) pos = p;
+        if (lane == 0) pb[j] = p;
+        const double pv = __shfl_sync(0xffffffffu, a[0], lp);
+        const bool below = row && pos > j && pv != 0.0;
+        double l = 0.0;
+        if (below) {
+            l = a[0] / pv;
+            a[0] = l;
+        }
+        stage[j * 32 + lane] = a[0];  // final: L entry below the pivot, U entry on and above it
+#pragma unroll
+        for (int c = 1; c < NMAX; c++) {
+            const double pc = __shfl_sync(0xffffffffu, a[c], lp);
+            a[c - 1] = below ? fma(-l, pc, a[c]) : a[c];
+        }
+        a[NMAX - 1] = 0.0;
+    }
+    __syncwarp();
+    if (row)
+        for (int c = 0; c < N; c++) Kb[(size_t)c * ld + pos] = stage[c * 32 + lane];
+    if (lane == 0) info[b] = sinfo;
+}
+
+template <int NMAX>
+int launch_warp_lu(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info, GfWork w, int nwork,
+                   cudaStream_t s) {
+    const int smem = 8 * NMAX * 32 * (int)sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(lu_warp_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    lu_warp_kernel<NMAX><<<(nwork + 7) / 8, 256, smem, s>>>(ld, Nvec, Nmax, K, piv, info, w, nwork);
+    return gf_launch_status();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -504,6 +583,10 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
     if (nwork <= 0 || Nmax == 0) return GF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     GfWork w{work, nwork_dev};
+    // warp-per-matrix, register-resident
+    if (Nmax <= 8) return launch_warp_lu<8>(ld, Nmax, Nvec, K, piv, info, w, nwork, s);
+    if (Nmax <= 16) return launch_warp_lu<16>(ld, Nmax, Nvec, K, piv, info, w, nwork, s);
+    if (Nmax <= 32) return launch_warp_lu<32>(ld, Nmax, Nvec, K, piv, info, w, nwork, s);
     const size_t full = (size_t)Nmax * (Nmax | 1) * sizeof(double);
     if (full <= 100 * 1024) {
         if (full > 48 * 1024) cudaFuncSetAttribute(lu_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full);

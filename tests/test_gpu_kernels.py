@@ -219,9 +219,11 @@ def test_lu_golden_kkt(K, golden, N):
     assert rel_err(solt[0, :N], g[f"kkt{N}/sol_trans"]) <= 1e-10
 
 
-@pytest.mark.parametrize("sizes", [[1, 2, 3, 5, 17, 31, 32, 33], [64, 63, 65, 100, 112], [113, 150, 257], [768, 700, 333]])
+@pytest.mark.parametrize("sizes", [[1, 2, 3, 5, 17, 31, 32], [32] * 19 + [7, 1], [1, 2, 3, 5, 17, 31, 32, 33],
+                                   [64, 63, 65, 100, 112], [113, 150, 257], [768, 700, 333]])
 def test_lu_ragged_batch_vs_lapack(K, sizes):
-    """Ragged orders in one batch (shared-memory kernel and blocked panel kernel); unsymmetric matrices,
+    """Ragged orders in one batch (warp-per-matrix register kernel, shared-memory kernel, blocked panel kernel +
+    DMMA trailing update); unsymmetric matrices,
     pivot sequence identical to LAPACK getrf on the transposed view, K x = r and K' x = r."""
     rng = np.random.default_rng(5)
     mats = [rng.standard_normal((N, N)) + 0.1 * np.eye(N) for N in sizes]
