@@ -194,13 +194,16 @@ template <int NB>
 __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                        double* __restrict__ K, int32_t* __restrict__ piv,
                                                        int32_t* __restrict__ info, GfWork work, int jstart,
-                                                       int one_column) {
+                                                       int one_column, int nwork) {
     // one_column = 0: the whole factorisation (FMA trailing update in this kernel);
     // one_column = 1: block column jstart only -- panel, interchanges, U12; the trailing update is lu_update_kernel
-    const int b = gf_instance(work, blockIdx.x);
+    // The CTAs stride over the work list, so that a (mostly) empty list -- the LU fallback of the LDL' path --
+    // costs a small grid instead of `nwork` CTAs that exit at once.
+    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int b = gf_instance(work, wi);
     if (b < 0) return;
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
-    if (jstart >= N) return;
+    if (jstart >= N) continue;
     extern __shared__ double P[];              // NB * rows doubles (panel), then 8*NB doubles (U strip)
     double* Us = P + (size_t)NB * ((Nfixed - jstart) | 1);  // Nfixed = batch-wide Nmax (launch_panel)
     __shared__ MaxLoc scratch[32];
@@ -330,6 +333,8 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
         __syncthreads();
     }
     if (threadIdx.x == 0) info[b] = sinfo;
+    __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -485,13 +490,14 @@ __device__ __forceinline__ double lu_dneg(double x) {
 
 template <int NB>
 __global__ void __launch_bounds__(256, 2) lu_update_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int j0,
-                                                            double* __restrict__ K, GfWork work) {
-    const int b = gf_instance(work, blockIdx.z);
+                                                            double* __restrict__ K, GfWork work, int nwork) {
+    for (int wi = blockIdx.z; wi < nwork; wi += gridDim.z) {
+    const int b = gf_instance(work, wi);
     if (b < 0) return;
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
     const int t0 = j0 + NB;
     const int c0 = t0 + blockIdx.y * 64, i0 = t0 + blockIdx.x * 128;
-    if (c0 >= N || i0 >= N) return;
+    if (c0 >= N || i0 >= N) continue;
     constexpr int AP = NB + 4;   // pitch of the A tile (== 4 or 12 mod 16: conflict-free fragment loads)
     constexpr int BP = 128 + 4;  // pitch of the B tile
     extern __shared__ double usm[];
@@ -546,7 +552,11 @@ __global__ void __launch_bounds__(256, 2) lu_update_kernel(int ld, const int32_t
             if (c < N && i + 1 < N) cp[1] = acc[mi][ni][1];
         }
     }
+    __syncthreads();  // the shared tiles are reused by the next work item
+    }
 }
+
+constexpr int LU_GRID_CAP = 256;
 
 template <int NB>
 int launch_panel(int ld, int Nmax, const int32_t* Nvec, int Nfixed, double* K, int32_t* piv, int32_t* info,
@@ -554,7 +564,9 @@ int launch_panel(int ld, int Nmax, const int32_t* Nvec, int Nfixed, double* K, i
     const size_t smem = ((size_t)NB * ((Nmax - jstart) | 1) + 8 * NB) * sizeof(double);
     if (smem > 227 * 1024) return GF_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(lu_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lu_panel_kernel<NB><<<nwork, 256, smem, s>>>(ld, Nvec, Nfixed, K, piv, info, w, jstart, one_column);
+    // a device-side count may be far below nwork (fallback lists): bound the grid, the CTAs stride
+    const int grid = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
+    lu_panel_kernel<NB><<<grid, 256, smem, s>>>(ld, Nvec, Nfixed, K, piv, info, w, jstart, one_column, nwork);
     return gf_launch_status();
 }
 
@@ -566,10 +578,11 @@ int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv
     if (rc != GF_OK) return rc;
     const int tr = Nmax - j0 - NB;
     if (tr > 0) {
-        dim3 grid((tr + 127) / 128, (tr + 63) / 64, nwork);
+        const int gz = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
+        dim3 grid((tr + 127) / 128, (tr + 63) / 64, gz);
         constexpr int USMEM = (64 * (NB + 4) + NB * 132) * (int)sizeof(double);
         cudaFuncSetAttribute(lu_update_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, USMEM);
-        lu_update_kernel<NB><<<grid, 256, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w);
+        lu_update_kernel<NB><<<grid, 256, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w, nwork);
         rc = gf_launch_status();
     }
     return rc;

@@ -124,7 +124,7 @@ def ldlt_factor(K, Nmax: int, Nvec, dvec, info, nneg, npos_expected, work: WorkL
     B, ld, _ = K.shape
     nblk = (Nmax + 63) // 64
     _call("gf_ldlt_factor", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(dvec), ptr(info), ptr(nneg), ptr(npos_expected),
-          *_w(work), launches=max(1, nblk))
+          *_w(work), launches=nblk * (2 if work.nwork >= 1024 and nblk > 2 else 1))
 
 
 def ldlt_solve(K, Nmax: int, Nvec, rhs, work: WorkList):
