@@ -145,6 +145,131 @@ class OracleProblem:
         raise NotImplementedError
 
 
+class GeneralQP(OracleProblem):
+    """QP with general constraints cl <= Ax + b <= cu (rows with cl == cu are equalities): the form the
+    reference's ConstrainedProblem (cons_problem.py:8-173) turns into equalities + slack bounds."""
+
+    def __init__(self, H, A, g, b, lb, ub, cons_lb, cons_ub):
+        super().__init__(lb, ub, num_cons=np.asarray(A).shape[0])
+        self.H, self.A = _dense(H), _dense(A)
+        self.g, self.b = np.asarray(g, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        self.cons_lb = np.asarray(cons_lb, dtype=np.float64)
+        self.cons_ub = np.asarray(cons_ub, dtype=np.float64)
+
+    def obj(self, x):
+        return float(0.5 * x @ (self.H @ x) + self.g @ x)
+
+    def obj_grad(self, x):
+        return self.H @ x + self.g
+
+    def cons(self, x):
+        return self.A @ x + self.b
+
+    def cons_jac(self, x):
+        return self.A
+
+    def lag_hess(self, x, y):
+        return self.H
+
+
+class HS71Constrained(OracleProblem):
+    """tests/pygradflow/hs71_cons.py: HS71 with an inequality and an equality constraint (no explicit slack)."""
+
+    def __init__(self):
+        super().__init__(np.ones(4), np.full(4, 5.0), num_cons=2)
+        self.cons_lb = np.array([25.0, 40.0])
+        self.cons_ub = np.array([np.inf, 40.0])
+
+    def obj(self, x):
+        return x[0] * x[3] * (x[0] + x[1] + x[2]) + x[2]
+
+    def obj_grad(self, x):
+        return np.array([(x[0] + x[1] + x[2]) * x[3] + x[0] * x[3], x[0] * x[3], x[0] * x[3] + 1,
+                         (x[0] + x[1] + x[2]) * x[0]])
+
+    def cons(self, x):
+        return np.array([np.prod(x), np.dot(x, x)])
+
+    def cons_jac(self, x):
+        return np.array([[x[1] * x[2] * x[3], x[0] * x[2] * x[3], x[0] * x[1] * x[3], x[0] * x[1] * x[2]],
+                         [2 * x[0], 2 * x[1], 2 * x[2], 2 * x[3]]])
+
+    def lag_hess(self, x, lag):
+        l1, l2 = lag
+        oh = np.array([[2 * x[3], x[3], x[3], 2 * x[0] + x[1] + x[2]], [x[3], 0, 0, x[0]], [x[3], 0, 0, x[0]],
+                       [2 * x[0] + x[1] + x[2], x[0], x[0], 0]])
+        h1 = np.array([[0, x[2] * x[3], x[1] * x[3], x[1] * x[2]], [x[2] * x[3], 0, x[0] * x[3], x[0] * x[2]],
+                       [x[1] * x[3], x[0] * x[3], 0, x[0] * x[1]], [x[1] * x[2], x[0] * x[2], x[0] * x[1], 0]])
+        return oh + l1 * h1 + l2 * 2.0 * np.eye(4)
+
+
+class ConstrainedProblem(OracleProblem):
+    """Slack reformulation of cl <= c(x) <= cu into equalities + bounds (cons_problem.py:8-173): a slack per
+    inequality row, c_i(x) - s_i = 0 with cl_i <= s_i <= cu_i; equality rows are shifted by -cl_i."""
+
+    def __init__(self, problem):
+        self.problem = problem
+        cl, cu = problem.cons_lb, problem.cons_ub
+        eq = cl == cu                                                  # :38-46
+        self.slack_positions = np.flatnonzero(~eq)
+        offs = np.where(eq & (cl != 0.0), -cl, 0.0)
+        self.cons_offsets = offs if (eq & (cl != 0.0)).any() else None
+        sp = self.slack_positions
+        super().__init__(np.concatenate([problem.var_lb, cl[sp]]), np.concatenate([problem.var_ub, cu[sp]]),
+                         num_cons=problem.num_cons)                    # :14-29
+
+    def _orig(self, x):
+        return x[: self.problem.num_vars]
+
+    def obj(self, x):
+        return self.problem.obj(self._orig(x))
+
+    def obj_grad(self, x):
+        return np.concatenate([self.problem.obj_grad(self._orig(x)), np.zeros(len(self.slack_positions))])
+
+    def cons(self, x):                                                 # :77-94
+        c = np.array(self.problem.cons(self._orig(x)), dtype=np.float64, copy=True)
+        if self.cons_offsets is not None:
+            c += self.cons_offsets
+        c[self.slack_positions] -= x[self.problem.num_vars:]
+        return c
+
+    def cons_jac(self, x):                                             # :96-113
+        J = _dense(self.problem.cons_jac(self._orig(x)))
+        E = np.zeros((self.num_cons, len(self.slack_positions)))
+        E[self.slack_positions, np.arange(len(self.slack_positions))] = -1.0
+        return np.hstack([J, E])
+
+    def lag_hess(self, x, y):                                          # :115-128
+        H = _dense(self.problem.lag_hess(self._orig(x), y))
+        n, ns = H.shape[0], len(self.slack_positions)
+        out = np.zeros((n + ns, n + ns))
+        out[:n, :n] = H
+        return out
+
+    def transform_sol(self, x, y):                                     # :130-157
+        c = self.problem.cons(x)
+        sp = self.slack_positions
+        return np.concatenate([x, np.clip(c[sp], self.problem.cons_lb[sp], self.problem.cons_ub[sp])]), y
+
+    def restore_sol(self, x, y, d):                                    # :159-173
+        return self._orig(x), y, self._orig(d)
+
+
+def solve_general(problem, params=None, x0=None, y0=None, record=False):
+    """Solver.solve for a problem with general constraint bounds: Transformation.create_transformed_iterate
+    (transform.py:29-54), the solve on the slack form, restore_sol (transform.py:88-104).  No scaling."""
+    n, m = problem.num_vars, problem.num_cons
+    x = np.clip(np.zeros(n), problem.var_lb, problem.var_ub) if x0 is None else np.broadcast_to(x0, (n,)).astype(float)
+    y = np.zeros(m) if y0 is None else np.broadcast_to(y0, (m,)).astype(float)
+    cp = ConstrainedProblem(problem)
+    xt, yt = cp.transform_sol(x, y)
+    res = Solver(cp, params).solve(xt, yt, record=record)
+    res.x_slack = res.x
+    res.x, res.y, res.d = cp.restore_sol(res.x, res.y, res.d)
+    return res
+
+
 class DenseQP(OracleProblem):
     """f = 1/2 x'Hx + g'x, c = Ax + b  (same formulas as tests/pygradflow/qp.py:4-30)."""
 

@@ -102,3 +102,25 @@ def ocp_batch(ks, stages: int = 128, nx: int = 8, nu: int = 8, h: float = 0.05):
     out = {key: np.stack([it[key] for it in items]) for key in ("A", "B", "Q", "R", "xinit", "x0", "y0")}
     out.update({key: items[0][key] for key in ("umax", "h", "stages", "nx", "nu")})
     return out
+
+
+def general_qp_instance(k: int, n: int, m: int):
+    """QP with general constraint bounds (the input form of the reference's slack transform): qp_instance's data,
+    the first half of the rows equalities A x + b = e_i with small non-zero right-hand sides, the second half
+    ranges -r_i <= A x + b <= r_i (one of them one-sided)."""
+    d = qp_instance(k, n, m)
+    rng = np.random.default_rng(5000 + k)
+    me = m // 2
+    e = 0.05 * rng.standard_normal(me)
+    r = rng.uniform(0.05, 0.3, m - me)
+    cl = np.concatenate([e, -r])
+    cu = np.concatenate([e, r])
+    if m - me > 0:
+        cu[-1] = np.inf
+    d.update(cons_lb=cl, cons_ub=cu)
+    return d
+
+
+def general_qp_batch(ks, n: int, m: int):
+    items = [general_qp_instance(int(k), n, m) for k in ks]
+    return {key: np.stack([it[key] for it in items]) for key in items[0]}

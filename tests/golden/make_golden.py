@@ -95,6 +95,32 @@ class RefChainedRosenbrock(Problem):
         return sps.diags([off, main, off], [-1, 0, 1], format="csc")
 
 
+class RefGeneralQP(Problem):
+    """QP with general constraint bounds; Solver wraps it in the reference's ConstrainedProblem (slack transform)."""
+
+    def __init__(self, d):
+        self.H = sps.csc_matrix(d["H"])
+        self.A = sps.csr_matrix(d["A"])
+        self.g = d["g"]
+        self.b = d["b"]
+        super().__init__(d["lb"], d["ub"], cons_lb=d["cons_lb"], cons_ub=d["cons_ub"])
+
+    def obj(self, x):
+        return 0.5 * x @ (self.H @ x) + self.g @ x
+
+    def obj_grad(self, x):
+        return self.H @ x + self.g
+
+    def cons(self, x):
+        return self.A @ x + self.b
+
+    def cons_jac(self, x):
+        return self.A
+
+    def lag_hess(self, x, _):
+        return self.H
+
+
 class RefOCP(Problem):
     """cfg4 family as a reference Problem: the formulas of the oracle's OCP class (identical arithmetic), returned
     as scipy.sparse matrices like the reference's own fixtures."""
@@ -330,6 +356,20 @@ def golden_full_size_qp():
     np.savez_compressed(os.path.join(HERE, "qp512.npz"), **flat("qp_n512_m256_k0/Simplified", res))
 
 
+def golden_constrained():
+    """Slack transform (cons_problem.py, transform.py): general QPs and the reference's own HS71Constrained fixture;
+    the recorded iterates are those of the transformed problem (x, slacks), the result is the restored one."""
+    out = {}
+    for (n, m, k) in [(16, 8, 0), (24, 12, 1)]:
+        d = synth.general_qp_instance(k, n, m)
+        res = trace_solve(RefGeneralQP(d), params_for("Simplified"), d["x0"], d["y0"])
+        out.update(flat(f"gqp_n{n}_m{m}_k{k}/Simplified", res))
+    hs = _load_ref_fixture("hs71_cons").HS71Constrained()
+    res = trace_solve(hs, params_for("Simplified"), np.array([1.0, 5.0, 5.0, 1.0]), np.zeros(2))
+    out.update(flat("hs71_cons/Simplified", res))
+    np.savez_compressed(os.path.join(HERE, "constrained.npz"), **out)
+
+
 def golden_ocp():
     """cfg4-style discretised optimal-control problems (small): full traces of the real reference."""
     out = {}
@@ -348,6 +388,7 @@ if __name__ == "__main__":
     golden_solves()
     golden_full_size_qp()
     golden_ocp()
+    golden_constrained()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -167,6 +167,36 @@ def test_solve_ocp(golden, S, nx, nu, k, newton):
     assert res.status == 1
 
 
+@pytest.mark.parametrize("n,m,k", [(16, 8, 0), (24, 12, 1)])
+def test_slack_transform_general_qp(golden, n, m, k):
+    """cons_problem.py / transform.py: general constraint bounds through the slack form, against the reference."""
+    g = golden("constrained")
+    key = f"gqp_n{n}_m{m}_k{k}/Simplified"
+    d = synth.general_qp_instance(k, n, m)
+    p = orc.GeneralQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"], d["cons_lb"], d["cons_ub"])
+    res = orc.solve_general(p, orc.OracleParams(), d["x0"], d["y0"], record=True)
+    assert res.status == int(g[f"{key}/status"]) == 1
+    horizon = noise_horizon(res.trace)
+    assert [t["accept"] for t in res.trace][: horizon + 1] == list(g[f"{key}/accepts"])[: horizon + 1]
+    for row, i in enumerate(g[f"{key}/trace_idx"]):
+        if i <= horizon and i < len(res.trace):
+            assert rel_err(res.trace[i]["x"], g[f"{key}/trace_x"][row]) <= RTOL  # iterates incl. slacks
+    if horizon >= len(res.trace):
+        assert res.iterations == int(g[f"{key}/iterations"])
+    assert rel_err(res.x, g[f"{key}/x"]) <= 1e-6 and res.x.shape == (n,)
+    cons = p.cons(res.x)
+    assert (cons >= d["cons_lb"] - 1e-6).all() and (cons <= d["cons_ub"] + 1e-6).all()
+
+
+def test_slack_transform_hs71_constrained(golden):
+    """tests/pygradflow/test_solver.py:133-137 (HS71Constrained): known optimum, and the reference's own trace."""
+    g = golden("constrained")
+    res = orc.solve_general(orc.HS71Constrained(), orc.OracleParams(), np.array([1.0, 5.0, 5.0, 1.0]), np.zeros(2))
+    assert res.status == 1 and res.iterations == int(g["hs71_cons/Simplified/iterations"])
+    assert np.allclose(res.x, [1.0, 4.74299964, 3.82114998, 1.37940829], atol=1e-6)  # instances.py:38-40
+    assert rel_err(res.x, g["hs71_cons/Simplified/x"]) <= RTOL
+
+
 def test_solve_tame(golden):
     res = _check_solve(golden("solves"), "tame", orc.Tame(), np.zeros(2), np.zeros(1))
     assert np.allclose(res.x, [0.5, 0.5], atol=1e-6)  # tests/pygradflow/instances.py:57-68
