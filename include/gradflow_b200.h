@@ -205,6 +205,24 @@ int gf_armijo_residual(int B, int n, int m, const double* xt, const double* yt, 
                        int32_t* trials, int32_t* state, double* next_res, const int32_t* work,
                        const int32_t* nwork_dev, int nwork, void* stream);
 
+/* ---- banded L D L' for families whose KKT matrix is banded under a given ordering (cfg4: discretised optimal
+ * control).  Replaces lu_solver.py:9-21 on the matrix of symmetric_step_solver.py:49-77, assembled as the FULL
+ * (n + m) system in the family's order with identity rows / columns for the active variables, so order and band do
+ * not depend on the active set.  order[t] = full KKT index (variables 0..n-1, constraints n..n+m-1) at band
+ * position t, pos = its inverse; Kband [B, n+m, bw+1] with Kband[b][t][d] = K(t, t-d); bw + 1 even and <= 64.
+ * gf_band_permute moves a vector between the reduced standard order (inactive variables in perm order, then
+ * constraints; leading dimension ld) and the band order. */
+int gf_band_assemble(int B, int n, int m, int bw, const double* H, const double* J, const uint8_t* active,
+                     const int32_t* order, const double* dt, const double* rho, double* Kband, const int32_t* work,
+                     const int32_t* nwork_dev, int nwork, void* stream);
+int gf_band_factor(int B, int N, int bw, double* Kband, int32_t* info, int32_t* nneg, const int32_t* work,
+                   const int32_t* nwork_dev, int nwork, void* stream);
+int gf_band_solve(int B, int N, int bw, const double* Kband, double* v, const int32_t* work, const int32_t* nwork_dev,
+                  int nwork, void* stream);
+int gf_band_permute(int B, int n, int m, int ld, const int32_t* perm, const int32_t* nI, const int32_t* pos,
+                    double* stdv, double* bandv, int to_band, const int32_t* work, const int32_t* nwork_dev, int nwork,
+                    void* stream);
+
 /* ---- host-buffer entry (the reference hands its step solver host arrays: scaled_step_solver.py:76-79) ---- */
 
 /* H [cnt, n, n] is symmetric (problem.py:174-192): copy only its lower block triangle (row blocks of `blk` rows,

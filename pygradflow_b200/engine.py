@@ -27,14 +27,24 @@ def _roundup(a: int, b: int) -> int:
     return ((a + b - 1) // b) * b
 
 
+BAND_MIN_N = 256  # order from which Auto prefers the family's banded ordering over the dense LDL'
+
+
 class KKTEngine:
-    def __init__(self, B: int, n: int, m: int, device, linear: LinearSolverType = LinearSolverType.Auto):
+    def __init__(self, B: int, n: int, m: int, device, linear: LinearSolverType = LinearSolverType.Auto, band=None):
+        """band: optional (order, half_bandwidth) of the family's KKT ordering (BatchedProblem.kkt_band)."""
         self.B, self.n, self.m = B, n, m
         self.device = device
         N = n + m
         if linear == LinearSolverType.Auto:
-            linear = LinearSolverType.LU if N <= SMALL_N else LinearSolverType.LDLT
+            if band is not None and N >= BAND_MIN_N:
+                linear = LinearSolverType.Banded
+            else:
+                linear = LinearSolverType.LU if N <= SMALL_N else LinearSolverType.LDLT
         self.linear = linear
+        if linear == LinearSolverType.Banded:
+            self._init_banded(band)
+            return
         self.ld = max(_roundup(N, 64), 64) if linear == LinearSolverType.LDLT else max(N, 1)
         f64 = dict(dtype=torch.float64, device=device)
         i32 = dict(dtype=torch.int32, device=device)
@@ -55,20 +65,64 @@ class KKTEngine:
             self._fb = WorkList(torch.zeros((B,), **i32), torch.zeros((1,), **i32), B)
         self.n_factor_calls = 0
 
+    def _init_banded(self, band):
+        assert band is not None, "LinearSolverType.Banded needs a problem family with kkt_band()"
+        B, n, m, device = self.B, self.n, self.m, self.device
+        N = n + m
+        order, bw = band
+        bw = int(bw) | 1  # bw + 1 even: rows move as 16-byte pieces
+        assert bw + 1 <= 64 and len(order) == N
+        f64 = dict(dtype=torch.float64, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.bw = bw
+        self.order = torch.as_tensor(order, dtype=torch.int32).to(device).contiguous()
+        self.pos = torch.empty_like(self.order)
+        self.pos[self.order.long()] = torch.arange(N, **i32)
+        self.ld = N
+        self.K = None  # no dense KKT matrix in this mode
+        self.Kband = torch.empty((B, N, bw + 1), **f64)
+        self.bandv = torch.zeros((B, N), **f64)
+        self.rhs = torch.zeros((B, N), **f64)
+        self.perm = torch.zeros((B, n), **i32)
+        self.nI = torch.zeros((B,), **i32)
+        self.Nvec = torch.zeros((B,), **i32)
+        self.info = torch.zeros((B,), **i32)
+        self.nneg = torch.zeros((B,), **i32)
+        self.active = torch.zeros((B, n), dtype=torch.uint8, device=device)
+        self.n_factor_calls = 0
+
     # ---------------------------------------------------------------------------------------
     def update_active_set(self, work: WorkList, active: Optional[torch.Tensor] = None):
         """np.where(~A) / np.where(A) for the stored active set (self.active unless given)."""
         K.index_sets(self.active if active is None else active, self.m, self.perm, self.nI, self.Nvec, work)
 
+    def assemble(self, H, J, dt, rho, work: WorkList):
+        """The reduced symmetric KKT matrix of symmetric_step_solver.py:49-77 in the layout of the factorisation."""
+        if self.linear == LinearSolverType.Banded:
+            K.band_assemble(H, J, self.active, self.order, self.bw, dt, rho, self.Kband, work)
+        elif self.linear == LinearSolverType.LU:
+            K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, work)
+        else:
+            K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 64, True, work)
+
     def factor(self, H, J, dt, rho, work: WorkList):
         """Assemble the reduced symmetric KKT matrix and factorise it; per-instance result in self.info."""
+        self.assemble(H, J, dt, rho, work)
+        self.factor_assembled(H, J, dt, rho, work)
+
+    def factor_assembled(self, H, J, dt, rho, work: WorkList):
         self.n_factor_calls += 1
         Nmax = self.n + self.m
+        if self.linear == LinearSolverType.Banded:
+            K.band_factor(self.Kband, self.bw, self.info, self.nneg, work)
+            # inertia of a quasi-definite K: exactly m negative pivots (the active rows are +1); anything else is
+            # reported like a failed factorisation (the step is rejected and lambda doubled, step_control.py:102-104)
+            torch.where((self.info == 0) & (self.nneg != self.m), torch.full_like(self.info, -2), self.info,
+                        out=self.info)
+            return
         if self.linear == LinearSolverType.LU:
-            K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, work)
             K.lu_factor(self.K, Nmax, self.Nvec, self.piv, self.info, work)
             return
-        K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 64, True, work)
         K.ldlt_factor(self.K, Nmax, self.Nvec, self.dvec, self.info, self.nneg, self.nI, work)
         # Instances whose pivots are not those of a quasi-definite matrix (or hit a zero pivot) are
         # re-assembled in full and factorised with partial pivoting, like the reference's LU.
@@ -83,6 +137,11 @@ class KKTEngine:
     def solve(self, rhs, work: WorkList, trans: bool = False):
         """rhs[B, ld] <- K^{-1} rhs for the instances in ``work``."""
         Nmax = self.n + self.m
+        if self.linear == LinearSolverType.Banded:
+            K.band_permute(self.perm, self.nI, self.pos, rhs, self.bandv, True, self.m, work)
+            K.band_solve(self.Kband, self.bw, self.bandv, work)  # symmetric: trans is irrelevant
+            K.band_permute(self.perm, self.nI, self.pos, rhs, self.bandv, False, self.m, work)
+            return
         if self.linear == LinearSolverType.LU:
             K.lu_solve(self.K, Nmax, self.Nvec, self.piv, rhs, trans, work)
             return

@@ -224,3 +224,26 @@ def h2d_sym_lower_bytes(cnt: int, n: int) -> int:
 def symmetrize_lower(H, cnt: int):
     """Rebuild the blocks above the diagonal of H[:cnt] from the transferred lower block triangle."""
     _call("gf_symmetrize_lower", ptr(H), cnt, H.shape[1], SYM_BLOCK, _stream())
+
+
+def band_assemble(H, J, active, order, bw: int, dt, rho, Kband, work: WorkList):
+    B, n, _ = H.shape
+    m = 0 if J is None else J.shape[1]
+    _call("gf_band_assemble", B, n, m, bw, ptr(H), ptr(J), ptr(active), ptr(order), ptr(dt), ptr(rho), ptr(Kband),
+          *_w(work))
+
+
+def band_factor(Kband, bw: int, info, nneg, work: WorkList):
+    B, N, _ = Kband.shape
+    _call("gf_band_factor", B, N, bw, ptr(Kband), ptr(info), ptr(nneg), *_w(work))
+
+
+def band_solve(Kband, bw: int, v, work: WorkList):
+    B, N, _ = Kband.shape
+    _call("gf_band_solve", B, N, bw, ptr(Kband), ptr(v), *_w(work))
+
+
+def band_permute(perm, nI, pos, stdv, bandv, to_band: bool, m: int, work: WorkList):
+    B, n = perm.shape
+    _call("gf_band_permute", B, n, m, stdv.shape[1], ptr(perm), ptr(nI), ptr(pos), ptr(stdv), ptr(bandv),
+          1 if to_band else 0, *_w(work))

@@ -43,6 +43,10 @@ SIGNATURES = {
     "gf_merit_grad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_ls_trial": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_armijo_residual": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P] + _WORK,
+    "gf_band_assemble": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_band_factor": [_I, _I, _I, _P, _P, _P] + _WORK,
+    "gf_band_solve": [_I, _I, _I, _P, _P] + _WORK,
+    "gf_band_permute": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I] + _WORK,
     "gf_h2d_sym_lower": [_P, _P, _I, _I, _I, _P],
     "gf_symmetrize_lower": [_P, _I, _I, _I, _P],
     "gf_build_worklist": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P],

@@ -28,7 +28,7 @@ class NewtonKKTStepper:
         self.problem = problem
         p = problem
         B, n, m, dev = p.B, p.n, p.m, p.device
-        self.engine = KKTEngine(B, n, m, dev, linear)
+        self.engine = KKTEngine(B, n, m, dev, linear, band=problem.kkt_band())
         f64 = dict(dtype=torch.float64, device=dev)
         self.grad = torch.zeros((B, n), **f64)
         self.cons = torch.zeros((B, m), **f64)
@@ -83,11 +83,7 @@ class NewtonKKTStepper:
         H = prob.lag_hess(x, ym, self.Hbuf, w)
         if timing:
             t.append(self._mark())
-        Nmax = prob.n + m
-        if eng.linear == LinearSolverType.LDLT:
-            K.kkt_assemble(H, J, eng.perm, eng.nI, self.dt, rho, eng.K, 64, True, w)
-        else:
-            K.kkt_assemble(H, J, eng.perm, eng.nI, self.dt, rho, eng.K, 1, False, w)
+        eng.assemble(H, J, self.dt, rho, w)
         if timing:
             t.append(self._mark())
         self._factor_only(H, J, rho)
@@ -116,8 +112,8 @@ class NewtonKKTStepper:
         """Factorise the assembled K (KKTEngine.factor minus the assembly, so the phases time separately)."""
         eng, w = self.engine, self.work
         Nmax = self.problem.n + self.problem.m
-        if eng.linear == LinearSolverType.LU:
-            K.lu_factor(eng.K, Nmax, eng.Nvec, eng.piv, eng.info, w)
+        if eng.linear in (LinearSolverType.LU, LinearSolverType.Banded):
+            eng.factor_assembled(H, J, self.dt, rho, w)
             return
         K.ldlt_factor(eng.K, Nmax, eng.Nvec, eng.dvec, eng.info, eng.nneg, eng.nI, w)
         eng.fbkey.copy_(eng.info)

@@ -25,11 +25,13 @@ class NewtonType(enum.Enum):
 class LinearSolverType(enum.Enum):
     """LU is the reference default (params.py:236).  LDLT is the B200 symmetric factorisation with
     inertia (the contract of the reference's MA57 / MUMPS / SSIDS / Cholesky wrappers); Auto picks LDLT
-    for quasi-definite systems of order > 112 with a per-instance pivoted-LU fallback, LU otherwise."""
+    for quasi-definite systems of order > 112 with a per-instance pivoted-LU fallback, LU otherwise -- and
+    Banded (banded LDLT in the family's own KKT ordering) when the problem family provides one."""
 
     LU = enum.auto()
     LDLT = enum.auto()
     Auto = enum.auto()
+    Banded = enum.auto()
 
 
 class PenaltyUpdate(enum.Enum):

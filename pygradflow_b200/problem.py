@@ -53,6 +53,11 @@ class BatchedProblem:
         """The sub-batch of instances ``idx`` (used to shard the batch across ranks)."""
         raise NotImplementedError
 
+    def kkt_band(self):
+        """Optional: (order, half_bandwidth) of an ordering of the n + m KKT unknowns (variables 0..n-1, constraints
+        n..n+m-1) under which the KKT matrix of every instance is banded; None for dense families."""
+        return None
+
 
 class BatchedQP(BatchedProblem):
     """f = x'Hx/2 + g'x, c = Ax + b (the reference's generic QP, tests/pygradflow/qp.py:4-30)."""
@@ -155,6 +160,17 @@ class BatchedOCP(BatchedProblem):
         self._zero_once(out)
         K.ocp_hess(self.S, self.nx, self.nu, 0.1 * self.h, self.Q, self.R, x, y, out, work)
         return out
+
+    def kkt_band(self):
+        """Stage-interleaved order y_0, z_0, y_1, z_1, ...: c_j couples z_{j-1} (x_j) and z_j, so the half-bandwidth
+        is nx + (nx + nu) - 1."""
+        S, nx, nu = self.S, self.nx, self.nu
+        w = nx + nu
+        order = []
+        for j in range(S):
+            order += [self.n + j * nx + r for r in range(nx)]
+            order += [j * w + c for c in range(w)]
+        return order, nx + w - 1
 
     def select(self, idx):
         q = object.__new__(BatchedOCP)
