@@ -93,7 +93,15 @@ __global__ void __launch_bounds__(32) band_factor_kernel(int N, int bw, double* 
         const double dj = win[sj * W];
         if (!(isfinite(dj)) || dj == 0.0) { if (bad == 0) bad = j + 1; }
         if (dj < 0.0) neg++;
-        const double rinv = (dj != 0.0) ? 1.0 / dj : 0.0;
+        double rinv;
+        {   // 1 / dj: MUFU seed + cubic step + Newton step (a full division is ~3x longer on this critical path)
+            double r0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(dj));
+            const double e = fma(-dj, r0, 1.0);
+            r0 = fma(r0, fma(e, e, e), r0);
+            rinv = fma(r0, fma(-dj, r0, 1.0), r0);
+            if (dj == 0.0) rinv = 0.0;
+        }
         const int nb = min(bw, N - 1 - j);  // rows below inside the band
         const int s1 = sj + 1;              // slot of row j + 1 (before wrap-around)
         // column j: row r = j + 1 + k has its entry at d = k + 1
@@ -153,14 +161,26 @@ __global__ void __launch_bounds__(32) band_solve_kernel(int N, int bw, const dou
     __syncwarp();
     const int d0 = 1 + lane, d1 = 33 + lane;  // this lane's band offsets (bw <= 63)
     // forward, unit lower: z_{t+d} -= L(t+d, t) z_t  (column t of L: Kmat[t+d][d])
-    for (int t0 = 0; t0 < N; t0 += 8) {
-        double a0[8], a1[8];
+    auto fetch_fwd = [&](int t0, double (&a0)[8], double (&a1)[8]) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int t = t0 + u;
             a0[u] = (d0 <= bw && t + d0 < N) ? Kmat[(size_t)(t + d0) * W + d0] : 0.0;
             a1[u] = (d1 <= bw && t + d1 < N) ? Kmat[(size_t)(t + d1) * W + d1] : 0.0;
         }
+    };
+    auto fetch_bwd = [&](int t0, double (&a0)[8], double (&a1)[8]) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int t = t0 - u;
+            a0[u] = (t >= 0 && d0 <= bw && t - d0 >= 0) ? Kmat[(size_t)t * W + d0] : 0.0;
+            a1[u] = (t >= 0 && d1 <= bw && t - d1 >= 0) ? Kmat[(size_t)t * W + d1] : 0.0;
+        }
+    };
+    double a0[8], a1[8], n0[8], n1[8];
+    fetch_fwd(0, a0, a1);
+    for (int t0 = 0; t0 < N; t0 += 8) {
+        fetch_fwd(t0 + 8, n0, n1);  // the next eight steps' entries are in flight while these eight are applied
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int t = t0 + u;
@@ -171,18 +191,15 @@ __global__ void __launch_bounds__(32) band_solve_kernel(int N, int bw, const dou
                 __syncwarp();
             }
         }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { a0[u] = n0[u]; a1[u] = n1[u]; }
     }
     for (int t = lane; t < N; t += 32) z[t] /= Kmat[(size_t)t * W];
     __syncwarp();
     // backward: x_{t-d} -= L(t, t-d) x_t  (row t of L: Kmat[t][d], contiguous)
+    fetch_bwd(N - 1, a0, a1);
     for (int t0 = N - 1; t0 >= 0; t0 -= 8) {
-        double a0[8], a1[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int t = t0 - u;
-            a0[u] = (t >= 0 && d0 <= bw && t - d0 >= 0) ? Kmat[(size_t)t * W + d0] : 0.0;
-            a1[u] = (t >= 0 && d1 <= bw && t - d1 >= 0) ? Kmat[(size_t)t * W + d1] : 0.0;
-        }
+        fetch_bwd(t0 - 8, n0, n1);
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int t = t0 - u;
@@ -193,6 +210,8 @@ __global__ void __launch_bounds__(32) band_solve_kernel(int N, int bw, const dou
                 __syncwarp();
             }
         }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { a0[u] = n0[u]; a1[u] = n1[u]; }
     }
     for (int t = lane; t < N; t += 32) vb[t] = z[t];
 }
