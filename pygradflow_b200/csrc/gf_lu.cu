@@ -608,6 +608,10 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
         return gf_launch_status();
     }
     if (Nmax > 3500 || nwork > 65535) return GF_ERR_UNSUPPORTED;
+    // A device-counted work list is the fallback list of the LDL' path: usually empty, at most a few instances.
+    // One launch of the whole-factorisation kernel (bounded grid, FMA trailing update) instead of two per block
+    // column keeps its cost at a few microseconds when there is nothing to do.
+    if (nwork_dev != nullptr && Nmax <= 830) return launch_panel<32>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
     // Multi-launch right-looking factorisation: per block column a pivoted panel kernel (panel resident in shared
     // memory, so its width follows the rows that are left) and the DMMA trailing update.
     int j0 = 0;
