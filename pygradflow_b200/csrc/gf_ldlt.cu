@@ -373,6 +373,8 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     if (nchunks > 0) load_stage(0, 0);
     else load_diag_block(sm + EPI_XS, Kb, j0, ld);
     cp_async_commit();
+    // reciprocal pivots of block column k for the epilogue: fetched and inverted now, behind the main loop
+    const double my_rinv = (tid < NB) ? 1.0 / __ldg(db + j0 + tid) : 0.0;
     // accumulators start from the current A tile (these loads overlap the first pipeline stage)
     double acc[4][NI][2];
 #pragma unroll
@@ -424,7 +426,7 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
             *reinterpret_cast<double2*>(Cs + r * EP + c) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
     }
-    if (tid < NB) rinv[tid] = 1.0 / db[j0 + tid];
+    if (tid < NB) rinv[tid] = my_rinv;
     __syncthreads();
     TRACE_MARK(2);
     // every warp solves ROWS / 8 full rows (all 64 columns), so the triangular pruning of the k range loads all
@@ -517,6 +519,7 @@ __device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const
     if (nchunks > 0) load_stage(0, 0);
     else load_diag_block(sm + EPI_XS, Kb, j0, ld);
     cp_async_commit();
+    const double my_rinv = (tid < NB) ? 1.0 / __ldg(db + j0 + tid) : 0.0;  // for the epilogue, behind the main loop
     double acc[4][4][2];
     {
         const int colbase = (diag_part ? i0 + (wn - 2) * 32 : j0 + wn * 32) + 2 * q;
@@ -588,7 +591,7 @@ __device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const
             }
         }
     }
-    if (tid < NB) rinv[tid] = 1.0 / db[j0 + tid];
+    if (tid < NB) rinv[tid] = my_rinv;
     __syncthreads();
     TRACE_MARK(2);
 
