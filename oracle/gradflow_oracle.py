@@ -94,6 +94,7 @@ class OracleParams:
     local_infeas_tol: float = 1e-8
     newton_type: str = "simplified"  # simplified | full | active_set | globalized
     newton_tol: float = 1e-8
+    step_control_type: str = "distance_ratio"  # distance_ratio | residuum_ratio | exact | fixed
     penalty_update: str = "dual_norm"  # dual_norm | constant
     iteration_limit: Optional[int] = None
     obj_lower_limit: float = -1e10
@@ -1122,6 +1123,72 @@ class DistanceRatioController:
             return ControlResult(iterate, 2.0 * (1.0 / dt), None, False, 0)
 
 
+class ResiduumRatioController(DistanceRatioController):
+    """residuum_ratio_control.py:12-63: one Newton step, theta = |F(mid)| / |F(orig)| (unscaled residual)."""
+
+    def step(self, iterate, rho, dt):
+        p = self.params
+        lamb = 1.0 / dt
+        method = self._newton(iterate, rho, dt)
+        func = ImplicitFunc(self.problem, iterate, dt)
+        mid = method.step(iterate)
+        self.total_newton_steps += 1
+        mid_norm = float(np.linalg.norm(func.value_at(mid.iterate, rho)))
+        if mid_norm <= p.newton_tol:
+            return ControlResult(mid.iterate, max(lamb * p.lamb_red, p.lamb_min), mid.active_set, True, 1)
+        orig_norm = float(np.linalg.norm(func.value_at(iterate, rho)))
+        theta = mid_norm / orig_norm
+        accepted = theta <= p.theta_max
+        if accepted:
+            lamb_n = max(p.lamb_min, lamb / self.pi.update(theta))
+        else:
+            lamb_n = lamb * p.lamb_inc  # (the reference's reset branch is dead: LogController.error_sum stays 0.0)
+        return ControlResult(mid.iterate, lamb_n, mid.active_set, accepted, 1, theta)
+
+
+class ExactController(DistanceRatioController):
+    """exact_control.py:10-66: Newton steps until |F| <= newton_tol (accept, lambda / 2) or the contraction rate
+    exceeds 1/2 / ten steps are used up (reject, 2 lambda)."""
+
+    max_num_it = 10
+    rate_bound = 0.5
+
+    def step(self, iterate, rho, dt):
+        p = self.params
+        lamb = 1.0 / dt
+        func = ImplicitFunc(self.problem, iterate, dt)
+        curr = float(np.linalg.norm(func.value_at(iterate, rho)))
+        method = self._newton(iterate, rho, dt)
+        cur_it = iterate
+        for i in range(self.max_num_it):
+            st = method.step(cur_it)
+            self.total_newton_steps += 1
+            nxt = st.iterate
+            val = float(np.linalg.norm(func.value_at(nxt, rho)))
+            if val <= p.newton_tol:
+                return ControlResult(nxt, 0.5 * lamb, st.active_set, True, i + 1)
+            if val / curr > self.rate_bound:
+                break
+            curr = val
+            cur_it = nxt
+        return ControlResult(nxt, 2.0 * lamb, st.active_set, False, i + 1)
+
+
+class FixedStepSizeController(DistanceRatioController):
+    """fixed_control.py:7-19: one Newton step, always accepted, lambda stays lamb_init."""
+
+    def step(self, iterate, rho, dt):
+        st = self._newton(iterate, rho, dt).step(iterate)
+        self.total_newton_steps += 1
+        return ControlResult(st.iterate, self.params.lamb_init, st.active_set, True, 1)
+
+
+def step_controller(problem, params):
+    """step_control.py:123-150 (the Newton-based controllers)."""
+    return {"distance_ratio": DistanceRatioController, "residuum_ratio": ResiduumRatioController,
+            "exact": ExactController, "fixed": FixedStepSizeController}[params.step_control_type](problem, params)
+
+
 # --------------------------------------------------------------------------
 # Penalty (pygradflow/penalty.py:36-74)
 # --------------------------------------------------------------------------
@@ -1197,7 +1264,7 @@ class Solver:
         """solver.py:207-231."""
         p = self.params
         it = initial_iterate(self.problem, p, x0, y0)
-        ctrl = DistanceRatioController(self.problem, p)
+        ctrl = step_controller(self.problem, p)
         res = ctrl.compute_step(it, p.rho, 1.0 / p.lamb_init)
         nxt = res.iterate
         return nxt.x, nxt.y, nxt.bounds_dual
@@ -1209,7 +1276,7 @@ class Solver:
         iterate = initial_iterate(problem, p, x0, y0)
         iterate.check_eval()
         lamb = p.lamb_init
-        ctrl = DistanceRatioController(problem, p)
+        ctrl = step_controller(problem, p)
         ctrl.trace_hook = step_hook
         penalty = Penalty(problem, p)
         rho = penalty.rho

@@ -34,6 +34,16 @@ class LinearSolverType(enum.Enum):
     Banded = enum.auto()
 
 
+class StepControlType(enum.Enum):
+    """pygradflow/params.py:113-130, the Newton-based controllers (step_control.py:123-150).  Optimizing / BoxReduced
+    solve the proximal sub-problem with Ipopt / a box solver instead of the Newton-KKT path and are out of scope."""
+
+    DistanceRatio = enum.auto()
+    ResiduumRatio = enum.auto()
+    Exact = enum.auto()
+    Fixed = enum.auto()
+
+
 class PenaltyUpdate(enum.Enum):
     """pygradflow/params.py:133-139 (only the two strategies on the named path)."""
 
@@ -62,6 +72,7 @@ class Params:
     local_infeas_tol: float = 1e-8
     newton_type: NewtonType = NewtonType.Simplified
     newton_tol: float = 1e-8
+    step_control_type: StepControlType = StepControlType.DistanceRatio
     step_solver: Optional[Callable[..., Any]] = None
     linear_solver_type: LinearSolverType = LinearSolverType.Auto
     penalty_update: PenaltyUpdate = PenaltyUpdate.DualNorm
@@ -72,7 +83,7 @@ class Params:
 
     def __post_init__(self):
         for key, cls in (("newton_type", NewtonType), ("linear_solver_type", LinearSolverType),
-                         ("penalty_update", PenaltyUpdate)):
+                         ("penalty_update", PenaltyUpdate), ("step_control_type", StepControlType)):
             v = getattr(self, key)
             if not isinstance(v, cls):
                 setattr(self, key, cls[_enum_name(v)])  # accepts strings and the reference's own enums
@@ -96,5 +107,7 @@ class Params:
                 v = getattr(ref, f)
                 if f == "penalty_update" and _enum_name(v) not in PenaltyUpdate.__members__:
                     raise ValueError(f"penalty_update={_enum_name(v)} is outside the B200 path (Constant / DualNorm)")
+                if f == "step_control_type" and _enum_name(v) not in StepControlType.__members__:
+                    raise ValueError(f"step_control_type={_enum_name(v)} is outside the B200 path (Newton-based only)")
                 kw[f] = v
         return Params(**kw)

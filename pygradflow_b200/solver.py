@@ -23,7 +23,7 @@ import torch
 from . import kernels as K
 from .engine import KKTEngine
 from .kernels import WorkList
-from .params import NewtonType, Params, PenaltyUpdate
+from .params import NewtonType, Params, PenaltyUpdate, StepControlType
 from .problem import BatchedProblem
 
 PHASE_SECOND = 1
@@ -71,6 +71,7 @@ class BatchedSolver:
 
         self.cur, self.mid, self.fin = point(), point(), point()
         self.dL0, self.dLm, self.jty, self.jtc = vec(n), vec(n), vec(n), vec(n)
+        self.dLf = vec(n)
         self.F = vec(n + m)
         self.lamb = torch.zeros((B,), **f64)
         self.rho = torch.zeros((B,), **f64)
@@ -78,6 +79,8 @@ class BatchedSolver:
         self.err_sum = torch.zeros((B,), **f64)
         self.lamb_next = torch.zeros((B,), **f64)
         self.diff1, self.diff2, self.mid_norm = (torch.zeros((B,), **f64) for _ in range(3))
+        self.fin_norm, self.orig_norm = (torch.zeros((B,), **f64) for _ in range(2))
+        self.loop_key = torch.zeros((B,), **i32)
         self.theta = torch.zeros((B,), **f64)
         self.total_res = torch.zeros((B,), **f64)
         self.status = torch.zeros((B,), **i32)
@@ -86,10 +89,11 @@ class BatchedSolver:
         self.phase = torch.zeros((B,), **i32)
         self.run = WorkList(torch.zeros((B,), **i32), torch.zeros((1,), **i32), B)
         self.second = WorkList(torch.zeros((B,), **i32), torch.zeros((1,), **i32), B)
-        self.Jbuf = [None, None]
+        self.Jbuf = [None, None, None]
         self.Hbuf = [None, None]
+        exact = self.params.step_control_type == StepControlType.Exact
         if m > 0 and not p.jac_constant:
-            self.Jbuf = [torch.zeros((B, m, n), **f64) for _ in range(2)]
+            self.Jbuf = [torch.zeros((B, m, n), **f64) for _ in range(3 if exact else 2)]
         if not p.hess_constant:
             self.Hbuf = [torch.zeros((B, n, n), **f64) for _ in range(2)]
         self.newton_step_count = torch.zeros((1,), dtype=torch.int64, device=dev)
@@ -195,19 +199,33 @@ class BatchedSolver:
         self.run.nwork = nw
 
     def _step(self, on_iteration, outer):
-        """One outer iteration of every running instance: two Newton steps, step-size control, commit."""
+        """One outer iteration of every running instance: Newton step(s), step-size control, commit."""
+        prm = self.params
+        K.dt_from_lamb(self.lamb, self.dt)
+        ctl = prm.step_control_type
+        if ctl == StepControlType.DistanceRatio:
+            self._control_distance_ratio()
+        elif ctl == StepControlType.Exact:
+            self._control_exact()
+        else:
+            self._control_single(fixed=ctl == StepControlType.Fixed)
+        if on_iteration is not None:
+            on_iteration(outer, self)
+        # ---- accept / reject, penalty, counters (solver.py:318-378)
+        dual_norm = prm.penalty_update == PenaltyUpdate.DualNorm
+        K.commit(self.phase, self.lamb_next, prm.lamb_max, dual_norm, self.mid, self.fin, self.cur, self.lamb,
+                 self.rho, self.iters, self.accepted, self.status)
+
+    # ---- Newton steps -------------------------------------------------------------------------
+    def _first_newton_step(self):
+        """newton_method(...) at the current iterate and its first step -> self.mid; evaluates the problem there
+        and the unscaled residual norm |F(mid)| (what every Newton-based controller looks at first)."""
         prm, prob, eng = self.params, self.problem, self.engine
         m = prob.m
-        run, second = self.run, self.second
+        run = self.run
         x, y, grad, cons, obj = self.cur
         J0 = self._J0
-        full = prm.newton_type == NewtonType.Full
-        active_set_newton = prm.newton_type == NewtonType.ActiveSet
-        dual_norm = prm.penalty_update == PenaltyUpdate.DualNorm
         lb, ub = prob.var_lb, prob.var_ub
-        K.dt_from_lamb(self.lamb, self.dt)
-
-        # ---- first Newton step from (x^, y^) = current iterate
         K.residual(x, self._y(self.cur), x, self._y(self.cur), self.dL0, self._cons(self.cur), lb, ub, self.dt,
                    True, 0, eng.active, self.F, None, run)
         xm, ym, gm, cm, om = self.mid
@@ -217,66 +235,187 @@ class BatchedSolver:
             st = self.globalized.step(self.cur, self.dL0, self.cur, self.dt, self.rho, xm, ym if m > 0 else None,
                                       self.diff1, run)
             ls_failed = (st == 2) & (eng.info == 0)  # a failed factorisation is a rejected step, not a failed search
-            H0 = None
+            self._H0 = None
         else:
-            H0 = prob.lag_hess(x, self._y(self.cur), self.Hbuf[0], run)
+            self._H0 = prob.lag_hess(x, self._y(self.cur), self.Hbuf[0], run)
             eng.update_active_set(run)
-            eng.factor(H0, J0, self.dt, self.rho, run)
-            eng.step(H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
+            eng.factor(self._H0, J0, self.dt, self.rho, run)
+            eng.step(self._H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
                      ym if m > 0 else None, self.diff1, run)
-        prob.eval(xm, gm, cm, om, run)
-        Jm = prob.jac(xm, self.Jbuf[1], run) if m > 0 else None
-        self._aug_grad(Jm, self.mid, self.dLm, None, None, run)
-        # ||F_unscaled(mid)|| with the active set recomputed at mid (distance_ratio_control.py:34)
-        K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub, self.dt,
-                   False, 0, None, None, self.mid_norm, run)
+        self._eval_point(self.mid, self.dLm, 1, self.mid_norm, run)
+        return ls_failed
+
+    def _eval_point(self, pt, dL, jslot, norm_out, work):
+        """Problem callbacks at `pt`, its augmented-Lagrangian gradient and ||F_unscaled(pt)|| w.r.t. the current
+        iterate, active set recomputed at pt (distance_ratio_control.py:34 and the other controllers alike)."""
+        prob = self.problem
+        m = prob.m
+        x, y = self.cur[0], self._y(self.cur)
+        prob.eval(pt[0], pt[2], pt[3], pt[4], work)
+        J = prob.jac(pt[0], self.Jbuf[jslot], work) if m > 0 else None
+        self._aug_grad(J, pt, dL, None, None, work)
+        K.residual(pt[0], self._y(pt), x, y, dL, self._cons(pt), prob.var_lb, prob.var_ub, self.dt, False, 0, None,
+                   None, norm_out, work)
+        return J
+
+    def _next_newton_step(self, src, dL_src, J_src, dst, diff, work):
+        """A further step of the same NewtonMethod object from `src` (evaluated, with dL_src / J_src) into `dst`."""
+        prm, prob, eng = self.params, self.problem, self.engine
+        m = prob.m
+        x, y = self.cur[0], self._y(self.cur)
+        lb, ub = prob.var_lb, prob.var_ub
+        full = prm.newton_type == NewtonType.Full
+        active_set_newton = prm.newton_type == NewtonType.ActiveSet
+        if self.globalized is not None:
+            # derivatives / active set at src, direction from the residual at the ORIGINAL iterate
+            st = self.globalized.step(self.cur, self.dL0, src, self.dt, self.rho, dst[0], dst[1] if m > 0 else None,
+                                      diff, work)
+            return st
+        Hs, Js = self._H0, self._J0
+        if full or active_set_newton:
+            # Full: active set + derivatives at src (newton.py:83-89); ActiveSet: active set at src,
+            # derivatives frozen (newton.py:205-215).  Refactoring with an unchanged active set
+            # reproduces the same factor, so it is done unconditionally.
+            K.residual(src[0], self._y(src), x, y, dL_src, self._cons(src), lb, ub, self.dt, True, 0, eng.active,
+                       self.F, None, work)
+            if full:
+                Hs = prob.lag_hess(src[0], self._y(src), self.Hbuf[1], work)
+                Js = J_src
+            eng.update_active_set(work)
+            eng.factor(Hs, Js, self.dt, self.rho, work)
+            # a failed refactorisation rejects the step like the first one would (step_control.py:102-104)
+        else:
+            K.residual(src[0], self._y(src), x, y, dL_src, self._cons(src), lb, ub, self.dt, True, 1, eng.active,
+                       self.F, None, work)
+        eng.step(Hs, Js, src[0], self._y(src), self.F, self.dt, self.rho, lb, ub, dst[0],
+                 dst[1] if m > 0 else None, diff, work)
+        return None
+
+    # ---- controllers (step_control.py:123-150) ------------------------------------------------
+    def _control_distance_ratio(self):
+        """DistanceRatioController.step (distance_ratio_control.py:18-78)."""
+        prm, prob, eng = self.params, self.problem, self.engine
+        run, second = self.run, self.second
+        ls_failed = self._first_newton_step()
         K.dr_first(self.status, eng.info, self.dt, self.mid_norm, self.diff1, prm.newton_tol, prm.lamb_red,
                    prm.lamb_min, self.phase, self.lamb_next)
         if ls_failed is not None:  # the reference raises out of Solver.solve (newton.py:294): the instance stops here
             self._line_search_failed(ls_failed)
         K.build_worklist(self.phase, PHASE_SECOND, PHASE_SECOND, second, parent=run)
         second.nwork = run.nwork
-
         # ---- second Newton step from mid
-        Hs, Js = H0, J0
-        if full or active_set_newton:
-            # Full: active set + derivatives at mid (newton.py:83-89); ActiveSet: active set at mid,
-            # derivatives frozen (newton.py:205-215).  Refactoring with an unchanged active set
-            # reproduces the same factor, so it is done unconditionally.
-            K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub,
-                       self.dt, True, 0, eng.active, self.F, None, second)
-            if full:
-                Hs = prob.lag_hess(xm, self._y(self.mid), self.Hbuf[1], second)
-                Js = Jm
-            eng.update_active_set(second)
-            eng.factor(Hs, Js, self.dt, self.rho, second)
-            # a failed refactorisation rejects the step like the first one would (step_control.py:102-104)
-        elif self.globalized is None:
-            K.residual(xm, self._y(self.mid), x, self._y(self.cur), self.dLm, self._cons(self.mid), lb, ub,
-                       self.dt, True, 1, eng.active, self.F, None, second)
-        xf, yf, gf, cf, of = self.fin
-        if self.globalized is not None:
-            # second step: derivatives / active set at mid, direction from the residual at the ORIGINAL iterate
-            st = self.globalized.step(self.cur, self.dL0, self.mid, self.dt, self.rho, xf, yf if m > 0 else None,
-                                      self.diff2, second)
+        Jm = self.Jbuf[1] if (prob.m > 0 and not prob.jac_constant) else self._J0
+        st = self._next_newton_step(self.mid, self.dLm, Jm, self.fin, self.diff2, second)
+        if self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet):
             self._mark_failed_second(eng)
+        if st is not None:
             self._line_search_failed((st == 2) & (self.phase == PHASE_SECOND))
-        else:
-            eng.step(Hs, Js, xm, self._y(self.mid), self.F, self.dt, self.rho, lb, ub, xf,
-                     yf if m > 0 else None, self.diff2, second)
-        if full or active_set_newton:
-            self._mark_failed_second(eng)
         K.dr_second(self.dt, self.diff1, self.diff2, prm.theta_max, prm.log_theta_ref, prm.K_P, prm.K_I,
                     prm.lamb_min, prm.lamb_inc, self.err_sum, self.phase, self.lamb_next, self.theta)
+        xf, yf, gf, cf, of = self.fin
         prob.eval(xf, gf, cf, of, second)
-
-        if on_iteration is not None:
-            on_iteration(outer, self)
-        # ---- accept / reject, penalty, counters (solver.py:318-378)
         ph = self.phase
         self.newton_step_count += ((ph >= 2) & (ph <= 4)).sum() + ((ph == 3) | (ph == 4)).sum()
-        K.commit(self.phase, self.lamb_next, prm.lamb_max, dual_norm, self.mid, self.fin, self.cur, self.lamb,
-                 self.rho, self.iters, self.accepted, self.status)
+
+    def _control_single(self, fixed: bool):
+        """ResiduumRatioController.step (residuum_ratio_control.py:18-63) / FixedStepSizeController.step
+        (fixed_control.py:12-19): one Newton step per outer iteration."""
+        prm, prob, eng = self.params, self.problem, self.engine
+        run = self.run
+        ls_failed = self._first_newton_step()
+        lamb = 1.0 / self.dt
+        running = self.status == 0
+        failed = running & (eng.info != 0)
+        ok = running & ~failed
+        two, four, five = (torch.full_like(self.phase, v) for v in (2, 4, 5))
+        zero = torch.zeros_like(self.phase)
+        if fixed:
+            self.phase.copy_(torch.where(failed, five, torch.where(ok, two, zero)))
+            self.lamb_next.copy_(torch.where(failed, 2.0 * lamb, torch.full_like(lamb, prm.lamb_init)))
+        else:
+            x, y = self.cur[0], self._y(self.cur)
+            K.residual(x, y, x, y, self.dL0, self._cons(self.cur), prob.var_lb, prob.var_ub, self.dt, False, 0, None,
+                       None, self.orig_norm, run)
+            conv = ok & (self.mid_norm <= prm.newton_tol)
+            rest = ok & ~conv
+            theta = self.mid_norm / self.orig_norm
+            acc = rest & (theta <= prm.theta_max)
+            err = prm.log_theta_ref - torch.log(theta)              # controller.py:44-52,72-77 (log-PI)
+            err_new = self.err_sum + err
+            lmod = torch.exp(prm.K_P * err + prm.K_I * err_new)
+            self.err_sum.copy_(torch.where(acc, err_new, self.err_sum))
+            self.theta.copy_(theta)
+            lam_conv = torch.clamp(lamb * prm.lamb_red, min=prm.lamb_min)
+            lam_acc = torch.clamp(lamb / lmod, min=prm.lamb_min)
+            self.lamb_next.copy_(torch.where(failed, 2.0 * lamb, torch.where(conv, lam_conv, torch.where(
+                acc, lam_acc, lamb * prm.lamb_inc))))
+            self.phase.copy_(torch.where(failed, five, torch.where(conv | acc, two, torch.where(rest, four, zero))))
+        if ls_failed is not None:
+            self._line_search_failed(ls_failed)
+        self.newton_step_count += ok.sum()
+
+    EXACT_MAX_IT = 10      # exact_control.py:11
+    EXACT_RATE_BOUND = 0.5
+
+    def _control_exact(self):
+        """ExactController.step (exact_control.py:16-66): Newton steps until ||F|| <= newton_tol (accept, lambda / 2)
+        or the contraction rate exceeds 1/2 / ten steps are used up (reject, 2 lambda).  The steps alternate
+        between the `mid` and `fin` buffers; an instance that stops at an even step is committed from `mid`
+        (phase 2), at an odd step from `fin` (phase 3)."""
+        prm, prob, eng = self.params, self.problem, self.engine
+        run, loop = self.run, self.second
+        x, y = self.cur[0], self._y(self.cur)
+        K.residual(x, y, x, y, self.dL0, self._cons(self.cur), prob.var_lb, prob.var_ub, self.dt, False, 0, None, None,
+                   self.orig_norm, run)
+        ls_failed = self._first_newton_step()
+        lamb = 1.0 / self.dt
+        running = self.status == 0
+        failed = running & (eng.info != 0)
+        it = running & ~failed                      # instances still inside the Newton loop
+        curr = self.orig_norm.clone()
+        phase = torch.where(failed, torch.full_like(self.phase, 5), torch.zeros_like(self.phase))
+        lamb_next = torch.where(failed, 2.0 * lamb, lamb)
+        if ls_failed is not None:
+            self._line_search_failed(ls_failed)
+            it = it & ~ls_failed
+        pts = (self.mid, self.fin)
+        dLs = (self.dLm, self.dLf)
+        norms = (self.mid_norm, self.fin_norm)
+        diffs = (self.diff1, self.diff2)
+        nsteps = torch.zeros_like(self.newton_step_count)
+        for i in range(self.EXACT_MAX_IT):
+            val = norms[i % 2]
+            nsteps += it.sum()
+            conv = it & (val <= prm.newton_tol)
+            brk = it & ~conv & ((val / curr) > self.EXACT_RATE_BOUND)
+            last = i == self.EXACT_MAX_IT - 1
+            stop = conv | brk | (it if last else torch.zeros_like(it))
+            phase = torch.where(conv, torch.full_like(phase, 2 + (i % 2)), torch.where(stop & ~conv, torch.full_like(phase, 4), phase))
+            lamb_next = torch.where(conv, 0.5 * lamb, torch.where(stop & ~conv, 2.0 * lamb, lamb_next))
+            it = it & ~stop
+            curr = torch.where(it, val, curr)
+            if last:
+                break
+            self.loop_key.copy_(it.to(torch.int32))
+            K.build_worklist(self.loop_key, 1, 1, loop, parent=run)
+            loop.nwork = run.nwork
+            src, dst = pts[i % 2], pts[(i + 1) % 2]
+            Jsrc = self.Jbuf[1 + (i % 2)] if (prob.m > 0 and not prob.jac_constant) else self._J0
+            st = self._next_newton_step(src, dLs[i % 2], Jsrc, dst, diffs[(i + 1) % 2], loop)
+            # a failed refactorisation (Full / ActiveSet / Globalized) ends the loop like a StepSolverError
+            if self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet):
+                bad = it & (eng.info != 0)
+                phase = torch.where(bad, torch.full_like(phase, 5), phase)
+                lamb_next = torch.where(bad, 2.0 * lamb, lamb_next)
+                it = it & ~bad
+            if st is not None:
+                lsf = it & (st == 2)
+                self._line_search_failed(lsf)
+                it = it & ~lsf
+            self._eval_point(dst, dLs[(i + 1) % 2], 1 + ((i + 1) % 2), norms[(i + 1) % 2], loop)
+        self.phase.copy_(torch.where(self.status == 0, phase, torch.zeros_like(phase)))
+        self.lamb_next.copy_(lamb_next)
+        self.newton_step_count += nsteps
 
     def _line_search_failed(self, mask):
         """Armijo search exhausted (newton.py:294 raises a bare Exception that ends Solver.solve): the instance

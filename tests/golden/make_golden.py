@@ -370,6 +370,25 @@ def golden_constrained():
     np.savez_compressed(os.path.join(HERE, "constrained.npz"), **out)
 
 
+def golden_controllers():
+    """The other Newton-based step controllers (step_control.py:123-150): ResiduumRatio, Exact, Fixed."""
+    from pygradflow.params import StepControlType
+
+    out = {}
+    for ctl in ("ResiduumRatio", "Exact", "Fixed"):
+        kw = dict(step_control_type=StepControlType[ctl])
+        if ctl == "Fixed":
+            kw.update(iteration_limit=60)
+        for (n, m, k) in [(16, 8, 0), (32, 16, 2)]:
+            d = synth.qp_instance(k, n, m)
+            res = trace_solve(RefQP(d), params_for("Simplified", **kw), d["x0"], d["y0"])
+            out.update(flat(f"{ctl}/qp_n{n}_m{m}_k{k}", res))
+        d = synth.rosenbrock_instance(0, 8)
+        res = trace_solve(RefChainedRosenbrock(d), params_for("Simplified", **kw), d["x0"], d["y0"], keep_every=5)
+        out.update(flat(f"{ctl}/ros_n8_k0", res))
+    np.savez_compressed(os.path.join(HERE, "controllers.npz"), **out)
+
+
 def golden_ocp():
     """cfg4-style discretised optimal-control problems (small): full traces of the real reference."""
     out = {}
@@ -389,6 +408,7 @@ if __name__ == "__main__":
     golden_full_size_qp()
     golden_ocp()
     golden_constrained()
+    golden_controllers()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

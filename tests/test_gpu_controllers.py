@@ -1,0 +1,73 @@
+"""The other Newton-based step controllers of the reference (step_control.py:123-150: ResiduumRatio, Exact, Fixed)
+through the batched driver, per instance against the oracle and against traces of the REAL reference."""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_err  # noqa: E402
+from oracle import gradflow_oracle as orc  # noqa: E402
+from pygradflow_b200 import synth  # noqa: E402
+
+NAMES = {"ResiduumRatio": "residuum_ratio", "Exact": "exact", "Fixed": "fixed"}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _params(ctl, newton="Simplified"):
+    from pygradflow_b200.params import NewtonType, Params, StepControlType
+
+    return Params(step_control_type=StepControlType[ctl], newton_type=NewtonType[newton],
+                  iteration_limit=60 if ctl == "Fixed" else None)
+
+
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("ctl", ["ResiduumRatio", "Exact", "Fixed"])
+def test_controllers_qp_vs_oracle(ctl, newton):
+    from pygradflow_b200.problem import BatchedQP
+    from pygradflow_b200.solver import BatchedSolver
+
+    B, n, m = 8, 16, 8
+    d = synth.qp_batch(range(B), n, m)
+    prob = BatchedQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+    res = BatchedSolver(prob, _params(ctl, newton)).solve(d["x0"], d["y0"])
+    for b in range(B):
+        p = orc.DenseQP(d["H"][b], d["A"][b], d["g"][b], d["b"][b], d["lb"][b], d["ub"][b])
+        ref = orc.Solver(p, orc.OracleParams(step_control_type=NAMES[ctl], newton_type=newton.lower(),
+                                             iteration_limit=60 if ctl == "Fixed" else None)).solve(d["x0"][b], d["y0"][b])
+        assert int(res.status[b].item()) == ref.status, (b, ctl)
+        assert int(res.iterations[b].item()) == ref.iterations, (b, ctl)
+        assert int(res.accepted_steps[b].item()) == ref.accepted_steps, (b, ctl)
+        assert rel_err(res.x[b].cpu().numpy(), ref.x) <= 1e-8
+        assert rel_err(res.y[b].cpu().numpy(), ref.y) <= 1e-8
+
+
+@pytest.mark.parametrize("ctl", ["ResiduumRatio", "Exact", "Fixed"])
+def test_controllers_golden_reference(golden, ctl):
+    from pygradflow_b200.problem import BatchedQP, BatchedRosenbrock
+    from pygradflow_b200.solver import BatchedSolver
+
+    g = golden("controllers")
+    for (n, m, k) in [(16, 8, 0), (32, 16, 2)]:
+        d = synth.qp_batch([k], n, m)
+        prob = BatchedQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+        res = BatchedSolver(prob, _params(ctl)).solve(d["x0"], d["y0"])
+        key = f"{ctl}/qp_n{n}_m{m}_k{k}"
+        assert int(res.status[0].item()) == int(g[f"{key}/status"])
+        assert int(res.iterations[0].item()) == int(g[f"{key}/iterations"])
+        assert int(res.accepted_steps[0].item()) == int(g[f"{key}/accepted_steps"])
+        assert rel_err(res.x[0].cpu().numpy(), g[f"{key}/x"]) <= 1e-8
+    d = synth.rosenbrock_batch([0], 8)
+    prob = BatchedRosenbrock(d["a"], d["b"], d["lb"], d["ub"])
+    res = BatchedSolver(prob, _params(ctl)).solve(d["x0"], None)
+    key = f"{ctl}/ros_n8_k0"
+    assert int(res.status[0].item()) == int(g[f"{key}/status"])
+    assert int(res.iterations[0].item()) == int(g[f"{key}/iterations"])
+    assert int(res.accepted_steps[0].item()) == int(g[f"{key}/accepted_steps"])
+    assert rel_err(res.x[0].cpu().numpy(), g[f"{key}/x"]) <= 1e-7

@@ -197,6 +197,30 @@ def test_slack_transform_hs71_constrained(golden):
     assert rel_err(res.x, g["hs71_cons/Simplified/x"]) <= RTOL
 
 
+@pytest.mark.parametrize("ctl", ["ResiduumRatio", "Exact", "Fixed"])
+@pytest.mark.parametrize("prob", ["qp_n16_m8_k0", "qp_n32_m16_k2", "ros_n8_k0"])
+def test_other_step_controllers(golden, ctl, prob):
+    """residuum_ratio_control.py, exact_control.py, fixed_control.py against the reference's traces."""
+    g = golden("controllers")
+    key = f"{ctl}/{prob}"
+    if prob.startswith("qp"):
+        n, m, k = (int(t[1:]) for t in prob.split("_")[1:])
+        d = synth.qp_instance(k, n, m)
+        p = orc.DenseQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+    else:
+        d = synth.rosenbrock_instance(0, 8)
+        p = orc.ChainedRosenbrock(d["a"], d["b"], d["lb"], d["ub"])
+    name = {"ResiduumRatio": "residuum_ratio", "Exact": "exact", "Fixed": "fixed"}[ctl]
+    params = orc.OracleParams(step_control_type=name, iteration_limit=60 if ctl == "Fixed" else None)
+    res = orc.Solver(p, params).solve(d["x0"], d["y0"], record=True)
+    assert res.status == int(g[f"{key}/status"])
+    assert res.iterations == int(g[f"{key}/iterations"]) and res.accepted_steps == int(g[f"{key}/accepted_steps"])
+    assert [t["accept"] for t in res.trace] == list(g[f"{key}/accepts"])
+    for row, i in enumerate(g[f"{key}/trace_idx"]):
+        assert rel_err(res.trace[i]["x"], g[f"{key}/trace_x"][row]) <= 1e-8, (key, i)
+    assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8
+
+
 def test_solve_tame(golden):
     res = _check_solve(golden("solves"), "tame", orc.Tame(), np.zeros(2), np.zeros(1))
     assert np.allclose(res.x, [0.5, 0.5], atol=1e-6)  # tests/pygradflow/instances.py:57-68
