@@ -751,7 +751,12 @@ __global__ void __launch_bounds__(256) ldlt_solve_kernel(int ld, const int32_t* 
         for (int jj = wid; jj < jb; jj += nw) {
             const double* row = Kb + (size_t)(j0 + jj) * ld;
             double acc = 0.0;
-            for (int i = lane; i < j0; i += 32) acc += __ldg(row + i) * v[i];
+            int i = lane;
+            for (; i + 96 < j0; i += 128) {  // four loads in flight per lane
+                const double r0 = __ldg(row + i), r1 = __ldg(row + i + 32), r2 = __ldg(row + i + 64), r3 = __ldg(row + i + 96);
+                acc += r0 * v[i] + r1 * v[i + 32] + r2 * v[i + 64] + r3 * v[i + 96];
+            }
+            for (; i < j0; i += 32) acc += __ldg(row + i) * v[i];
             acc = warp_sum(acc);
             if (lane == 0) part[jj] = acc;
         }
@@ -788,7 +793,15 @@ __global__ void __launch_bounds__(256) ldlt_solve_kernel(int ld, const int32_t* 
         __syncthreads();
         for (int j = threadIdx.x; j < j0; j += blockDim.x) {
             double acc = 0.0;
-            for (int ii = 0; ii < jb; ii++) acc += __ldg(Kb + (size_t)(j0 + ii) * ld + j) * v[j0 + ii];
+            int ii = 0;
+            for (; ii + 8 <= jb; ii += 8) {  // eight loads in flight per thread
+                double h[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) h[u] = __ldg(Kb + (size_t)(j0 + ii + u) * ld + j);
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc += h[u] * v[j0 + ii + u];
+            }
+            for (; ii < jb; ii++) acc += __ldg(Kb + (size_t)(j0 + ii) * ld + j) * v[j0 + ii];
             v[j] -= acc;
         }
         __syncthreads();

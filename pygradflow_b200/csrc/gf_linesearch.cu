@@ -39,7 +39,12 @@ __global__ void merit_grad_kernel(int n, int m, const double* __restrict__ H, co
     for (int j = wid; j < m; j += nw) {
         const double* row = Jb + (size_t)j * n;
         double acc = 0.0;
-        for (int i = lane; i < n; i += 32) acc += __ldg(row + i) * v[i];
+        int i = lane;
+        for (; i + 96 < n; i += 128) {  // four loads in flight per lane
+            const double r0 = __ldg(row + i), r1 = __ldg(row + i + 32), r2 = __ldg(row + i + 64), r3 = __ldg(row + i + 96);
+            acc += r0 * v[i] + r1 * v[i + 32] + r2 * v[i + 64] + r3 * v[i + 96];
+        }
+        for (; i < n; i += 32) acc += __ldg(row + i) * v[i];
         acc = warp_sum(acc);  // u_j = (J v)_j
         if (lane == 0) {
             const double fy = Fb[n + j];
@@ -53,9 +58,25 @@ __global__ void merit_grad_kernel(int n, int m, const double* __restrict__ H, co
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double acc = lamb * Fb[i];
         const double* hc = Hb + i;  // H symmetric: column i read as row i
-        for (int j = 0; j < n; j++) acc = fma(__ldg(hc + (size_t)j * n), v[j], acc);
+        int j = 0;
+        for (; j + 8 <= n; j += 8) {  // eight loads in flight per thread
+            double h[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) h[u] = __ldg(hc + (size_t)(j + u) * n);
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = fma(h[u], v[j + u], acc);
+        }
+        for (; j < n; j++) acc = fma(__ldg(hc + (size_t)j * n), v[j], acc);
         const double* jc = Jb + i;
-        for (int j = 0; j < m; j++) acc = fma(__ldg(jc + (size_t)j * n), z[j], acc);
+        j = 0;
+        for (; j + 8 <= m; j += 8) {
+            double h[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) h[u] = __ldg(jc + (size_t)(j + u) * n);
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = fma(h[u], z[j + u], acc);
+        }
+        for (; j < m; j++) acc = fma(__ldg(jc + (size_t)j * n), z[j], acc);
         ip += acc * dx[(size_t)b * n + i];
     }
     const double s2 = block_sum(ss, red);

@@ -337,6 +337,33 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
     }
 }
 
+// Row dot with four loads in flight per lane / column axpy term with eight loads in flight per thread (the
+// substitution kernels are HBM-bound: without the explicit batching one load per lane is outstanding).
+__device__ __forceinline__ double lu_row_dot(const double* __restrict__ row, const double* v, int lo, int hi, int lane) {
+    double acc = 0.0;
+    int i = lo + lane;
+    for (; i + 96 < hi; i += 128) {
+        const double r0 = __ldg(row + i), r1 = __ldg(row + i + 32), r2 = __ldg(row + i + 64), r3 = __ldg(row + i + 96);
+        acc += r0 * v[i] + r1 * v[i + 32] + r2 * v[i + 64] + r3 * v[i + 96];
+    }
+    for (; i < hi; i += 32) acc += __ldg(row + i) * v[i];
+    return acc;
+}
+
+__device__ __forceinline__ double lu_col_dot(const double* __restrict__ col, int ld, const double* v, int jb) {
+    double acc = 0.0;
+    int jj = 0;
+    for (; jj + 8 <= jb; jj += 8) {
+        double h[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) h[u] = __ldg(col + (size_t)(jj + u) * ld);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += h[u] * v[jj + u];
+    }
+    for (; jj < jb; jj++) acc += __ldg(col + (size_t)jj * ld) * v[jj];
+    return acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Blocked substitution on the packed LU factors; rhs[b] (length >= N) is overwritten by the solution.
 __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
@@ -366,7 +393,7 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             for (int jj = wid; jj < jb; jj += nw) {
                 const double* row = Kb + (size_t)(j0 + jj) * ld;
                 double acc = 0.0;
-                for (int i = lane; i < j0; i += 32) acc += __ldg(row + i) * v[i];
+                acc = lu_row_dot(row, v, 0, j0, lane);
                 acc = warp_sum(acc);
                 if (lane == 0) part[jj] = acc;
             }
@@ -394,7 +421,7 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             for (int jj = wid; jj < jb; jj += nw) {
                 const double* row = Kb + (size_t)(j0 + jj) * ld;
                 double acc = 0.0;
-                for (int i = j0 + jb + lane; i < N; i += 32) acc += __ldg(row + i) * v[i];
+                acc = lu_row_dot(row, v, j0 + jb, N, lane);
                 acc = warp_sum(acc);
                 if (lane == 0) part[jj] = acc;
             }
@@ -444,7 +471,7 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             __syncthreads();
             for (int i = j0 + jb + threadIdx.x; i < N; i += blockDim.x) {
                 double acc = 0.0;
-                for (int jj = 0; jj < jb; jj++) acc += __ldg(Kb + (size_t)(j0 + jj) * ld + i) * v[j0 + jj];
+                acc = lu_col_dot(Kb + (size_t)j0 * ld + i, ld, v + j0, jb);
                 v[i] -= acc;
             }
             __syncthreads();
@@ -471,7 +498,7 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             __syncthreads();
             for (int i = threadIdx.x; i < j0; i += blockDim.x) {
                 double acc = 0.0;
-                for (int jj = 0; jj < jb; jj++) acc += __ldg(Kb + (size_t)(j0 + jj) * ld + i) * v[j0 + jj];
+                acc = lu_col_dot(Kb + (size_t)j0 * ld + i, ld, v + j0, jb);
                 v[i] -= acc;
             }
             __syncthreads();
