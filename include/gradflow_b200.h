@@ -104,6 +104,13 @@ int gf_residual(int B, int n, int m, const double* x, const double* y, const dou
                 const double* dL, const double* cons, const double* lb, const double* ub, const double* dt,
                 int scaled, int active_mode, uint8_t* active, double* F, double* nrm, const int32_t* work,
                 const int32_t* nwork_dev, int nwork, void* stream);
+/* the same with the tau-variant of the active-set decision: tau[B] from ActiveSetType Explicit / Smallest / Largest
+ * (newton_control.py:60-88); the active set is decided on f_x x + f_x0 x0 - f_d dL (implicit_func.py:237-244),
+ * the residual is unchanged.  tau == NULL is gf_residual. */
+int gf_residual_tau(int B, int n, int m, const double* x, const double* y, const double* x0, const double* y0,
+                    const double* dL, const double* cons, const double* lb, const double* ub, const double* dt,
+                    const double* tau, int scaled, int active_mode, uint8_t* active, double* F, double* nrm,
+                    const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 
 /* np.where(~active)[0] / np.where(active)[0] (scaled_step_solver.py:51-52): perm[b] = inactive indices
  * ascending followed by active indices ascending, nI[b] = #inactive, Nvec[b] = nI[b] + m (may be NULL). */

@@ -95,6 +95,8 @@ class OracleParams:
     newton_type: str = "simplified"  # simplified | full | active_set | globalized
     newton_tol: float = 1e-8
     step_control_type: str = "distance_ratio"  # distance_ratio | residuum_ratio | exact | fixed
+    active_set_type: str = "standard"  # standard | explicit | smallest | largest  (params.py:14-18,225-227)
+    active_set_tau: Optional[float] = None
     penalty_update: str = "dual_norm"  # dual_norm | constant
     iteration_limit: Optional[int] = None
     obj_lower_limit: float = -1e10
@@ -1076,8 +1078,34 @@ class DistanceRatioController:
         self.trace_hook = None
 
     def _newton(self, iterate, rho, dt):
-        # newton_control.py:22-38 with compute_tau -> None (ActiveSetType.Standard, :75-76)
-        return newton_method(self.problem, self.params, iterate, dt, rho, None)
+        # newton_control.py:22-38
+        return newton_method(self.problem, self.params, iterate, dt, rho, self.compute_tau(iterate, rho))
+
+    def tau_vals(self, iterate, rho):
+        """newton_control.py:40-58."""
+        x, g = iterate.x, iterate.aug_lag_deriv_x(rho)
+        xl, xu = self.problem.var_lb, self.problem.var_ub
+        nonzero = np.logical_not(np.isclose(g, 0.0))
+        pos, neg = (g > 0.0) & nonzero, (g < 0.0) & nonzero
+        tv = np.full_like(x, fill_value=-1)
+        tv[pos] = (x[pos] - xl[pos]) / g[pos]
+        tv[neg] = (xu[neg] - x[neg]) / -g[neg]
+        return tv
+
+    def compute_tau(self, iterate, rho):
+        """newton_control.py:60-88 (no user active_set_method)."""
+        t = self.params.active_set_type
+        if t == "explicit":
+            assert self.params.active_set_tau is not None
+            return self.params.active_set_tau
+        if t == "standard":
+            return None
+        tv = self.tau_vals(iterate, rho)
+        if t == "smallest":
+            if (tv <= 0).all():
+                return 1.0
+            return 0.5 * np.min(tv[tv > 0])
+        return max(np.max(tv), 1.0)
 
     def step(self, iterate, rho, dt):
         assert dt > 0.0

@@ -20,14 +20,21 @@ __global__ void residual_kernel(int n, int m, const double* __restrict__ x, cons
                                 const double* __restrict__ x0, const double* __restrict__ y0,
                                 const double* __restrict__ dL, const double* __restrict__ cons,
                                 const double* __restrict__ lb, const double* __restrict__ ub,
-                                const double* __restrict__ dt, int scaled, int active_mode,
-                                uint8_t* __restrict__ active, double* __restrict__ F, double* __restrict__ nrm,
-                                GfWork work) {
+                                const double* __restrict__ dt, const double* __restrict__ tau, int scaled,
+                                int active_mode, uint8_t* __restrict__ active, double* __restrict__ F,
+                                double* __restrict__ nrm, GfWork work) {
     const int b = gf_instance(work, blockIdx.x);
     if (b < 0) return;
     __shared__ double red[32];
     const double dtb = dt[b];
     const double lamb = 1.0 / dtb;  // implicit_func.py:212
+    // tau-variant of the point whose box position decides the active set (implicit_func.py:237-244,
+    // newton_control.py:60-88); tau never enters the residual itself (:219-231)
+    const bool use_tau = tau != nullptr && active_mode == 0;
+    const double tb = use_tau ? tau[b] : 0.0;
+    const double f_x = __dmul_rn(lamb, __dsub_rn(1.0, __dmul_rn(tb, lamb)));
+    const double f_x0 = __dmul_rn(__dmul_rn(tb, lamb), lamb);
+    const double f_d = __dmul_rn(tb, lamb);
     double ss = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const size_t o = (size_t)b * n + i;
@@ -45,7 +52,15 @@ __global__ void residual_kernel(int n, int m, const double* __restrict__ x, cons
         }
         bool act;
         if (active_mode == 0) {
-            act = (p < lo - GF_ACTIVE_SLACK) || (p > hi + GF_ACTIVE_SLACK);  // :44
+            double pa = p;
+            if (use_tau) {
+                if (scaled)  // f_x x + f_x0 x0 - f_d dL
+                    pa = __dsub_rn(__dadd_rn(__dmul_rn(f_x, x[o]), __dmul_rn(f_x0, x0[o])), __dmul_rn(f_d, dL[o]));
+                else         // (1 - tau lamb) x + (tau lamb) x0 - tau dL   (:133-146)
+                    pa = __dsub_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, f_d), x[o]), __dmul_rn(f_d, x0[o])),
+                                   __dmul_rn(tb, dL[o]));
+            }
+            act = (pa < lo - GF_ACTIVE_SLACK) || (pa > hi + GF_ACTIVE_SLACK);  // :44
             if (active != nullptr) active[o] = act ? 1 : 0;
         } else {
             act = active[o] != 0;
@@ -462,7 +477,21 @@ extern "C" int gf_residual(int B, int n, int m, const double* x, const double* y
     if (active_mode == 1 && !active) return GF_ERR_ARG;
     if (nwork <= 0) return GF_OK;
     residual_kernel<<<nwork, pick_threads(n + m), 0, (cudaStream_t)stream>>>(
-        n, m, x, y, x0, y0, dL, cons, lb, ub, dt, scaled, active_mode, active, F, nrm, GfWork{work, nwork_dev});
+        n, m, x, y, x0, y0, dL, cons, lb, ub, dt, nullptr, scaled, active_mode, active, F, nrm, GfWork{work, nwork_dev});
+    return gf_launch_status();
+}
+
+extern "C" int gf_residual_tau(int B, int n, int m, const double* x, const double* y, const double* x0,
+                               const double* y0, const double* dL, const double* cons, const double* lb,
+                               const double* ub, const double* dt, const double* tau, int scaled, int active_mode,
+                               uint8_t* active, double* F, double* nrm, const int32_t* work, const int32_t* nwork_dev,
+                               int nwork, void* stream) {
+    if (B <= 0 || n <= 0 || m < 0 || !x || !x0 || !dL || !lb || !ub || !dt) return GF_ERR_ARG;
+    if (m > 0 && (!y || !y0 || !cons)) return GF_ERR_ARG;
+    if (active_mode == 1 && !active) return GF_ERR_ARG;
+    if (nwork <= 0) return GF_OK;
+    residual_kernel<<<nwork, pick_threads(n + m), 0, (cudaStream_t)stream>>>(
+        n, m, x, y, x0, y0, dL, cons, lb, ub, dt, tau, scaled, active_mode, active, F, nrm, GfWork{work, nwork_dev});
     return gf_launch_status();
 }
 

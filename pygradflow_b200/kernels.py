@@ -81,9 +81,14 @@ def aug_lag_grad(J, grad, cons, y, rho, dL, jty, jtc, work: WorkList):
           *_w(work))
 
 
-def residual(x, y, x0, y0, dL, cons, lb, ub, dt, scaled: bool, active_mode: int, active, F, nrm, work: WorkList):
+def residual(x, y, x0, y0, dL, cons, lb, ub, dt, scaled: bool, active_mode: int, active, F, nrm, work: WorkList,
+             tau=None):
     B, n = x.shape
     m = 0 if y is None else y.shape[1]
+    if tau is not None:
+        _call("gf_residual_tau", B, n, m, ptr(x), ptr(y), ptr(x0), ptr(y0), ptr(dL), ptr(cons), ptr(lb), ptr(ub),
+              ptr(dt), ptr(tau), 1 if scaled else 0, active_mode, ptr(active), ptr(F), ptr(nrm), *_w(work))
+        return
     _call("gf_residual", B, n, m, ptr(x), ptr(y), ptr(x0), ptr(y0), ptr(dL), ptr(cons), ptr(lb), ptr(ub), ptr(dt),
           1 if scaled else 0, active_mode, ptr(active), ptr(F), ptr(nrm), *_w(work))
 

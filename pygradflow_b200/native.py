@@ -28,6 +28,7 @@ SIGNATURES = {
     "gf_ocp_hess": [_I, _I, _I, _I, _D, _P, _P, _P, _P, _P] + _WORK,
     "gf_aug_lag_grad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_residual": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P] + _WORK,
+    "gf_residual_tau": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P] + _WORK,
     "gf_index_sets": [_I, _I, _I, _P, _P, _P, _P] + _WORK,
     "gf_kkt_assemble": [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_kkt_rhs": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,

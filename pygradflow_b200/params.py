@@ -34,6 +34,15 @@ class LinearSolverType(enum.Enum):
     Banded = enum.auto()
 
 
+class ActiveSetType(enum.Enum):
+    """pygradflow/params.py:14-18: how the point that decides the active set is chosen (newton_control.py:60-88)."""
+
+    Standard = enum.auto()
+    Explicit = enum.auto()
+    SmallestActiveSet = enum.auto()
+    LargestActiveSet = enum.auto()
+
+
 class StepControlType(enum.Enum):
     """pygradflow/params.py:113-130, the Newton-based controllers (step_control.py:123-150).  Optimizing / BoxReduced
     solve the proximal sub-problem with Ipopt / a box solver instead of the Newton-KKT path and are out of scope."""
@@ -73,6 +82,8 @@ class Params:
     newton_type: NewtonType = NewtonType.Simplified
     newton_tol: float = 1e-8
     step_control_type: StepControlType = StepControlType.DistanceRatio
+    active_set_type: ActiveSetType = ActiveSetType.Standard
+    active_set_tau: Optional[float] = None
     step_solver: Optional[Callable[..., Any]] = None
     linear_solver_type: LinearSolverType = LinearSolverType.Auto
     penalty_update: PenaltyUpdate = PenaltyUpdate.DualNorm
@@ -83,7 +94,8 @@ class Params:
 
     def __post_init__(self):
         for key, cls in (("newton_type", NewtonType), ("linear_solver_type", LinearSolverType),
-                         ("penalty_update", PenaltyUpdate), ("step_control_type", StepControlType)):
+                         ("penalty_update", PenaltyUpdate), ("step_control_type", StepControlType),
+                         ("active_set_type", ActiveSetType)):
             v = getattr(self, key)
             if not isinstance(v, cls):
                 setattr(self, key, cls[_enum_name(v)])  # accepts strings and the reference's own enums

@@ -23,7 +23,7 @@ import torch
 from . import kernels as K
 from .engine import KKTEngine
 from .kernels import WorkList
-from .params import NewtonType, Params, PenaltyUpdate, StepControlType
+from .params import ActiveSetType, NewtonType, Params, PenaltyUpdate, StepControlType
 from .problem import BatchedProblem
 
 PHASE_SECOND = 1
@@ -82,6 +82,8 @@ class BatchedSolver:
         self.fin_norm, self.orig_norm = (torch.zeros((B,), **f64) for _ in range(2))
         self.loop_key = torch.zeros((B,), **i32)
         self.theta = torch.zeros((B,), **f64)
+        self.tau = torch.zeros((B,), **f64)
+        self._tau = None
         self.total_res = torch.zeros((B,), **f64)
         self.status = torch.zeros((B,), **i32)
         self.iters = torch.zeros((B,), **i32)
@@ -226,8 +228,9 @@ class BatchedSolver:
         x, y, grad, cons, obj = self.cur
         J0 = self._J0
         lb, ub = prob.var_lb, prob.var_ub
+        tau = self._compute_tau()
         K.residual(x, self._y(self.cur), x, self._y(self.cur), self.dL0, self._cons(self.cur), lb, ub, self.dt,
-                   True, 0, eng.active, self.F, None, run)
+                   True, 0, eng.active, self.F, None, run, tau=tau)
         xm, ym, gm, cm, om = self.mid
         ls_failed = None
         if self.globalized is not None:
@@ -244,6 +247,32 @@ class BatchedSolver:
                      ym if m > 0 else None, self.diff1, run)
         self._eval_point(self.mid, self.dLm, 1, self.mid_norm, run)
         return ls_failed
+
+    def _compute_tau(self):
+        """NewtonController.compute_tau / tau_vals (newton_control.py:40-88) at the current iterate, per instance."""
+        prm, prob = self.params, self.problem
+        t = prm.active_set_type
+        self._tau = None
+        if t == ActiveSetType.Standard:
+            assert prm.active_set_tau is None
+            return None
+        assert self.globalized is None, "tau-based active sets with the globalized Newton method are not supported"
+        if t == ActiveSetType.Explicit:
+            assert prm.active_set_tau is not None
+            self.tau.fill_(float(prm.active_set_tau))
+        else:
+            x, g = self.cur[0], self.dL0
+            nonzero = g.abs() > 1e-8                                  # np.isclose(g, 0.0): atol 1e-8
+            pos, neg = (g > 0.0) & nonzero, (g < 0.0) & nonzero
+            tv = torch.where(pos, (x - prob.var_lb) / g, torch.where(neg, (prob.var_ub - x) / -g, torch.full_like(x, -1.0)))
+            if t == ActiveSetType.SmallestActiveSet:
+                big = torch.where(tv > 0, tv, torch.full_like(tv, float("inf")))
+                mn = big.min(dim=1).values
+                self.tau.copy_(torch.where(torch.isinf(mn), torch.ones_like(mn), 0.5 * mn))
+            else:
+                self.tau.copy_(torch.clamp(tv.max(dim=1).values, min=1.0))
+        self._tau = self.tau
+        return self._tau
 
     def _eval_point(self, pt, dL, jslot, norm_out, work):
         """Problem callbacks at `pt`, its augmented-Lagrangian gradient and ||F_unscaled(pt)|| w.r.t. the current
@@ -277,7 +306,7 @@ class BatchedSolver:
             # derivatives frozen (newton.py:205-215).  Refactoring with an unchanged active set
             # reproduces the same factor, so it is done unconditionally.
             K.residual(src[0], self._y(src), x, y, dL_src, self._cons(src), lb, ub, self.dt, True, 0, eng.active,
-                       self.F, None, work)
+                       self.F, None, work, tau=self._tau)
             if full:
                 Hs = prob.lag_hess(src[0], self._y(src), self.Hbuf[1], work)
                 Js = J_src

@@ -389,6 +389,23 @@ def golden_controllers():
     np.savez_compressed(os.path.join(HERE, "controllers.npz"), **out)
 
 
+def golden_active_set_types():
+    """tau-based active sets (newton_control.py:40-88, implicit_func.py:233-246)."""
+    from pygradflow.params import ActiveSetType
+
+    out = {}
+    cases = [("Smallest", dict(active_set_type=ActiveSetType.SmallestActiveSet)),
+             ("Largest", dict(active_set_type=ActiveSetType.LargestActiveSet)),
+             ("Explicit", dict(active_set_type=ActiveSetType.Explicit, active_set_tau=0.3))]
+    for name, kw in cases:
+        for newton in ("Simplified", "Full"):
+            for (n, m, k) in [(16, 8, 0), (32, 16, 2)]:
+                d = synth.qp_instance(k, n, m)
+                res = trace_solve(RefQP(d), params_for(newton, **kw), d["x0"], d["y0"])
+                out.update(flat(f"{name}/{newton}/qp_n{n}_m{m}_k{k}", res))
+    np.savez_compressed(os.path.join(HERE, "active_set_types.npz"), **out)
+
+
 def golden_ocp():
     """cfg4-style discretised optimal-control problems (small): full traces of the real reference."""
     out = {}
@@ -409,6 +426,7 @@ if __name__ == "__main__":
     golden_ocp()
     golden_constrained()
     golden_controllers()
+    golden_active_set_types()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -71,3 +71,53 @@ def test_controllers_golden_reference(golden, ctl):
     assert int(res.iterations[0].item()) == int(g[f"{key}/iterations"])
     assert int(res.accepted_steps[0].item()) == int(g[f"{key}/accepted_steps"])
     assert rel_err(res.x[0].cpu().numpy(), g[f"{key}/x"]) <= 1e-7
+
+
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("kind", ["Smallest", "Largest", "Explicit"])
+def test_tau_active_set_types_vs_oracle(kind, newton):
+    """ActiveSetType Explicit / SmallestActiveSet / LargestActiveSet (newton_control.py:40-88): the active set is
+    decided on the tau-variant of the projected point (implicit_func.py:237-244), per instance."""
+    from pygradflow_b200.params import ActiveSetType, NewtonType, Params
+    from pygradflow_b200.problem import BatchedQP
+    from pygradflow_b200.solver import BatchedSolver
+
+    B, n, m = 6, 16, 8
+    d = synth.qp_batch(range(B), n, m)
+    prob = BatchedQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+    kw = {"Smallest": dict(active_set_type=ActiveSetType.SmallestActiveSet),
+          "Largest": dict(active_set_type=ActiveSetType.LargestActiveSet),
+          "Explicit": dict(active_set_type=ActiveSetType.Explicit, active_set_tau=0.3)}[kind]
+    okw = {"Smallest": dict(active_set_type="smallest"), "Largest": dict(active_set_type="largest"),
+           "Explicit": dict(active_set_type="explicit", active_set_tau=0.3)}[kind]
+    res = BatchedSolver(prob, Params(newton_type=NewtonType[newton], **kw)).solve(d["x0"], d["y0"])
+    for b in range(B):
+        p = orc.DenseQP(d["H"][b], d["A"][b], d["g"][b], d["b"][b], d["lb"][b], d["ub"][b])
+        ref = orc.Solver(p, orc.OracleParams(newton_type=newton.lower(), **okw)).solve(d["x0"][b], d["y0"][b])
+        assert int(res.status[b].item()) == ref.status == 1
+        if kind == "Largest":  # hundreds of iterations: past the rounding-noise horizon the paths differ slightly
+            assert abs(int(res.iterations[b].item()) - ref.iterations) <= 0.1 * ref.iterations
+            assert rel_err(res.x[b].cpu().numpy(), ref.x) <= 1e-4
+        else:
+            assert int(res.iterations[b].item()) == ref.iterations
+            assert int(res.accepted_steps[b].item()) == ref.accepted_steps
+            assert rel_err(res.x[b].cpu().numpy(), ref.x) <= 1e-8
+
+
+def test_tau_active_set_types_golden_reference(golden):
+    from pygradflow_b200.params import ActiveSetType, NewtonType, Params
+    from pygradflow_b200.problem import BatchedQP
+    from pygradflow_b200.solver import BatchedSolver
+
+    g = golden("active_set_types")
+    for name, kw in [("Smallest", dict(active_set_type=ActiveSetType.SmallestActiveSet)),
+                     ("Explicit", dict(active_set_type=ActiveSetType.Explicit, active_set_tau=0.3))]:
+        for newton in ("Simplified", "Full"):
+            for (n, m, k) in [(16, 8, 0), (32, 16, 2)]:
+                d = synth.qp_batch([k], n, m)
+                prob = BatchedQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+                res = BatchedSolver(prob, Params(newton_type=NewtonType[newton], **kw)).solve(d["x0"], d["y0"])
+                key = f"{name}/{newton}/qp_n{n}_m{m}_k{k}"
+                assert int(res.status[0].item()) == int(g[f"{key}/status"])
+                assert int(res.iterations[0].item()) == int(g[f"{key}/iterations"])
+                assert rel_err(res.x[0].cpu().numpy(), g[f"{key}/x"]) <= 1e-8

@@ -221,6 +221,22 @@ def test_other_step_controllers(golden, ctl, prob):
     assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8
 
 
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("kind", ["Smallest", "Explicit"])
+def test_tau_active_set_types(golden, kind, newton):
+    """newton_control.py:40-88 + implicit_func.py:237-244 against the reference."""
+    g = golden("active_set_types")
+    okw = {"Smallest": dict(active_set_type="smallest"), "Explicit": dict(active_set_type="explicit", active_set_tau=0.3)}[kind]
+    for (n, m, k) in [(16, 8, 0), (32, 16, 2)]:
+        d = synth.qp_instance(k, n, m)
+        p = orc.DenseQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+        res = orc.Solver(p, orc.OracleParams(newton_type=NEWTON[newton], **okw)).solve(d["x0"], d["y0"], record=True)
+        key = f"{kind}/{newton}/qp_n{n}_m{m}_k{k}"
+        assert res.status == int(g[f"{key}/status"]) and res.iterations == int(g[f"{key}/iterations"])
+        assert [t["accept"] for t in res.trace] == list(g[f"{key}/accepts"])
+        assert rel_err(res.x, g[f"{key}/x"]) <= RTOL
+
+
 def test_solve_tame(golden):
     res = _check_solve(golden("solves"), "tame", orc.Tame(), np.zeros(2), np.zeros(1))
     assert np.allclose(res.x, [0.5, 0.5], atol=1e-6)  # tests/pygradflow/instances.py:57-68
