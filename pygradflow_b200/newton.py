@@ -110,15 +110,4 @@ class NewtonKKTStepper:
 
     def _factor_only(self, H, J, rho):
         """Factorise the assembled K (KKTEngine.factor minus the assembly, so the phases time separately)."""
-        eng, w = self.engine, self.work
-        Nmax = self.problem.n + self.problem.m
-        if eng.linear in (LinearSolverType.LU, LinearSolverType.Banded):
-            eng.factor_assembled(H, J, self.dt, rho, w)
-            return
-        K.ldlt_factor(eng.K, Nmax, eng.Nvec, eng.dvec, eng.info, eng.nneg, eng.nI, w)
-        eng.fbkey.copy_(eng.info)
-        K.build_worklist(eng.fbkey, 0, 0, eng._fb, parent=None, invert=True)
-        eng._fb.nwork = w.nwork
-        K.kkt_assemble(H, J, eng.perm, eng.nI, self.dt, rho, eng.K, 1, False, eng._fb)
-        K.lu_factor(eng.K, Nmax, eng.Nvec, eng.piv, eng.info_lu, eng._fb)
-        torch.where(eng.fbkey != 0, eng.info_lu, eng.info, out=eng.info)
+        self.engine.factor_assembled(H, J, self.dt, rho, self.work)

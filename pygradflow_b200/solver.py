@@ -50,11 +50,10 @@ class BatchedResult:
 class BatchedSolver:
     """``Solver(problem, params).solve(x0, y0)`` for a whole batch on one GPU."""
 
-    def __init__(self, problem: BatchedProblem, params: Optional[Params] = None, sync_every: int = 1,
-                 use_graph: bool = True, graph_steps: int = 8):
+    def __init__(self, problem: BatchedProblem, params: Optional[Params] = None, use_graph: bool = True,
+                 graph_steps: int = 8):
         self.problem = problem
         self.params = params if params is not None else Params()
-        self.sync_every = max(1, int(sync_every))
         self.use_graph = bool(use_graph)
         self.graph_steps = max(1, int(graph_steps))  # captured units replayed between two reads of the running count
         p = problem

@@ -32,7 +32,7 @@ def main():
     ap.add_argument("--linear", default="Auto")
     ap.add_argument("--newton", default="Simplified")
     ap.add_argument("--check", type=int, default=4)
-    ap.add_argument("--sync-every", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true", help="run every outer iteration eagerly (no CUDA-graph replay)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     B = args.B
@@ -54,7 +54,7 @@ def main():
         x0, y0 = d["x0"], d["y0"]
     gen_s = time.perf_counter() - t0
     params = Params(linear_solver_type=LinearSolverType[args.linear], newton_type=NewtonType[args.newton])
-    solver = BatchedSolver(prob, params, sync_every=args.sync_every)
+    solver = BatchedSolver(prob, params, use_graph=not args.no_graph)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = solver.solve(x0, y0)
