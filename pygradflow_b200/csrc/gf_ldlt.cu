@@ -683,7 +683,10 @@ __global__ void __launch_bounds__(256, 3) ldlt_diag0_kernel(int ld, const int32_
     const int b = gf_instance(work, woff + blockIdx.x);
     if (b < 0) return;
     extern __shared__ double sm[];
-    if (padded_order(Nvec, Nfixed, b, ld) <= 0) return;
+    if (padded_order(Nvec, Nfixed, b, ld) <= 0) {  // empty system (everything active, no constraints): trivially ok
+        if (threadIdx.x == 0) { info[b] = 0; nneg[b] = 0; }
+        return;
+    }
     double(*S)[DP] = reinterpret_cast<double(*)[DP]>(sm);
     const double* Kb = K + (size_t)b * ld * ld;
     for (int e = threadIdx.x; e < NB * NB / 2; e += blockDim.x) {

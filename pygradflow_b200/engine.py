@@ -123,7 +123,15 @@ class KKTEngine:
         if self.linear == LinearSolverType.LU:
             K.lu_factor(self.K, Nmax, self.Nvec, self.piv, self.info, work)
             return
+        ev = getattr(self, "ldlt_events", None)  # optional CUDA-event pairs around the factorisation launches alone
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         K.ldlt_factor(self.K, Nmax, self.Nvec, self.dvec, self.info, self.nneg, self.nI, work)
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            ev.append((e0, e1))
         # Instances whose pivots are not those of a quasi-definite matrix (or hit a zero pivot) are
         # re-assembled in full and factorised with partial pivoting, like the reference's LU.
         self.fbkey.copy_(self.info)

@@ -51,6 +51,12 @@ class NewtonKKTStepper:
     # -- optional per-phase CUDA-event timing (used by bench.py for the roofline numbers) -----------
     def enable_timing(self):
         self.events = {ph: [] for ph in PHASES}
+        self.engine.ldlt_events = []
+
+    def ldlt_ms(self) -> Optional[float]:
+        """Mean milliseconds of the gf_ldlt_factor launches alone (inside the `factor` phase), after a synchronize."""
+        ev = getattr(self.engine, "ldlt_events", None)
+        return sum(a.elapsed_time(b) for a, b in ev) / len(ev) if ev else None
 
     def _mark(self):
         e = torch.cuda.Event(enable_timing=True)

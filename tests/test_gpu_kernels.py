@@ -331,3 +331,17 @@ def test_ldlt_flags_non_quasidefinite(K):
     bad[3, 3] = -5.0
     _, info, _, _, _ = _ldlt_gpu(K, [Km, bad], [r, r], npos=[96 - m, 96 - m])
     assert info[0] == 0 and info[1] == -2
+
+
+def test_ldlt_empty_system_resets_info(K):
+    """N = 0 (everything active, m = 0): nothing to factorise, but a stale info word must not survive."""
+    Kt = torch.zeros(2, 64, 64, dtype=torch.float64, device="cuda")
+    dvec = torch.zeros(2, 64, dtype=torch.float64, device="cuda")
+    info = torch.full((2,), 7, dtype=torch.int32, device="cuda")
+    nneg = torch.full((2,), 5, dtype=torch.int32, device="cuda")
+    Nv = torch.zeros(2, dtype=torch.int32, device="cuda")
+    rhs = torch.ones(2, 64, dtype=torch.float64, device="cuda")
+    K.ldlt_factor(Kt, 0, Nv, dvec, info, nneg, None, allw(K, 2))
+    K.ldlt_solve(Kt, 0, Nv, rhs, allw(K, 2))
+    K.ldlt_factor(Kt, 5, Nv, dvec, info, nneg, None, allw(K, 2))  # Nmax > 0 but every instance empty
+    assert info.cpu().tolist() == [0, 0] and nneg.cpu().tolist() == [0, 0]
