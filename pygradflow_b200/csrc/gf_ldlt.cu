@@ -336,7 +336,8 @@ __device__ __forceinline__ double xt_fragment(const double* Xs, int kq, int n) {
 
 // One ROWS x 64 tile of block column k (rows i0.., all inside the padded order): update + triangular solve.
 // ROWS = 128: 4 x 2 warps of 32 x 32;  ROWS = 64 (odd remainder block): 2 x 4 warps of 32 x 16.
-template <int ROWS>
+// LROWS: A rows the shared-memory layout is sized for (128 inside the column kernel, 64 in the 64-row-only kernel).
+template <int ROWS, int LROWS = TM>
 __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int ld, double* __restrict__ Kb,
                                                 const double* __restrict__ db) {
     constexpr int WN = (ROWS == 128) ? 2 : 4;   // warps along the 64 columns
@@ -344,7 +345,10 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     constexpr int WC = NI * 8;                  // columns per warp
     constexpr int AT = ROWS / 16;               // 16-byte pieces per thread per stage for the A rows
     double* As = sm;                            // stage s: A rows at s * STAGE_ROWS * PSP, B rows TM rows later
-    double* Bs = sm + TM * PSP;
+    constexpr int SSTRIDE = (LROWS + TN) * PSP;  // doubles per pipeline stage
+    static_assert(NB * EP <= SSTRIDE, "Xs must fit into one pipeline stage");
+    static_assert(ROWS <= LROWS, "layout too small");
+    double* Bs = sm + LROWS * PSP;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm = wid / WN, wn = wid % WN;
     const int g = lane >> 2, q = lane & 3;
@@ -363,8 +367,8 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     auto load_stage = [&](int chunk, int stage) {
         const double* ga = gA + (size_t)(chunk >> 1) * NB * ld + (chunk & 1) * PKC;
         const double* gb = gB + chunk * PKC;
-        double* sa = sA + stage * STAGE_ROWS * PSP;
-        double* sb = sB + stage * STAGE_ROWS * PSP;
+        double* sa = sA + stage * SSTRIDE;
+        double* sb = sB + stage * SSTRIDE;
 #pragma unroll
         for (int t = 0; t < AT; t++) cp_async16(sa + t * 16 * PSP, ga + (t & 3) * gstride + (t >> 2) * NB);
 #pragma unroll
@@ -394,8 +398,8 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
         if (c + 1 < nchunks) load_stage(c + 1, (c + 1) & 1);
         else load_diag_block(sm + EPI_XS, Kb, j0, ld);   // stage 0 is idle during the last chunk
         cp_async_commit();
-        const double* as = As + (c & 1) * STAGE_ROWS * PSP + (wm * 32 + g) * PSP + q;
-        const double* bs = Bs + (c & 1) * STAGE_ROWS * PSP + (wn * WC + g) * PSP + q;
+        const double* as = As + (c & 1) * SSTRIDE + (wm * 32 + g) * PSP + q;
+        const double* bs = Bs + (c & 1) * SSTRIDE + (wn * WC + g) * PSP + q;
 #pragma unroll
         for (int kk = 0; kk < PKC; kk += 4) {
             double a[4], bf[NI];
@@ -416,7 +420,8 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     // ---- epilogue: W = C X' (DMMA), L[i,k] = W D^{-1} -> lower triangle, W' = -W -> mirrored block
     const double* Xs = sm + EPI_XS;
     double* Cs = sm + PN_CS;
-    double* rinv = sm + PN_RINV;
+    double* rinv = sm + PN_CS + LROWS * EP;
+    static_assert((PN_CS + LROWS * EP + NB) <= STAGES * SSTRIDE, "panel epilogue must fit");
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
         const int r = wm * 32 + mi * 8 + g;
@@ -727,6 +732,22 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
     else ldlt_panel_tile<64>(sm, i0, j0, ld, Kb, db);   // odd remainder block: Np - i0 == 64
 }
 
+// Panel tiles only, 64 rows each, three CTAs per SM (<= 85 registers, 74 KB shared memory): the rows below block
+// k + 1 of block column k.  Launched beside the chain kernel of the same column.
+constexpr int P64_SMEM = STAGES * 2 * NB * PSP * (int)sizeof(double);
+__global__ void __launch_bounds__(256, 3) ldlt_panel64_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k,
+                                                               double* __restrict__ K, const double* __restrict__ dvec,
+                                                               GfWork work, int woff) {
+    const int b = gf_instance(work, woff + blockIdx.y);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    const int Np = padded_order(Nvec, Nfixed, b, ld);
+    const int j0 = k * NB;
+    const int i0 = j0 + 2 * NB + blockIdx.x * NB;
+    if (i0 >= Np) return;
+    ldlt_panel_tile<64, 64>(sm, i0, j0, ld, K + (size_t)b * ld * ld, dvec + (size_t)b * ld);
+}
+
 // ------------------------------------------------------------------------------------------------
 // x = K^{-1} r via L z = r, z /= d, L' x = z.  rhs[b] (length >= N) is overwritten.
 __global__ void __launch_bounds__(256) ldlt_solve_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
@@ -818,8 +839,9 @@ __global__ void __launch_bounds__(256) ldlt_solve_kernel(int ld, const int32_t* 
 // interleave, so the tail of one half's launch (few long chain CTAs left) is filled by the other half's CTAs.
 namespace {
 struct LdltLanes {
-    cudaStream_t s[2];
-    cudaEvent_t fork, join[2];
+    cudaStream_t s[2];    // chain (or whole-column) stream of each half batch
+    cudaStream_t sp[2];   // panel stream of each half batch (split mode)
+    cudaEvent_t fork, join[2], evc[2], evp[2];
     bool ok;
 };
 LdltLanes* ldlt_lanes() {
@@ -835,7 +857,10 @@ LdltLanes* ldlt_lanes() {
         L.ok = true;
         for (int i = 0; i < 2; i++) {
             L.ok = L.ok && cudaStreamCreateWithFlags(&L.s[i], cudaStreamNonBlocking) == cudaSuccess;
+            L.ok = L.ok && cudaStreamCreateWithFlags(&L.sp[i], cudaStreamNonBlocking) == cudaSuccess;
             L.ok = L.ok && cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming) == cudaSuccess;
+            L.ok = L.ok && cudaEventCreateWithFlags(&L.evc[i], cudaEventDisableTiming) == cudaSuccess;
+            L.ok = L.ok && cudaEventCreateWithFlags(&L.evp[i], cudaEventDisableTiming) == cudaSuccess;
         }
         L.ok = L.ok && cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) == cudaSuccess;
     }
@@ -873,6 +898,37 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
         cudaEventRecord(L->fork, s);
         for (int i = 0; i < 2; i++) cudaStreamWaitEvent(L->s[i], L->fork, 0);
     }
+    // opt-in experiment (GF_LDLT_P64=1): +2 % on uniform batches, nothing on the ragged bench batch
+    static const bool split_on = [] { const char* e = getenv("GF_LDLT_P64"); return e != nullptr && e[0] == '1'; }();
+    if (L != nullptr && split_on) {
+        // Split mode: per half batch a chain stream (chain CTAs only, 2 per SM) and a panel stream (64-row panel tiles,
+        // 3 per SM).  chain(k) needs panel(k-1); panel(k) needs chain(k-1) (the diagonal block of column k).
+        cudaFuncSetAttribute(ldlt_panel64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM);
+        for (int i = 0; i < 2; i++) {
+            ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i]);
+            cudaEventRecord(L->evc[i], st[i]);
+        }
+        bool have_p[2] = {false, false};
+        for (int k = 0; k + 1 < nblk; k++) {
+            const int below = Np - (k + 2) * NB;
+            const int t64 = below / NB;
+            for (int i = 0; i < 2; i++) {
+                if (have_p[i]) cudaStreamWaitEvent(st[i], L->evp[i], 0);
+                if (t64 > 0) cudaStreamWaitEvent(L->sp[i], L->evc[i], 0);
+                ldlt_column_kernel<<<cnt[i], 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg, npos_expected, w,
+                                                                    off[i], cnt[i], 1);
+                if (t64 > 0)
+                    ldlt_panel64_kernel<<<dim3(t64, cnt[i]), 256, P64_SMEM, L->sp[i]>>>(ld, Nvec, Nmax, k, K, dvec, w, off[i]);
+                cudaEventRecord(L->evc[i], st[i]);
+                if (t64 > 0) {
+                    cudaEventRecord(L->evp[i], L->sp[i]);
+                    have_p[i] = true;
+                }
+            }
+        }
+        for (int i = 0; i < 2; i++)
+            if (have_p[i]) cudaStreamWaitEvent(st[i], L->evp[i], 0);
+    } else {
     // issue order interleaves the lanes launch by launch
     for (int i = 0; i < nlane; i++)
         ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i]);
@@ -882,6 +938,7 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
         for (int i = 0; i < nlane; i++)
             ldlt_column_kernel<<<tiles * cnt[i], 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
                                                                          npos_expected, w, off[i], cnt[i], tiles);
+    }
     }
     if (L != nullptr) {
         for (int i = 0; i < 2; i++) {

@@ -345,3 +345,37 @@ def test_ldlt_empty_system_resets_info(K):
     K.ldlt_solve(Kt, 0, Nv, rhs, allw(K, 2))
     K.ldlt_factor(Kt, 5, Nv, dvec, info, nneg, None, allw(K, 2))  # Nmax > 0 but every instance empty
     assert info.cpu().tolist() == [0, 0] and nneg.cpu().tolist() == [0, 0]
+
+
+def test_ldlt_split_mode_matches_default(K):
+    """The opt-in split launch scheme (chain kernel + 64-row panel kernel on separate streams, GF_LDLT_P64=1) runs in
+    a subprocess (the switch is read once) and must give the same factors as the default scheme."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import os, sys, torch, numpy as np\n"
+        "sys.path.insert(0, os.getcwd())\n"
+        "from pygradflow_b200 import kernels as K, synth\n"
+        "B, N = 1100, 200\n"
+        "Km, r, m = synth.kkt_instance(N)\n"
+        "ld = 256\n"
+        "Kd = np.tile(np.eye(ld), (B, 1, 1)); Kd[:, :N, :N] = np.tril(Km)\n"
+        "Kt = torch.as_tensor(Kd, device='cuda')\n"
+        "i32 = dict(dtype=torch.int32, device='cuda')\n"
+        "Nv = torch.full((B,), N, **i32); info = torch.zeros(B, **i32); nneg = torch.zeros(B, **i32)\n"
+        "dvec = torch.zeros(B, ld, dtype=torch.float64, device='cuda')\n"
+        "K.ldlt_factor(Kt, N, Nv, dvec, info, nneg, None, K.WorkList.all(B))\n"
+        "torch.cuda.synchronize()\n"
+        "assert int(info.abs().sum()) == 0 and int((nneg != m).sum()) == 0\n"
+        "print(repr(float(torch.tril(Kt[:, :N, :N]).double().sum())), repr(float(dvec.sum())))\n"
+    )
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, GF_LDLT_P64=flag)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                             cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append(res.stdout.strip())
+    assert outs[0] == outs[1]
