@@ -151,6 +151,14 @@ int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, c
 int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, double* dvec, int32_t* info,
                    int32_t* nneg, const int32_t* npos_expected, const int32_t* work, const int32_t* nwork_dev,
                    int nwork, void* stream);
+/* gf_kkt_assemble (lower triangle, padded to 64) fused into the factorisation: every tile of K is gathered from H, J
+ * and the index sets at its first touch instead of being written and read back once (symmetric_step_solver.py:27-39,
+ * 49-77 + lu_solver.py:9-17 in one call).  Same result as gf_kkt_assemble(pad 64, lower only) + gf_ldlt_factor with
+ * npos_expected = nI, bit for bit. */
+int gf_kkt_ldlt_factor(int B, int n, int m, int ld, const double* H, const double* J, const int32_t* perm,
+                       const int32_t* nI, const double* dt, const double* rho, const int32_t* Nvec, double* K,
+                       double* dvec, int32_t* info, int32_t* nneg, const int32_t* work, const int32_t* nwork_dev,
+                       int nwork, void* stream);
 int gf_ldlt_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, double* rhs, int ldr,
                   const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 

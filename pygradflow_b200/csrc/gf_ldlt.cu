@@ -29,6 +29,7 @@
 #include "gf_common.cuh"
 #include "../../include/gradflow_b200.h"
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #ifdef GF_LDLT_TRACE
@@ -66,6 +67,63 @@ __device__ __forceinline__ int padded_order(const int32_t* Nvec, int Nfixed, int
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
     const int Np = ((N + NB - 1) / NB) * NB;
     return Np < ld ? Np : ld;
+}
+
+// Optional on-the-fly assembly of the KKT matrix (the fused entry gf_kkt_ldlt_factor): instead of reading the
+// assembled lower triangle from K, the first touch of every tile gathers it from H, J and the index sets, exactly as
+// kkt_assemble_kernel would have written it (symmetric_step_solver.py:27-39,49-77) -- this saves writing and
+// re-reading K once (9.6 GB each at cfg3).  H == nullptr: K already holds the assembled matrix.
+struct KktSrc {
+    const double* H;
+    const double* J;
+    const int32_t* perm;
+    const int32_t* nI;
+    const double* dt;
+    const double* rho;
+    int n, m;
+};
+
+struct KktView {  // per-instance view of KktSrc
+    const double* Hb;
+    const double* Jb;
+    const int32_t* pb;
+    int nI, N, n;
+    double lamb, corner;
+    bool on;
+};
+
+__device__ __forceinline__ KktView kkt_view(const KktSrc& s, int b) {
+    KktView v;
+    v.on = s.H != nullptr;
+    if (!v.on) return v;
+    v.Hb = s.H + (size_t)b * s.n * s.n;
+    v.Jb = s.J != nullptr ? s.J + (size_t)b * s.m * s.n : nullptr;
+    v.pb = s.perm + (size_t)b * s.n;
+    v.nI = s.nI[b];
+    v.N = v.nI + s.m;
+    v.n = s.n;
+    v.lamb = 1.0 / s.dt[b];                                   // symmetric_step_solver.py:30
+    v.corner = -v.lamb / (1.0 + v.lamb * s.rho[b]);           // :60-62
+    return v;
+}
+
+// entry (r, c) of the padded, reduced KKT matrix, lower triangle (c > r: never used, 0)
+__device__ __forceinline__ double kkt_lower(const KktView& v, int r, int c) {
+    if (c > r) return 0.0;
+    if (r < v.nI) {
+        const double h = __ldg(v.Hb + (size_t)__ldg(v.pb + r) * v.n + __ldg(v.pb + c));
+        return r == c ? __dadd_rn(h, v.lamb) : h;             // H + diag(lamb)  :34-36
+    }
+    if (r < v.N) {
+        if (c < v.nI) return __ldg(v.Jb + (size_t)(r - v.nI) * v.n + __ldg(v.pb + c));
+        return r == c ? v.corner : 0.0;
+    }
+    return r == c ? 1.0 : 0.0;                                // identity padding up to the 64-block
+}
+
+__device__ __forceinline__ double2 kkt_load2(const KktView& v, const double* __restrict__ Kb, int ld, int r, int c) {
+    if (!v.on) return *reinterpret_cast<const double2*>(Kb + (size_t)r * ld + c);
+    return make_double2(kkt_lower(v, r, c), kkt_lower(v, r, c + 1));
 }
 
 // Sign flip on the integer pipe (the FP64 pipe is the contended resource here).
@@ -339,7 +397,7 @@ __device__ __forceinline__ double xt_fragment(const double* Xs, int kq, int n) {
 // LROWS: A rows the shared-memory layout is sized for (128 inside the column kernel, 64 in the 64-row-only kernel).
 template <int ROWS, int LROWS = TM>
 __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int ld, double* __restrict__ Kb,
-                                                const double* __restrict__ db) {
+                                                const double* __restrict__ db, const KktView& kv) {
     constexpr int WN = (ROWS == 128) ? 2 : 4;   // warps along the 64 columns
     constexpr int NI = 8 / WN;                  // 8-column DMMA tiles per warp
     constexpr int WC = NI * 8;                  // columns per warp
@@ -383,10 +441,10 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     double acc[4][NI][2];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
-        const double* rowp = Kb + (size_t)(i0 + wm * 32 + mi * 8 + g) * ld + j0 + wn * WC + 2 * q;
+        const int rr = i0 + wm * 32 + mi * 8 + g, cc = j0 + wn * WC + 2 * q;
 #pragma unroll
         for (int ni = 0; ni < NI; ni++) {
-            const double2 v = *reinterpret_cast<const double2*>(rowp + ni * 8);
+            const double2 v = kkt_load2(kv, Kb, ld, rr, cc + ni * 8);
             acc[mi][ni][0] = v.x;
             acc[mi][ni][1] = v.y;
         }
@@ -487,7 +545,7 @@ __device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const
                                                 int Nfixed, int k, double* __restrict__ K,
                                                 double* __restrict__ dvec, int32_t* __restrict__ info,
                                                 int32_t* __restrict__ nneg,
-                                                const int32_t* __restrict__ npos_expected) {
+                                                const int32_t* __restrict__ npos_expected, const KktView& kv) {
     const int Np = padded_order(Nvec, Nfixed, b, ld);
     const int j0 = k * NB, i0 = j0 + NB;
     if (i0 >= Np) return;
@@ -530,11 +588,11 @@ __device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const
         const int colbase = (diag_part ? i0 + (wn - 2) * 32 : j0 + wn * 32) + 2 * q;
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
-            const double* rowp = Kb + (size_t)(i0 + wm * 32 + mi * 8 + g) * ld + colbase;
+            const int rr = i0 + wm * 32 + mi * 8 + g;
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) {
                 double2 v = make_double2(0.0, 0.0);
-                if (!skip) v = *reinterpret_cast<const double2*>(rowp + ni * 8);
+                if (!skip) v = kkt_load2(kv, Kb, ld, rr, colbase + ni * 8);
                 acc[mi][ni][0] = v.x;
                 acc[mi][ni][1] = v.y;
             }
@@ -684,10 +742,11 @@ __global__ void __launch_bounds__(256, 3) ldlt_diag0_kernel(int ld, const int32_
                                                              double* __restrict__ K, double* __restrict__ dvec,
                                                              int32_t* __restrict__ info, int32_t* __restrict__ nneg,
                                                              const int32_t* __restrict__ npos_expected, GfWork work,
-                                                             int woff) {
+                                                             int woff, KktSrc src) {
     const int b = gf_instance(work, woff + blockIdx.x);
     if (b < 0) return;
     extern __shared__ double sm[];
+    const KktView kv = kkt_view(src, b);
     if (padded_order(Nvec, Nfixed, b, ld) <= 0) {  // empty system (everything active, no constraints): trivially ok
         if (threadIdx.x == 0) { info[b] = 0; nneg[b] = 0; }
         return;
@@ -696,7 +755,7 @@ __global__ void __launch_bounds__(256, 3) ldlt_diag0_kernel(int ld, const int32_
     const double* Kb = K + (size_t)b * ld * ld;
     for (int e = threadIdx.x; e < NB * NB / 2; e += blockDim.x) {
         const int r = e >> 5, c = (e & 31) * 2;
-        const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)r * ld + c);
+        const double2 v = kkt_load2(kv, Kb, ld, r, c);
         S[r][c] = v.x;
         S[r][c + 1] = v.y;
     }
@@ -710,7 +769,7 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
                                                              int k, double* __restrict__ K, double* __restrict__ dvec,
                                                              int32_t* __restrict__ info, int32_t* __restrict__ nneg,
                                                              const int32_t* __restrict__ npos_expected, GfWork work,
-                                                             int woff, int cnt, int tiles) {
+                                                             int woff, int cnt, int tiles, KktSrc src) {
     // 1-D grid of cnt * tiles CTAs: the cnt chain CTAs (the long ones) come first, then the panel tiles
     const int lin = blockIdx.x;
     const int wi = lin < cnt ? lin : (lin - cnt) / (tiles - 1);
@@ -718,8 +777,9 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
     const int b = gf_instance(work, woff + wi);
     if (b < 0) return;
     extern __shared__ double sm[];
+    const KktView kv = kkt_view(src, b);
     if (tile == 0) {
-        ldlt_chain_body(sm, b, ld, Nvec, Nfixed, k, K, dvec, info, nneg, npos_expected);
+        ldlt_chain_body(sm, b, ld, Nvec, Nfixed, k, K, dvec, info, nneg, npos_expected, kv);
         return;
     }
     const int Np = padded_order(Nvec, Nfixed, b, ld);
@@ -728,8 +788,8 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
     if (i0 >= Np) return;
     double* Kb = K + (size_t)b * ld * ld;
     const double* db = dvec + (size_t)b * ld;
-    if (Np - i0 >= TM) ldlt_panel_tile<128>(sm, i0, j0, ld, Kb, db);
-    else ldlt_panel_tile<64>(sm, i0, j0, ld, Kb, db);   // odd remainder block: Np - i0 == 64
+    if (Np - i0 >= TM) ldlt_panel_tile<128>(sm, i0, j0, ld, Kb, db, kv);
+    else ldlt_panel_tile<64>(sm, i0, j0, ld, Kb, db, kv);   // odd remainder block: Np - i0 == 64
 }
 
 // Panel tiles only, 64 rows each, three CTAs per SM (<= 85 registers, 74 KB shared memory): the rows below block
@@ -737,7 +797,7 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
 constexpr int P64_SMEM = STAGES * 2 * NB * PSP * (int)sizeof(double);
 __global__ void __launch_bounds__(256, 3) ldlt_panel64_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k,
                                                                double* __restrict__ K, const double* __restrict__ dvec,
-                                                               GfWork work, int woff) {
+                                                               GfWork work, int woff, KktSrc src) {
     const int b = gf_instance(work, woff + blockIdx.y);
     if (b < 0) return;
     extern __shared__ double sm[];
@@ -745,7 +805,7 @@ __global__ void __launch_bounds__(256, 3) ldlt_panel64_kernel(int ld, const int3
     const int j0 = k * NB;
     const int i0 = j0 + 2 * NB + blockIdx.x * NB;
     if (i0 >= Np) return;
-    ldlt_panel_tile<64, 64>(sm, i0, j0, ld, K + (size_t)b * ld * ld, dvec + (size_t)b * ld);
+    ldlt_panel_tile<64, 64>(sm, i0, j0, ld, K + (size_t)b * ld * ld, dvec + (size_t)b * ld, kkt_view(src, b));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -869,9 +929,9 @@ LdltLanes* ldlt_lanes() {
 constexpr int LDLT_SPLIT_MIN = 1024;  // below this many matrices a launch has no tail worth hiding
 }  // namespace
 
-extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, double* dvec, int32_t* info,
-                              int32_t* nneg, const int32_t* npos_expected, const int32_t* work,
-                              const int32_t* nwork_dev, int nwork, void* stream) {
+static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double* K, double* dvec, int32_t* info,
+                            int32_t* nneg, const int32_t* npos_expected, const int32_t* work,
+                            const int32_t* nwork_dev, int nwork, void* stream, KktSrc src) {
     if (B <= 0 || ld <= 0 || (ld % NB) != 0 || Nmax < 0 || Nmax > ld || !K || !dvec || !info || !nneg)
         return GF_ERR_ARG;
     if (nwork <= 0 || Nmax == 0) return GF_OK;
@@ -905,7 +965,7 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
         // 3 per SM).  chain(k) needs panel(k-1); panel(k) needs chain(k-1) (the diagonal block of column k).
         cudaFuncSetAttribute(ldlt_panel64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM);
         for (int i = 0; i < 2; i++) {
-            ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i]);
+            ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i], src);
             cudaEventRecord(L->evc[i], st[i]);
         }
         bool have_p[2] = {false, false};
@@ -916,9 +976,9 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
                 if (have_p[i]) cudaStreamWaitEvent(st[i], L->evp[i], 0);
                 if (t64 > 0) cudaStreamWaitEvent(L->sp[i], L->evc[i], 0);
                 ldlt_column_kernel<<<cnt[i], 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg, npos_expected, w,
-                                                                    off[i], cnt[i], 1);
+                                                                    off[i], cnt[i], 1, src);
                 if (t64 > 0)
-                    ldlt_panel64_kernel<<<dim3(t64, cnt[i]), 256, P64_SMEM, L->sp[i]>>>(ld, Nvec, Nmax, k, K, dvec, w, off[i]);
+                    ldlt_panel64_kernel<<<dim3(t64, cnt[i]), 256, P64_SMEM, L->sp[i]>>>(ld, Nvec, Nmax, k, K, dvec, w, off[i], src);
                 cudaEventRecord(L->evc[i], st[i]);
                 if (t64 > 0) {
                     cudaEventRecord(L->evp[i], L->sp[i]);
@@ -931,13 +991,13 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
     } else {
     // issue order interleaves the lanes launch by launch
     for (int i = 0; i < nlane; i++)
-        ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i]);
+        ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i], src);
     for (int k = 0; k + 1 < nblk; k++) {
         const int below = Np - (k + 2) * NB;              // rows under block k+1
         const int tiles = 1 + (below + TM - 1) / TM;      // chain CTA + 128-row panel tiles
         for (int i = 0; i < nlane; i++)
             ldlt_column_kernel<<<tiles * cnt[i], 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
-                                                                         npos_expected, w, off[i], cnt[i], tiles);
+                                                                         npos_expected, w, off[i], cnt[i], tiles, src);
     }
     }
     if (L != nullptr) {
@@ -947,6 +1007,23 @@ extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, doub
         }
     }
     return gf_launch_status();
+}
+
+extern "C" int gf_ldlt_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, double* dvec, int32_t* info,
+                              int32_t* nneg, const int32_t* npos_expected, const int32_t* work,
+                              const int32_t* nwork_dev, int nwork, void* stream) {
+    KktSrc none;
+    memset(&none, 0, sizeof(none));
+    return ldlt_factor_impl(B, ld, Nmax, Nvec, K, dvec, info, nneg, npos_expected, work, nwork_dev, nwork, stream, none);
+}
+
+extern "C" int gf_kkt_ldlt_factor(int B, int n, int m, int ld, const double* H, const double* J, const int32_t* perm,
+                                  const int32_t* nI, const double* dt, const double* rho, const int32_t* Nvec, double* K,
+                                  double* dvec, int32_t* info, int32_t* nneg, const int32_t* work,
+                                  const int32_t* nwork_dev, int nwork, void* stream) {
+    if (n <= 0 || m < 0 || !H || !perm || !nI || !dt || !rho || !Nvec || (m > 0 && !J)) return GF_ERR_ARG;
+    KktSrc src{H, J, perm, nI, dt, rho, n, m};
+    return ldlt_factor_impl(B, ld, n + m, Nvec, K, dvec, info, nneg, nI, work, nwork_dev, nwork, stream, src);
 }
 
 extern "C" int gf_ldlt_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, double* rhs, int ldr,

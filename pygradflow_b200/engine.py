@@ -56,6 +56,10 @@ class KKTEngine:
         self.piv = torch.zeros((B, self.ld), **i32)
         self.info = torch.zeros((B,), **i32)
         self.active = torch.zeros((B, n), dtype=torch.uint8, device=device)
+        # Optional (LDL'): gather K inside the factorisation kernels instead of writing it first (gf_kkt_ldlt_factor).
+        # Bit-identical, but the dependent index -> H loads in every tile prologue cost the factorisation 2.9 ms while
+        # the saved assembly is 3.3 ms (cfg3): the step gains 1 %, the DMMA kernels lose 10 % -- off by default.
+        self.fuse_assembly = False
         if linear == LinearSolverType.LDLT:
             self.dvec = torch.zeros((B, self.ld), **f64)
             self.nneg = torch.zeros((B,), **i32)
@@ -102,7 +106,7 @@ class KKTEngine:
             K.band_assemble(H, J, self.active, self.order, self.bw, dt, rho, self.Kband, work)
         elif self.linear == LinearSolverType.LU:
             K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, work)
-        else:
+        elif not self.fuse_assembly:
             K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 64, True, work)
 
     def factor(self, H, J, dt, rho, work: WorkList):
@@ -127,7 +131,10 @@ class KKTEngine:
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        K.ldlt_factor(self.K, Nmax, self.Nvec, self.dvec, self.info, self.nneg, self.nI, work)
+        if self.fuse_assembly:
+            K.kkt_ldlt_factor(H, J, self.perm, self.nI, dt, rho, self.Nvec, self.K, self.dvec, self.info, self.nneg, work)
+        else:
+            K.ldlt_factor(self.K, Nmax, self.Nvec, self.dvec, self.info, self.nneg, self.nI, work)
         if ev is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()

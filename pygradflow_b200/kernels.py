@@ -132,6 +132,16 @@ def ldlt_factor(K, Nmax: int, Nvec, dvec, info, nneg, npos_expected, work: WorkL
           *_w(work), launches=nblk * (2 if work.nwork >= 1024 and nblk > 2 else 1))
 
 
+def kkt_ldlt_factor(H, J, perm, nI, dt, rho, Nvec, K, dvec, info, nneg, work: WorkList):
+    """gf_kkt_assemble (lower, padded) fused into gf_ldlt_factor."""
+    B, n, _ = H.shape
+    m = 0 if J is None else J.shape[1]
+    ld = K.shape[1]
+    nblk = (n + m + 63) // 64
+    _call("gf_kkt_ldlt_factor", B, n, m, ld, ptr(H), ptr(J), ptr(perm), ptr(nI), ptr(dt), ptr(rho), ptr(Nvec), ptr(K),
+          ptr(dvec), ptr(info), ptr(nneg), *_w(work), launches=nblk * (2 if work.nwork >= 1024 and nblk > 2 else 1))
+
+
 def ldlt_solve(K, Nmax: int, Nvec, rhs, work: WorkList):
     B, ld, _ = K.shape
     _call("gf_ldlt_solve", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(rhs), rhs.shape[1], *_w(work))

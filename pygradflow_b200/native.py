@@ -44,6 +44,7 @@ SIGNATURES = {
     "gf_merit_grad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_ls_trial": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_armijo_residual": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P] + _WORK,
+    "gf_kkt_ldlt_factor": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_band_assemble": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_band_factor": [_I, _I, _I, _P, _P, _P] + _WORK,
     "gf_band_solve": [_I, _I, _I, _P, _P] + _WORK,

@@ -379,3 +379,40 @@ def test_ldlt_split_mode_matches_default(K):
         assert res.returncode == 0, res.stderr[-2000:]
         outs.append(res.stdout.strip())
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("n,m", [(150, 40), (512, 256), (200, 0)])
+def test_fused_assembly_factor_is_bit_identical(K, n, m):
+    """gf_kkt_ldlt_factor (K gathered inside the factorisation kernels) == gf_kkt_assemble + gf_ldlt_factor, bit for
+    bit, on ragged active sets."""
+    B = 6
+    rng = np.random.default_rng(n + m)
+    d = synth.qp_batch(range(B), n, m)
+    active = rng.uniform(size=(B, n)) < rng.uniform(0.0, 0.5, size=(B, 1))
+    active[0] = False
+    f64 = dict(dtype=torch.float64, device="cuda")
+    i32 = dict(dtype=torch.int32, device="cuda")
+    H, J = dev(d["H"]), (dev(d["A"]) if m else None)
+    act = torch.as_tensor(active.astype(np.uint8), device="cuda")
+    perm, nI, Nvec = torch.zeros((B, n), **i32), torch.zeros(B, **i32), torch.zeros(B, **i32)
+    w = allw(K, B)
+    K.index_sets(act, m, perm, nI, Nvec, w)
+    dt, rho = dev(10.0 ** rng.uniform(-1, 1, B)), dev(10.0 ** rng.uniform(-4, 0, B))
+    ld = ((n + m + 63) // 64) * 64
+    out = []
+    for fused in (False, True):
+        Kt = torch.full((B, ld, ld), float("nan"), **f64)
+        dvec, info, nneg = torch.zeros((B, ld), **f64), torch.zeros(B, **i32), torch.zeros(B, **i32)
+        if fused:
+            K.kkt_ldlt_factor(H, J, perm, nI, dt, rho, Nvec, Kt, dvec, info, nneg, w)
+        else:
+            K.kkt_assemble(H, J, perm, nI, dt, rho, Kt, 64, True, w)
+            K.ldlt_factor(Kt, n + m, Nvec, dvec, info, nneg, nI, w)
+        out.append((torch.tril(Kt).cpu().numpy(), dvec.cpu().numpy(), info.cpu().numpy(), nneg.cpu().numpy()))
+    Nv = Nvec.cpu().numpy()
+    for b in range(B):
+        Np = ((Nv[b] + 63) // 64) * 64
+        assert np.array_equal(out[0][0][b, :Np, :Np], out[1][0][b, :Np, :Np])
+        assert np.array_equal(out[0][1][b, :Np], out[1][1][b, :Np])
+    assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
+    assert (out[0][2] == 0).all()
