@@ -132,6 +132,21 @@ int gf_kkt_rhs(int B, int n, int m, int ld, const double* H, const double* J, co
                const double* F, const double* dt, const double* rho, double* rhs, const int32_t* work,
                const int32_t* nwork_dev, int nwork, void* stream);
 
+/* The unsymmetric full-order formulations of the scaled step (step/solver/__init__.py:12-31): K[b] (ld >= n + m) gets
+ * the matrix of AsymmetricStepSolver.compute_deriv (asymmetric_step_solver.py:77-104, unit rows for the active
+ * variables :37-75) or of ExtendedStepSolver._compute_deriv (extended_step_solver.py:39-83); gf_kkt_rhs_full the
+ * matching right-hand side (asymmetric_step_solver.py:106-123 / extended_step_solver.py:93).  The solution is
+ * (dx, sy) in the natural order for both: gf_step_finish with the identity permutation and nI = n finishes it. */
+#define GF_FORM_SYMMETRIC 0
+#define GF_FORM_ASYMMETRIC 1
+#define GF_FORM_EXTENDED 2
+int gf_kkt_assemble_full(int B, int n, int m, int ld, int form, const double* H, const double* J, const int32_t* perm,
+                         const int32_t* nI, const uint8_t* active, const double* dt, const double* rho, double* K,
+                         const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+int gf_kkt_rhs_full(int B, int n, int m, int ld, int form, const int32_t* perm, const int32_t* nI,
+                    const uint8_t* active, const double* F, const double* dt, const double* rho, double* rhs,
+                    const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
 /* ---- linear solver (linear_solver/lu_solver.py:9-21; LinearSolver contract linear_solver.py:18-31) ---- */
 
 /* LUSolver.__init__: in-place LU with partial pivoting of the order-Nvec[b] (or Nmax when Nvec == NULL)

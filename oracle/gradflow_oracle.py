@@ -104,6 +104,7 @@ class OracleParams:
     linear_solver: str = "splu"  # splu | lapack
     # plugin hook, same contract as pygradflow/step/solver/__init__.py:18-19
     step_solver: Optional[Callable] = None
+    step_solver_type: str = "symmetric"  # symmetric | asymmetric | extended | standard  (params.py:50-70,235)
     dtype = np.float64
 
 
@@ -925,12 +926,141 @@ class SymmetricStepSolver:
         return StepResult(iterate, dx, dy, self.active_set, None)
 
 
+class AsymmetricStepSolver(SymmetricStepSolver):
+    """asymmetric_step_solver.py:15-173: the full (n+m) system [[H + lamb I, J'], [J, -lamb fact I]] in the natural
+    order, the row of every active variable overwritten by the unit row (:37-75), rhs = (b0 | b1 by position, b2t)
+    (:106-123).  Same ScaledStepSolver shell as the symmetric solver (scaled_step_solver.py:85-107)."""
+
+    def full_system(self, b0, b1, b2t):
+        n, m, A = self.n, self.m, self.active_set
+        lamb = 1.0 / self.dt
+        K = np.zeros((n + m, n + m))
+        K[:n, :n] = self.hess + lamb * np.eye(n)
+        K[:n, n:] = self.jac.T
+        K[n:, :n] = self.jac
+        K[n:, n:] = (-lamb / (1.0 + lamb * self.rho)) * np.eye(m)
+        K[:n][A] = 0.0
+        K[np.where(A)[0], np.where(A)[0]] = 1.0
+        rhs = np.empty(n + m)
+        rhs[n:] = b2t
+        rhs[:n][A] = b0
+        rhs[:n][~A] = b1
+        return K, rhs
+
+    def linear_solver(self, K):
+        return OracleLUSolver(K, self.params.linear_solver, symmetric=False)
+
+    def solve(self, iterate):
+        b0, b1, b2 = self.initial_rhs(iterate)
+        rho = self.rho
+        lamb = 1.0 / self.dt
+        fact = 1.0 / (1.0 + lamb * rho)
+        b2t = fact * b2
+        K, rhs = self.full_system(b0, b1, b2t)
+        if self.K is None:
+            self.K = K
+        try:
+            if self.solver is None:
+                self.solver = self.linear_solver(self.K)
+                self.num_factorizations += 1
+            s = self.solver.solve(rhs)
+        except LinearSolverError as err:
+            raise StepSolverError() from err
+        self.last_rhs = rhs
+        self.last_sol = s
+        dx = s[: self.n]
+        dy = fact * (s[self.n :] - rho * b2)
+        return StepResult(iterate, dx, dy, self.active_set, None)
+
+
+class ExtendedStepSolver(AsymmetricStepSolver):
+    """extended_step_solver.py:12-112: rows = (selector rows of the active variables; inactive rows of
+    [H + lamb I, J']; [J, -lamb fact I]), columns in the natural order, rhs = (b0, b1, b2t) (:85-95)."""
+
+    def full_system(self, b0, b1, b2t):
+        n, m, A = self.n, self.m, self.active_set
+        lamb = 1.0 / self.dt
+        act, ina = np.where(A)[0], np.where(~A)[0]
+        nA = act.size
+        K = np.zeros((n + m, n + m))
+        K[np.arange(nA), act] = 1.0
+        K[nA:n, :n] = (self.hess + lamb * np.eye(n))[ina, :]
+        K[nA:n, n:] = self.jac.T[ina, :]
+        K[n:, :n] = self.jac
+        K[n:, n:] = (-lamb / (1.0 + lamb * self.rho)) * np.eye(m)
+        return K, np.concatenate([b0, b1, b2t])
+
+
+class StandardStepSolver:
+    """standard_step_solver.py:15-92: Newton step on the UNSCALED implicit function (implicit_func.py:100-199);
+    matrix F'(x_hat) with H_rho = H + rho J'J (:50-53), rhs = F(iterate) (:63), dx = sol[:n], dy = sol[n:]."""
+
+    def __init__(self, problem, params, orig_iterate, dt, rho):
+        self.problem = problem
+        self.params = params
+        self.orig_iterate = orig_iterate
+        self.dt = dt
+        self.rho = rho
+        self.n = problem.num_vars
+        self.m = problem.num_cons
+        self._func = ImplicitFunc(problem, orig_iterate, dt)
+        self.active_set = None
+        self.jac = None
+        self.hess = None
+        self.solver = None
+        self.K = None
+        self.num_factorizations = 0
+
+    @property
+    def func(self):
+        return self._func
+
+    def update_derivs(self, iterate):
+        self.jac = np.array(iterate.aug_lag_deriv_xy(), copy=True)
+        self.hess = np.array(iterate.aug_lag_deriv_xx(self.rho), copy=True)
+        self.solver = None
+        self.K = None
+
+    def update_active_set(self, active_set):
+        self.active_set = np.array(active_set, copy=True)
+        self.solver = None
+        self.K = None
+
+    def solve(self, iterate):
+        n, m, dt = self.n, self.m, self.dt
+        if self.K is None:
+            keep = np.logical_not(self.active_set).astype(np.float64)[:, None]
+            K = np.zeros((n + m, n + m))
+            K[:n, :n] = np.eye(n) + keep * (dt * self.hess)
+            K[:n, n:] = keep * (dt * self.jac.T)
+            K[n:, :n] = -dt * self.jac
+            K[n:, n:] = np.eye(m)
+            self.K = K
+        rhs = self._func.value_at(iterate, self.rho, self.active_set)
+        try:
+            if self.solver is None:
+                self.solver = OracleLUSolver(self.K, self.params.linear_solver, symmetric=False)
+                self.num_factorizations += 1
+            s = self.solver.solve(rhs)
+        except LinearSolverError as err:
+            raise StepSolverError() from err
+        self.last_rhs = rhs
+        self.last_sol = s
+        return StepResult(iterate, s[:n], s[n:], self.active_set, None)
+
+
 def make_step_solver(problem, params, iterate, dt, rho):
-    """step/solver/__init__.py:12-31 (only the plugin hook and the Symmetric default)."""
+    """step/solver/__init__.py:12-31."""
     assert dt > 0.0 and rho > 0.0
     if params.step_solver is not None:
         return params.step_solver(problem, params, iterate, dt, rho)
-    return SymmetricStepSolver(problem, params, iterate, dt, rho)
+    cls = {
+        "symmetric": SymmetricStepSolver,
+        "asymmetric": AsymmetricStepSolver,
+        "extended": ExtendedStepSolver,
+        "standard": StandardStepSolver,
+    }[params.step_solver_type]
+    return cls(problem, params, iterate, dt, rho)
 
 
 # --------------------------------------------------------------------------

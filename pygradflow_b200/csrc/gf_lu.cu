@@ -337,6 +337,170 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Block column j0 of the multi-launch factorisation with the panel resident in REGISTERS: thread t owns the R rows of
+// the panel that start at logical positions t, t + T, ... (R x NB doubles), no shared-memory copy of the panel, ONE
+// block barrier per pivot column.  Rows never move between threads -- every thread tracks the logical position `pos`
+// of its rows (the LAPACK interchange jj <-> p swaps two positions).  Pivot search: warp arg-max by shuffles (ties to
+// the smaller position, NaN never wins: block_maxloc's rule); the lane that holds a warp's candidate stages that row
+// next to the candidate, so after the barrier every warp reduces the <= 32 candidates again and reads the winner's
+// row directly.  Then, thread per storage row c outside the panel: the NB interchanges as ONE gather (src[] = inverse
+// of `pos`; values that leave the panel range always come from the panel range, so the entering values are held in
+// registers and the leaving ones are moved in batches of independent loads) and U12 = L11^{-1} M12.
+template <int NB, int R, int TMAX>
+__global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                           double* __restrict__ K, int32_t* __restrict__ piv,
+                                                           int32_t* __restrict__ info, GfWork work, int j0, int nwork) {
+    constexpr int NW = TMAX / 32;
+    constexpr int NONE = 1 << 20;
+    __shared__ double wrow[2][NW][NB];
+    __shared__ double wval[2][NW];
+    __shared__ int wpos[2][NW];
+    __shared__ double L11[NB][NB + 1];
+    __shared__ int spiv[NB];
+    __shared__ int src[R * TMAX];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5, T = blockDim.x, nw = T >> 5;
+#pragma unroll 1
+    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int b = gf_instance(work, wi);
+        if (b < 0) return;
+        const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+        if (j0 >= N) continue;
+        const int rows = N - j0, jb = min(NB, rows);
+        double* Kb = K + (size_t)b * ld * ld;
+        double a[R][NB];
+        int pos[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            pos[r] = t + r * T;
+#pragma unroll
+            for (int c = 0; c < NB; c++)
+                a[r][c] = (pos[r] < rows && c < jb) ? Kb[(size_t)(j0 + c) * ld + j0 + pos[r]] : 0.0;
+        }
+        int32_t sinfo = j0 == 0 ? 0 : info[b];
+#pragma unroll
+        for (int jj = 0; jj < NB; jj++) {
+            if (jj < jb) {
+                double v = -1.0;
+                int idx = NONE, rs = 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const double vr = fabs(a[r][jj]);
+                    const bool ok = t + r * T < rows && pos[r] >= jj && vr >= 0.0;  // excluded rows, NaN entries
+                    if (ok && (vr > v || (vr == v && pos[r] < idx))) { v = vr; idx = pos[r]; rs = r; }
+                }
+                double bv = v;
+                int bi = idx;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                const int buf = jj & 1;
+                if (bi == NONE) {
+                    if (lane == 0) { wval[buf][wid] = -1.0; wpos[buf][wid] = NONE; }
+                } else if (idx == bi) {  // positions are unique: exactly one lane
+                    wval[buf][wid] = bv;
+                    wpos[buf][wid] = bi;
+#pragma unroll
+                    for (int c = jj; c < NB; c++) {
+                        double x = a[0][c];
+#pragma unroll
+                        for (int r = 1; r < R; r++)
+                            if (rs == r) x = a[r][c];
+                        wrow[buf][wid][c] = x;
+                    }
+                }
+                __syncthreads();
+                bv = lane < nw ? wval[buf][lane] : -1.0;
+                bi = lane < nw ? wpos[buf][lane] : NONE;
+                int bw = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bw = ow; }
+                }
+                const int p = bi < NONE ? bi : jj;
+                record_pivot(bv, j0 + jj, &sinfo);
+                if (t == 0) spiv[jj] = p;
+                const double* pr = wrow[buf][bw];
+                const double pv = bi < NONE ? pr[jj] : 0.0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (pos[r] == p) pos[r] = jj;
+                    else if (pos[r] == jj) pos[r] = p;
+                    if (t + r * T < rows && pos[r] > jj && pv != 0.0) {
+                        const double l = a[r][jj] / pv;
+                        a[r][jj] = l;
+#pragma unroll
+                        for (int c = jj + 1; c < NB; c++) a[r][c] = fma(-l, pr[c], a[r][c]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (t + r * T < rows) {
+#pragma unroll
+                for (int c = 0; c < NB; c++)
+                    if (c < jb) Kb[(size_t)(j0 + c) * ld + j0 + pos[r]] = a[r][c];
+                src[pos[r]] = t + r * T;
+                if (pos[r] < jb) {
+#pragma unroll
+                    for (int c = 0; c < NB; c++) L11[pos[r]][c] = a[r][c];
+                }
+            }
+        }
+        if (t == 0) info[b] = sinfo;
+        __syncthreads();
+        if (t < jb) piv[(size_t)b * ld + j0 + t] = j0 + spiv[t];
+        // ---- interchanges on the storage rows outside the panel + U12
+#pragma unroll 1
+        for (int c = t; c < N; c += T) {
+            if (c >= j0 && c < j0 + jb) continue;
+            double* rowp = Kb + (size_t)c * ld + j0;
+            double u[NB];
+#pragma unroll
+            for (int k = 0; k < NB; k++) u[k] = (k < jb) ? rowp[src[k]] : 0.0;
+#pragma unroll
+            for (int j4 = 0; j4 < NB; j4 += 4) {
+                double d[4];
+                int dp[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    dp[e] = -1;
+                    if (j4 + e < jb) {
+                        const int p = spiv[j4 + e];
+                        if (p >= jb) {
+                            const int sp = src[p];
+                            if (sp != p) { dp[e] = p; d[e] = rowp[sp]; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (dp[e] >= 0) rowp[dp[e]] = d[e];
+            }
+            if (c >= j0 + jb) {
+#pragma unroll
+                for (int k = 1; k < NB; k++) {
+                    double sacc = u[k];
+#pragma unroll
+                    for (int q = 0; q < k; q++) sacc = fma(-L11[k][q], u[q], sacc);
+                    u[k] = sacc;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NB; k++)
+                if (k < jb) rowp[k] = u[k];
+        }
+        __syncthreads();
+    }
+}
+
 // Row dot with four loads in flight per lane / column axpy term with eight loads in flight per thread (the
 // substitution kernels are HBM-bound: without the explicit batching one load per lane is outstanding).
 __device__ __forceinline__ double lu_row_dot(const double* __restrict__ row, const double* v, int lo, int hi, int lane) {
@@ -598,10 +762,20 @@ int launch_panel(int ld, int Nmax, const int32_t* Nvec, int Nfixed, double* K, i
 }
 
 // One block column of the multi-launch factorisation: pivoted panel (one CTA per matrix), then the DMMA update.
-template <int NB>
+// R > 0: register-resident panel, R rows per thread (rows left <= 512 R); R = 0: the shared-memory panel.
+template <int NB, int R>
 int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info, GfWork w, int nwork,
                   cudaStream_t s, int j0) {
-    int rc = launch_panel<NB>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s, j0, 1);
+    int rc;
+    if constexpr (R > 0) {
+        int threads = ((Nmax - j0 + R - 1) / R + 31) & ~31;
+        threads = threads < 256 ? 256 : (threads > 512 ? 512 : threads);
+        const int grid = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
+        lu_regpanel_kernel<NB, R, 512><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork);
+        rc = gf_launch_status();
+    } else {
+        rc = launch_panel<NB>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s, j0, 1);
+    }
     if (rc != GF_OK) return rc;
     const int tr = Nmax - j0 - NB;
     if (tr > 0) {
@@ -645,9 +819,10 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
     while (j0 < Nmax) {
         const int rows = Nmax - j0;
         int rc;
-        if (rows <= 830) { rc = launch_column<32>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 32; }
-        else if (rows <= 1700) { rc = launch_column<16>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 16; }
-        else { rc = launch_column<8>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 8; }
+        if (rows <= 512) { rc = launch_column<32, 1>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 32; }
+        else if (rows <= 1024) { rc = launch_column<16, 2>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 16; }
+        else if (rows <= 2048) { rc = launch_column<8, 4>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 8; }
+        else { rc = launch_column<8, 0>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 8; }
         if (rc != GF_OK) return rc;
     }
     return GF_OK;

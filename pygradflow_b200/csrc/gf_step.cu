@@ -216,6 +216,90 @@ __global__ void kkt_rhs_kernel(int n, int m, int ld, const double* __restrict__ 
     for (int c = nI + m + threadIdx.x; c < ld; c += blockDim.x) out[c] = 0.0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The unsymmetric full-order formulations of the scaled step (step/solver/__init__.py:12-31), order n + m, columns in
+// the natural order (x, y):
+//   GF_FORM_ASYMMETRIC (asymmetric_step_solver.py:77-104): rows of [[H + lamb I, J'], [J, -lamb fact I]] in the
+//       natural order, the row of every active variable overwritten by the unit row (:37-75);
+//   GF_FORM_EXTENDED (extended_step_solver.py:39-83): (selector rows of the active variables, ascending; the
+//       inactive rows of [H + lamb I, J'], ascending; [J, -lamb fact I]).
+// One warp per row, rows of K written coalesced.
+template <int ROWS>
+__global__ void kkt_full_kernel(int n, int m, int ld, int form, const double* __restrict__ H,
+                                const double* __restrict__ J, const int32_t* __restrict__ perm,
+                                const int32_t* __restrict__ nIv, const uint8_t* __restrict__ active,
+                                const double* __restrict__ dt, const double* __restrict__ rho, double* __restrict__ K,
+                                GfWork work) {
+    const int b = gf_instance(work, blockIdx.y);
+    if (b < 0) return;
+    const int N = n + m;
+    const int r0 = blockIdx.x * ROWS;
+    if (r0 >= N) return;
+    const int nI = nIv[b], nA = n - nI;
+    const double lamb = 1.0 / dt[b];
+    const double corner = -lamb / __dadd_rn(1.0, __dmul_rn(lamb, rho[b]));
+    const double* Hb = H + (size_t)b * n * n;
+    const double* Jb = J + (size_t)b * m * n;
+    const int32_t* pb = perm + (size_t)b * n;
+    const uint8_t* ab = active + (size_t)b * n;
+    double* Kb = K + (size_t)b * ld * ld;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int rr = wid; rr < ROWS; rr += nw) {
+        const int r = r0 + rr;
+        if (r >= N) break;
+        double* out = Kb + (size_t)r * ld;
+        if (r >= n) {
+            const double* src = Jb + (size_t)(r - n) * n;
+            for (int c = lane; c < n; c += 32) out[c] = __ldg(src + c);
+            for (int c = n + lane; c < N; c += 32) out[c] = (c == r) ? corner : 0.0;
+            continue;
+        }
+        int unit = -1, hrow = -1;  // unit row e_unit, or row hrow of [H + lamb I, J']
+        if (form == GF_FORM_EXTENDED) {
+            if (r < nA) unit = pb[nI + r];
+            else hrow = pb[r - nA];
+        } else {
+            if (ab[r]) unit = r;
+            else hrow = r;
+        }
+        if (unit >= 0) {
+            for (int c = lane; c < N; c += 32) out[c] = (c == unit) ? 1.0 : 0.0;
+        } else {
+            const double* src = Hb + (size_t)hrow * n;
+            for (int c = lane; c < n; c += 32) {
+                double v = __ldg(src + c);
+                if (c == hrow) v = __dadd_rn(v, lamb);
+                out[c] = v;
+            }
+            for (int c = lane; c < m; c += 32) out[n + c] = __ldg(Jb + (size_t)c * n + hrow);
+        }
+    }
+}
+
+// rhs of the full-order formulations: b0 = dt F_x[A], b1 = F_x[I], b2t = fact F_y (scaled_step_solver.py:38-60,91-97)
+// placed by position (asymmetric_step_solver.py:106-123) or as (b0, b1, b2t) (extended_step_solver.py:93).
+__global__ void kkt_full_rhs_kernel(int n, int m, int ld, int form, const int32_t* __restrict__ perm,
+                                    const int32_t* __restrict__ nIv, const uint8_t* __restrict__ active,
+                                    const double* __restrict__ F, const double* __restrict__ dt,
+                                    const double* __restrict__ rho, double* __restrict__ rhs, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    const int nI = nIv[b], nA = n - nI;
+    const double dtb = dt[b];
+    const double lamb = 1.0 / dtb;
+    const double fact = 1.0 / __dadd_rn(1.0, __dmul_rn(lamb, rho[b]));
+    const double* Fb = F + (size_t)b * (n + m);
+    const int32_t* pb = perm + (size_t)b * n;
+    const uint8_t* ab = active + (size_t)b * n;
+    double* out = rhs + (size_t)b * ld;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        if (form == GF_FORM_EXTENDED) out[r] = r < nA ? __dmul_rn(dtb, Fb[pb[nI + r]]) : Fb[pb[r - nA]];
+        else out[r] = ab[r] ? __dmul_rn(dtb, Fb[r]) : Fb[r];
+    }
+    for (int j = threadIdx.x; j < m; j += blockDim.x) out[n + j] = __dmul_rn(fact, Fb[n + j]);
+    for (int c = n + m + threadIdx.x; c < ld; c += blockDim.x) out[c] = 0.0;
+}
+
 // dx[I] = s[:nI], dx[A] = b0, dy = fact (sy - rho b2); x+ = clip(x - dx) with dx fix-up; y+ = y - dy;
 // diff = sqrt(|dx|^2 + |dy|^2) with the post-clip dx.
 __global__ void step_finish_kernel(int n, int m, int ld, const double* __restrict__ xbase,
@@ -533,6 +617,32 @@ extern "C" int gf_kkt_rhs(int B, int n, int m, int ld, const double* H, const do
     if (smem > 48 * 1024) cudaFuncSetAttribute(kkt_rhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kkt_rhs_kernel<<<nwork, pick_threads(n), smem, (cudaStream_t)stream>>>(n, m, ld, H, J, perm, nI, F, dt, rho, rhs,
                                                                             GfWork{work, nwork_dev});
+    return gf_launch_status();
+}
+
+extern "C" int gf_kkt_assemble_full(int B, int n, int m, int ld, int form, const double* H, const double* J,
+                                    const int32_t* perm, const int32_t* nI, const uint8_t* active, const double* dt,
+                                    const double* rho, double* K, const int32_t* work, const int32_t* nwork_dev,
+                                    int nwork, void* stream) {
+    if (B <= 0 || n <= 0 || m < 0 || ld < n + m || !H || !perm || !nI || !active || !dt || !rho || !K) return GF_ERR_ARG;
+    if (m > 0 && !J) return GF_ERR_ARG;
+    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED) return GF_ERR_UNSUPPORTED;
+    if (nwork <= 0) return GF_OK;
+    constexpr int ROWS = 16;
+    dim3 grid((n + m + ROWS - 1) / ROWS, nwork);
+    kkt_full_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, ld, form, H, J, perm, nI, active, dt, rho, K,
+                                                                  GfWork{work, nwork_dev});
+    return gf_launch_status();
+}
+
+extern "C" int gf_kkt_rhs_full(int B, int n, int m, int ld, int form, const int32_t* perm, const int32_t* nI,
+                               const uint8_t* active, const double* F, const double* dt, const double* rho,
+                               double* rhs, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream) {
+    if (B <= 0 || n <= 0 || m < 0 || ld < n + m || !perm || !nI || !active || !F || !dt || !rho || !rhs) return GF_ERR_ARG;
+    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED) return GF_ERR_UNSUPPORTED;
+    if (nwork <= 0) return GF_OK;
+    kkt_full_rhs_kernel<<<nwork, pick_threads(n + m), 0, (cudaStream_t)stream>>>(n, m, ld, form, perm, nI, active, F, dt,
+                                                                                 rho, rhs, GfWork{work, nwork_dev});
     return gf_launch_status();
 }
 

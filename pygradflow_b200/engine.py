@@ -18,7 +18,7 @@ import torch
 
 from . import kernels as K
 from .kernels import WorkList
-from .params import LinearSolverType
+from .params import LinearSolverType, StepSolverType
 
 SMALL_N = 112  # order up to which the shared-memory-resident pivoted LU is used under Auto
 
@@ -31,11 +31,20 @@ BAND_MIN_N = 256  # order from which Auto prefers the family's banded ordering o
 
 
 class KKTEngine:
-    def __init__(self, B: int, n: int, m: int, device, linear: LinearSolverType = LinearSolverType.Auto, band=None):
-        """band: optional (order, half_bandwidth) of the family's KKT ordering (BatchedProblem.kkt_band)."""
+    def __init__(self, B: int, n: int, m: int, device, linear: LinearSolverType = LinearSolverType.Auto, band=None,
+                 formulation: StepSolverType = StepSolverType.Symmetric):
+        """band: optional (order, half_bandwidth) of the family's KKT ordering (BatchedProblem.kkt_band).
+        formulation: Symmetric = the reduced KKT system; Asymmetric / Extended = the full-order unsymmetric systems
+        of asymmetric_step_solver.py / extended_step_solver.py (always pivoted LU, order n + m for every instance)."""
         self.B, self.n, self.m = B, n, m
         self.device = device
         N = n + m
+        self.form = {StepSolverType.Symmetric: K.FORM_SYMMETRIC, StepSolverType.Asymmetric: K.FORM_ASYMMETRIC,
+                     StepSolverType.Extended: K.FORM_EXTENDED}[formulation]
+        if self.form != K.FORM_SYMMETRIC:
+            if linear not in (LinearSolverType.Auto, LinearSolverType.LU):
+                raise ValueError(f"step_solver_type={formulation.name} has an unsymmetric matrix: LU only")
+            linear = LinearSolverType.LU
         if linear == LinearSolverType.Auto:
             if band is not None and N >= BAND_MIN_N:
                 linear = LinearSolverType.Banded
@@ -56,6 +65,10 @@ class KKTEngine:
         self.piv = torch.zeros((B, self.ld), **i32)
         self.info = torch.zeros((B,), **i32)
         self.active = torch.zeros((B, n), dtype=torch.uint8, device=device)
+        if self.form != K.FORM_SYMMETRIC:
+            self.perm_id = torch.arange(n, **i32).repeat(B, 1).contiguous()
+            self.n_full = torch.full((B,), n, **i32)
+            self.N_full = torch.full((B,), N, **i32)
         # Optional (LDL'): gather K inside the factorisation kernels instead of writing it first (gf_kkt_ldlt_factor).
         # Bit-identical, but the dependent index -> H loads in every tile prologue cost the factorisation 2.9 ms while
         # the saved assembly is 3.3 ms (cfg3): the step gains 1 %, the DMMA kernels lose 10 % -- off by default.
@@ -102,7 +115,9 @@ class KKTEngine:
 
     def assemble(self, H, J, dt, rho, work: WorkList):
         """The reduced symmetric KKT matrix of symmetric_step_solver.py:49-77 in the layout of the factorisation."""
-        if self.linear == LinearSolverType.Banded:
+        if self.form != K.FORM_SYMMETRIC:
+            K.kkt_assemble_full(H, J, self.perm, self.nI, self.active, dt, rho, self.K, self.form, work)
+        elif self.linear == LinearSolverType.Banded:
             K.band_assemble(H, J, self.active, self.order, self.bw, dt, rho, self.Kband, work)
         elif self.linear == LinearSolverType.LU:
             K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, work)
@@ -125,7 +140,7 @@ class KKTEngine:
                         out=self.info)
             return
         if self.linear == LinearSolverType.LU:
-            K.lu_factor(self.K, Nmax, self.Nvec, self.piv, self.info, work)
+            K.lu_factor(self.K, Nmax, self._order(), self.piv, self.info, work)
             return
         ev = getattr(self, "ldlt_events", None)  # optional CUDA-event pairs around the factorisation launches alone
         if ev is not None:
@@ -158,7 +173,7 @@ class KKTEngine:
             K.band_permute(self.perm, self.nI, self.pos, rhs, self.bandv, False, self.m, work)
             return
         if self.linear == LinearSolverType.LU:
-            K.lu_solve(self.K, Nmax, self.Nvec, self.piv, rhs, trans, work)
+            K.lu_solve(self.K, Nmax, self._order(), self.piv, rhs, trans, work)
             return
         parent = None if work.list is None and work.count_dev is None else work
         K.build_worklist(self.fbkey, 0, 0, self._ok, parent=parent, invert=False)
@@ -168,8 +183,19 @@ class KKTEngine:
         K.ldlt_solve(self.K, Nmax, self.Nvec, rhs, self._ok)  # symmetric: trans is irrelevant
         K.lu_solve(self.K, Nmax, self.Nvec, self.piv, rhs, trans, self._fb)
 
+    def _order(self):
+        """Per-instance order of the system handed to the LU: |I| + m (reduced) or n + m (full-order formulations)."""
+        return self.Nvec if self.form == K.FORM_SYMMETRIC else self.N_full
+
     def step(self, H, J, xbase, ybase, F, dt, rho, lb, ub, xn, yn, diff, work: WorkList, dx=None, dy=None):
         """ScaledStepSolver.solve + StepResult for the current factor: rhs, substitution, step finish."""
+        if self.form != K.FORM_SYMMETRIC:
+            # asymmetric_step_solver.py:140-173 / extended_step_solver.py:85-112: the solution is (dx, sy) itself
+            K.kkt_rhs_full(self.n, self.m, self.perm, self.nI, self.active, F, dt, rho, self.rhs, self.form, work)
+            self.solve(self.rhs, work)
+            K.step_finish(xbase, ybase, self.rhs, self.perm_id, self.n_full, F, dt, rho, lb, ub, xn, yn, dx, dy, diff,
+                          work)
+            return
         K.kkt_rhs(H, J, self.perm, self.nI, F, dt, rho, self.rhs, work)
         self.solve(self.rhs, work)
         K.step_finish(xbase, ybase, self.rhs, self.perm, self.nI, F, dt, rho, lb, ub, xn, yn, dx, dy, diff, work)

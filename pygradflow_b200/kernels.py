@@ -114,6 +114,21 @@ def kkt_rhs(H, J, perm, nI, F, dt, rho, rhs, work: WorkList):
           *_w(work))
 
 
+FORM_SYMMETRIC, FORM_ASYMMETRIC, FORM_EXTENDED = 0, 1, 2  # GF_FORM_* of include/gradflow_b200.h
+
+
+def kkt_assemble_full(H, J, perm, nI, active, dt, rho, K, form: int, work: WorkList):
+    B, n, _ = H.shape
+    m = 0 if J is None else J.shape[1]
+    _call("gf_kkt_assemble_full", B, n, m, K.shape[1], form, ptr(H), ptr(J), ptr(perm), ptr(nI), ptr(active), ptr(dt),
+          ptr(rho), ptr(K), *_w(work))
+
+
+def kkt_rhs_full(n: int, m: int, perm, nI, active, F, dt, rho, rhs, form: int, work: WorkList):
+    _call("gf_kkt_rhs_full", rhs.shape[0], n, m, rhs.shape[1], form, ptr(perm), ptr(nI), ptr(active), ptr(F), ptr(dt),
+          ptr(rho), ptr(rhs), *_w(work))
+
+
 def lu_factor(K, Nmax: int, Nvec, piv, info, work: WorkList):
     B, ld, _ = K.shape
     _call("gf_lu_factor", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(piv), ptr(info), *_w(work))

@@ -32,6 +32,8 @@ SIGNATURES = {
     "gf_index_sets": [_I, _I, _I, _P, _P, _P, _P] + _WORK,
     "gf_kkt_assemble": [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_kkt_rhs": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_kkt_assemble_full": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_kkt_rhs_full": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_lu_factor": [_I, _I, _I, _P, _P, _P, _P] + _WORK,
     "gf_lu_solve": [_I, _I, _I, _P, _P, _P, _P, _I, _I] + _WORK,
     "gf_ldlt_factor": [_I, _I, _I, _P, _P, _P, _P, _P, _P] + _WORK,

@@ -34,6 +34,17 @@ class LinearSolverType(enum.Enum):
     Banded = enum.auto()
 
 
+class StepSolverType(enum.Enum):
+    """pygradflow/params.py:50-70: formulation of the Newton step system (step/solver/__init__.py:12-31).  Symmetric
+    is the reduced quasi-definite KKT system (LDL' or LU); Asymmetric and Extended are the full-order unsymmetric
+    systems of asymmetric_step_solver.py / extended_step_solver.py (pivoted LU).  Standard (the unscaled implicit
+    function) is restated in the oracle only."""
+
+    Extended = enum.auto()
+    Symmetric = enum.auto()
+    Asymmetric = enum.auto()
+
+
 class ActiveSetType(enum.Enum):
     """pygradflow/params.py:14-18: how the point that decides the active set is chosen (newton_control.py:60-88)."""
 
@@ -85,6 +96,7 @@ class Params:
     active_set_type: ActiveSetType = ActiveSetType.Standard
     active_set_tau: Optional[float] = None
     step_solver: Optional[Callable[..., Any]] = None
+    step_solver_type: StepSolverType = StepSolverType.Symmetric
     linear_solver_type: LinearSolverType = LinearSolverType.Auto
     penalty_update: PenaltyUpdate = PenaltyUpdate.DualNorm
     iteration_limit: Optional[int] = None
@@ -95,7 +107,7 @@ class Params:
     def __post_init__(self):
         for key, cls in (("newton_type", NewtonType), ("linear_solver_type", LinearSolverType),
                          ("penalty_update", PenaltyUpdate), ("step_control_type", StepControlType),
-                         ("active_set_type", ActiveSetType)):
+                         ("active_set_type", ActiveSetType), ("step_solver_type", StepSolverType)):
             v = getattr(self, key)
             if not isinstance(v, cls):
                 setattr(self, key, cls[_enum_name(v)])  # accepts strings and the reference's own enums
@@ -119,6 +131,8 @@ class Params:
                 v = getattr(ref, f)
                 if f == "penalty_update" and _enum_name(v) not in PenaltyUpdate.__members__:
                     raise ValueError(f"penalty_update={_enum_name(v)} is outside the B200 path (Constant / DualNorm)")
+                if f == "step_solver_type" and _enum_name(v) not in StepSolverType.__members__:
+                    raise ValueError(f"step_solver_type={_enum_name(v)} is outside the B200 path")
                 if f == "step_control_type" and _enum_name(v) not in StepControlType.__members__:
                     raise ValueError(f"step_control_type={_enum_name(v)} is outside the B200 path (Newton-based only)")
                 kw[f] = v

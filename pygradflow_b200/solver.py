@@ -58,7 +58,8 @@ class BatchedSolver:
         self.graph_steps = max(1, int(graph_steps))  # captured units replayed between two reads of the running count
         p = problem
         B, n, m, dev = p.B, p.n, p.m, p.device
-        self.engine = KKTEngine(B, n, m, dev, self.params.linear_solver_type, band=problem.kkt_band())
+        self.engine = KKTEngine(B, n, m, dev, self.params.linear_solver_type, band=problem.kkt_band(),
+                                formulation=self.params.step_solver_type)
         f64 = dict(dtype=torch.float64, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
 

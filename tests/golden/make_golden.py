@@ -406,6 +406,24 @@ def golden_active_set_types():
     np.savez_compressed(os.path.join(HERE, "active_set_types.npz"), **out)
 
 
+def golden_step_solvers():
+    """The other step-solver formulations (step/solver/__init__.py:12-31): Asymmetric, Extended, Standard."""
+    from pygradflow.params import StepSolverType
+
+    out = {}
+    for kind in ("Asymmetric", "Extended", "Standard"):
+        kw = dict(step_solver_type=StepSolverType[kind])
+        for newton in ("Simplified", "Full"):
+            for (n, m, k) in [(16, 8, 0), (32, 16, 2), (24, 0, 5)]:
+                d = synth.qp_instance(k, n, m)
+                res = trace_solve(RefQP(d), params_for(newton, **kw), d["x0"], d["y0"])
+                out.update(flat(f"{kind}/{newton}/qp_n{n}_m{m}_k{k}", res))
+        d = synth.rosenbrock_instance(0, 8)
+        res = trace_solve(RefChainedRosenbrock(d), params_for("Simplified", **kw), d["x0"], d["y0"], keep_every=5)
+        out.update(flat(f"{kind}/Simplified/ros_n8_k0", res))
+    np.savez_compressed(os.path.join(HERE, "step_solvers.npz"), **out)
+
+
 def golden_ocp():
     """cfg4-style discretised optimal-control problems (small): full traces of the real reference."""
     out = {}
@@ -427,6 +445,7 @@ if __name__ == "__main__":
     golden_constrained()
     golden_controllers()
     golden_active_set_types()
+    golden_step_solvers()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -220,7 +220,8 @@ def test_lu_golden_kkt(K, golden, N):
 
 
 @pytest.mark.parametrize("sizes", [[1, 2, 3, 5, 17, 31, 32], [32] * 19 + [7, 1], [1, 2, 3, 5, 17, 31, 32, 33],
-                                   [64, 63, 65, 100, 112], [113, 150, 257], [768, 700, 333]])
+                                   [64, 63, 65, 100, 112], [113, 150, 257], [768, 700, 333], [1000, 530, 513, 40],
+                                   [1100, 1030], [2100, 90]])
 def test_lu_ragged_batch_vs_lapack(K, sizes):
     """Ragged orders in one batch (warp-per-matrix register kernel, shared-memory kernel, blocked panel kernel +
     DMMA trailing update); unsymmetric matrices,
@@ -247,6 +248,23 @@ def test_lu_singular_and_nonfinite_info(K):
     nanm[1, 1] = np.nan
     _, info, _, _ = _lu_solve_gpu(K, [sing, zero, nanm, np.eye(2)], [np.ones(3), np.ones(4), np.ones(3), np.ones(2)])
     assert info[0] > 0 and info[1] == 1 and info[2] != 0 and info[3] == 0
+
+
+@pytest.mark.parametrize("N", [150, 300, 600, 1100])
+def test_lu_blocked_singular_and_nonfinite_info(K, N):
+    """info of the multi-launch path (register-resident panels): a zero column reports its 1-based index like
+    getrf, a NaN reports -1, a regular matrix in the same batch is untouched by its neighbours."""
+    rng = np.random.default_rng(N)
+    good = rng.standard_normal((N, N))
+    sing = good.copy()
+    col = N // 2 + 3
+    sing[col, :] = 0.0  # the kernels factor the transposed view: storage row = column of M
+    nanm = good.copy()
+    nanm[N // 3, N // 3] = np.nan
+    rhs = rng.standard_normal(N)
+    sol, info, _, _ = _lu_solve_gpu(K, [good, sing, nanm], [rhs, rhs, rhs])
+    assert info[0] == 0 and info[1] == col + 1 and info[2] == -1
+    assert rel_err(sol[0], np.linalg.solve(good, rhs)) <= 1e-14 * np.linalg.cond(good) * 10
 
 
 def test_lu_empty_system(K):

@@ -221,6 +221,31 @@ def test_other_step_controllers(golden, ctl, prob):
     assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8
 
 
+@pytest.mark.parametrize("kind", ["Asymmetric", "Extended", "Standard"])
+@pytest.mark.parametrize("prob", ["Simplified/qp_n16_m8_k0", "Full/qp_n32_m16_k2", "Simplified/qp_n24_m0_k5",
+                                  "Full/qp_n24_m0_k5", "Simplified/ros_n8_k0"])
+def test_step_solver_formulations(golden, kind, prob):
+    """asymmetric_step_solver.py, extended_step_solver.py, standard_step_solver.py against the reference's traces."""
+    g = golden("step_solvers")
+    key = f"{kind}/{prob}"
+    newton, name = prob.split("/")
+    if name.startswith("qp"):
+        n, m, k = (int(t[1:]) for t in name.split("_")[1:])
+        d = synth.qp_instance(k, n, m)
+        p = orc.DenseQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+    else:
+        d = synth.rosenbrock_instance(0, 8)
+        p = orc.ChainedRosenbrock(d["a"], d["b"], d["lb"], d["ub"])
+    params = orc.OracleParams(step_solver_type=kind.lower(), newton_type=NEWTON[newton])
+    res = orc.Solver(p, params).solve(d["x0"], d["y0"], record=True)
+    assert res.status == int(g[f"{key}/status"])
+    assert res.iterations == int(g[f"{key}/iterations"]) and res.accepted_steps == int(g[f"{key}/accepted_steps"])
+    assert [t["accept"] for t in res.trace] == list(g[f"{key}/accepts"])
+    for row, i in enumerate(g[f"{key}/trace_idx"]):
+        assert rel_err(res.trace[i]["x"], g[f"{key}/trace_x"][row]) <= 1e-8, (key, i)
+    assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8
+
+
 @pytest.mark.parametrize("newton", ["Simplified", "Full"])
 @pytest.mark.parametrize("kind", ["Smallest", "Explicit"])
 def test_tau_active_set_types(golden, kind, newton):

@@ -13,6 +13,7 @@ ap.add_argument("--N", type=int, default=768)
 ap.add_argument("--method", default="ldlt")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--general", action="store_true", help="dense random unsymmetric matrices (an interchange in almost every column)")
 args = ap.parse_args()
 B, N = args.B, args.N
 dev = "cuda"
@@ -33,6 +34,8 @@ for lo in range(0, B, 128):
     K0[lo:hi, nI:N, nI:N] = -0.99 * torch.eye(m, **f64)
     if ld > N:
         K0[lo:hi, N:, N:] = torch.eye(ld - N, **f64)
+if args.general:
+    K0[:, :N, :N] = torch.randn((B, N, N), generator=gen, **f64)
 rhs0 = torch.randn((B, ld), generator=gen, **f64); rhs0[:, N:] = 0
 Kw = torch.empty_like(K0); rhs = torch.empty_like(rhs0)
 Nvec = torch.full((B,), N, dtype=torch.int32, device=dev)
