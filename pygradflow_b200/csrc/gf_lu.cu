@@ -8,6 +8,10 @@
 //   K x = r   <=>  U' w = r, L' v = w, x = P' v        (trans = 0; both sweeps are row-contiguous dots)
 //   K' x = r  <=>  L z = P r, U x = z                  (trans = 1; row-contiguous axpys)
 // For the symmetric KKT matrix of the Symmetric step solver M = K.
+// Factor layout: the pivot sequence `piv` is LAPACK getrf's, but the interchanges of a 32-column block are NOT
+// applied to the blocks of L left of it (as LINPACK's dgefa does column by column, here block by block): every
+// interchange of a strided storage column costs a 32-byte sector per element, and the left part is half of them.
+// gf_lu_solve applies the interchanges block by block accordingly; the factors are only meaningful to it.
 //
 //   lu_warp_kernel   N <= 32: one warp per matrix, matrix resident in registers, pivoting by warp shuffles.
 //   lu_smem_kernel   N <= ~110: whole matrix resident in shared memory, one CTA per matrix (cfg2, n=64).
@@ -15,6 +19,7 @@
 //                    register-tiled trailing update streamed through L2/HBM.  Robust general path; the
 //                    throughput path for quasi-definite K is the LDL' in gf_ldlt.cu.
 //   lu_solve_kernel  blocked substitution, factors streamed once (HBM-bound).
+#include <cstdlib>
 #include "gf_common.cuh"
 #include "../../include/gradflow_b200.h"
 
@@ -87,7 +92,7 @@ __global__ void lu_smem_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfi
             record_pivot(best.v, j, &sinfo);
         }
         if (p != j) {
-            for (int c = threadIdx.x; c < N; c += blockDim.x) {
+            for (int c = (j & ~31) + threadIdx.x; c < N; c += blockDim.x) {  // not the earlier 32-column blocks
                 const double t = S[c * pitch + j];
                 S[c * pitch + j] = S[c * pitch + p];
                 S[c * pitch + p] = t;
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
         for (int c = 0; c < jb; c++)
             for (int i = threadIdx.x; i < rows; i += T) Kb[(size_t)(j0 + c) * ld + j0 + i] = P[c * pitch + i];
         // ---- row interchanges of M on the storage rows outside the panel, then U12 = L11^{-1} M12
-        for (int c = threadIdx.x; c < N; c += T) {
+        for (int c = (j0 & ~31) + threadIdx.x; c < N; c += T) {  // not the earlier 32-column blocks
             if (c >= j0 && c < j0 + jb) continue;
             double* row = Kb + (size_t)c * ld;
             for (int jj = 0; jj < jb; jj++) {
@@ -350,7 +355,8 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
 template <int NB, int R, int TMAX>
 __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                            double* __restrict__ K, int32_t* __restrict__ piv,
-                                                           int32_t* __restrict__ info, GfWork work, int j0, int nwork) {
+                                                           int32_t* __restrict__ info, GfWork work, int j0, int nwork,
+                                                           int dbg) {
     constexpr int NW = TMAX / 32;
     constexpr int NONE = 1 << 20;
     __shared__ double wrow[2][NW][NB];
@@ -378,9 +384,10 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
                 a[r][c] = (pos[r] < rows && c < jb) ? Kb[(size_t)(j0 + c) * ld + j0 + pos[r]] : 0.0;
         }
         int32_t sinfo = j0 == 0 ? 0 : info[b];
+        if ((dbg & 1) && t < NB) spiv[t] = t;
 #pragma unroll
         for (int jj = 0; jj < NB; jj++) {
-            if (jj < jb) {
+            if (jj < jb && !(dbg & 1)) {
                 double v = -1.0;
                 int idx = NONE, rs = 0;
 #pragma unroll
@@ -459,32 +466,26 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
         if (t < jb) piv[(size_t)b * ld + j0 + t] = j0 + spiv[t];
         // ---- interchanges on the storage rows outside the panel + U12
 #pragma unroll 1
-        for (int c = t; c < N; c += T) {
-            if (c >= j0 && c < j0 + jb) continue;
+        for (int c = (j0 & ~31) + t; c < N; c += T) {  // not the earlier 32-column blocks
+            if ((c >= j0 && c < j0 + jb) || (dbg & 2)) continue;
             double* rowp = Kb + (size_t)c * ld + j0;
+            // all loads of the row are issued before the first dependent use: the entering values (gather by src[])
+            // and the old values of the panel range (contiguous), which is where every leaving value comes from
+            double uo[NB];  // indexed by src[p] below: lives in local memory (L1), not in registers
+#pragma unroll
+            for (int k = 0; k < NB; k++) uo[k] = rowp[k];
             double u[NB];
 #pragma unroll
             for (int k = 0; k < NB; k++) u[k] = (k < jb) ? rowp[src[k]] : 0.0;
-#pragma unroll
-            for (int j4 = 0; j4 < NB; j4 += 4) {
-                double d[4];
-                int dp[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    dp[e] = -1;
-                    if (j4 + e < jb) {
-                        const int p = spiv[j4 + e];
-                        if (p >= jb) {
-                            const int sp = src[p];
-                            if (sp != p) { dp[e] = p; d[e] = rowp[sp]; }
-                        }
-                    }
+#pragma unroll 4
+            for (int jj = 0; jj < jb; jj++) {
+                const int p = spiv[jj];
+                if (p >= jb) {
+                    const int sp = src[p];
+                    if (sp != p) rowp[p] = uo[sp];
                 }
-#pragma unroll
-                for (int e = 0; e < 4; e++)
-                    if (dp[e] >= 0) rowp[dp[e]] = d[e];
             }
-            if (c >= j0 + jb) {
+            if (c >= j0 + jb && !(dbg & 4)) {
 #pragma unroll
                 for (int k = 1; k < NB; k++) {
                     double sacc = u[k];
@@ -528,8 +529,25 @@ __device__ __forceinline__ double lu_col_dot(const double* __restrict__ col, int
     return acc;
 }
 
+// The interchanges of one 32-column block applied to the vector (warp 0; v in shared memory): forward order for
+// L z = P r, reverse order for x = P' v.
+__device__ __forceinline__ void lu_block_swaps(double* v, const int32_t* pb, int j0, int jb, int lane, bool reverse) {
+    const int pj = lane < jb ? pb[j0 + lane] : 0;
+    for (int s = 0; s < jb; s++) {
+        const int jj = reverse ? jb - 1 - s : s;
+        const int p = __shfl_sync(0xffffffffu, pj, jj);
+        if (lane == 0 && p != j0 + jj) {
+            const double t = v[j0 + jj];
+            v[j0 + jj] = v[p];
+            v[p] = t;
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Blocked substitution on the packed LU factors; rhs[b] (length >= N) is overwritten by the solution.
+// The interchanges are applied block by block (32 columns), matching the factor layout (see the file header).
 __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                        const double* __restrict__ K, const int32_t* __restrict__ piv,
                                                        double* __restrict__ rhs, int ldr, int trans, GfWork work) {
@@ -537,14 +555,17 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
     if (b < 0) return;
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
     if (N <= 0) return;
-    extern __shared__ double v[];        // N (+pad) doubles
+    extern __shared__ double v[];        // Nfixed + 1 doubles, then Nfixed pivots
     __shared__ double Tb[32][33];
     __shared__ double part[32];
     const double* Kb = K + (size_t)b * ld * ld;
-    const int32_t* pb = piv + (size_t)b * ld;
+    int32_t* pb = reinterpret_cast<int32_t*>(v + Nfixed + 1);
     double* rb = rhs + (size_t)b * ldr;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) v[i] = rb[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        v[i] = rb[i];
+        pb[i] = piv[(size_t)b * ld + i];
+    }
     __syncthreads();
     if (!trans) {
         // forward: U' w = r  (storage row j, entries i <= j)
@@ -597,25 +618,12 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
                     if (lane < ii) s -= Tb[lane][ii] * w;
                 }
                 if (lane < jb) v[j0 + lane] = s;
+                __syncwarp();
+                lu_block_swaps(v, pb, j0, jb, lane, true);  // P_kb' : this block's interchanges, in reverse
             }
             __syncthreads();
         }
-        // x = P' v : undo the interchanges in reverse order
-        if (threadIdx.x == 0) {
-            for (int j = N - 1; j >= 0; j--) {
-                const int p = pb[j];
-                if (p != j) { const double t = v[j]; v[j] = v[p]; v[p] = t; }
-            }
-        }
-        __syncthreads();
     } else {
-        if (threadIdx.x == 0) {
-            for (int j = 0; j < N; j++) {
-                const int p = pb[j];
-                if (p != j) { const double t = v[j]; v[j] = v[p]; v[p] = t; }
-            }
-        }
-        __syncthreads();
         // forward: L z = P r  (axpy form; L(i,j) = K[j*ld + i], i > j)
         for (int j0 = 0; j0 < N; j0 += 32) {
             const int jb = min(32, N - j0);
@@ -625,6 +633,7 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             }
             __syncthreads();
             if (wid == 0) {
+                lu_block_swaps(v, pb, j0, jb, lane, false);  // P_kb : this block's interchanges
                 double s = (lane < jb) ? v[j0 + lane] : 0.0;
                 for (int jj = 0; jj < jb; jj++) {
                     const double z = __shfl_sync(0xffffffffu, s, jj);
@@ -679,32 +688,29 @@ __device__ __forceinline__ double lu_dneg(double x) {
     return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ULL);
 }
 
-template <int NB>
-__global__ void __launch_bounds__(256, 2) lu_update_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int j0,
-                                                            double* __restrict__ K, GfWork work, int nwork) {
+template <int NB, int TN>
+__global__ void __launch_bounds__(TN * 2, TN == 64 ? 4 : 2) lu_update_kernel(int ld, const int32_t* __restrict__ Nvec,
+                                                                              int Nfixed, int j0,
+                                                                              double* __restrict__ K, GfWork work,
+                                                                              int nwork) {
+    // TN = 64: four resident CTAs of four warps per SM instead of two of eight -- the kernel is a single-stage
+    // load / DMMA / store sequence per tile, so independent CTAs are what overlaps one tile's loads with another's math
+    constexpr int T = TN * 2;
     for (int wi = blockIdx.z; wi < nwork; wi += gridDim.z) {
     const int b = gf_instance(work, wi);
     if (b < 0) return;
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
     const int t0 = j0 + NB;
-    const int c0 = t0 + blockIdx.y * 64, i0 = t0 + blockIdx.x * 128;
+    const int c0 = t0 + blockIdx.y * 64, i0 = t0 + blockIdx.x * TN;
     if (c0 >= N || i0 >= N) continue;
-    constexpr int AP = NB + 4;   // pitch of the A tile (== 4 or 12 mod 16: conflict-free fragment loads)
-    constexpr int BP = 128 + 4;  // pitch of the B tile
+    constexpr int AP = NB + 4;  // pitch of the A tile (== 4 or 12 mod 16: conflict-free fragment loads)
+    constexpr int BP = TN + 4;  // pitch of the B tile
     extern __shared__ double usm[];
     double* As = usm;             // 64 x AP
     double* Bs = usm + 64 * AP;   // NB x BP
     double* Kb = K + (size_t)b * ld * ld;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm = wid >> 2, wn = wid & 3, g = lane >> 2, q = lane & 3;
-    for (int e = tid; e < 64 * NB; e += 256) {
-        const int c = e / NB, k = e - c * NB;
-        As[c * AP + k] = (c0 + c < N) ? Kb[(size_t)(c0 + c) * ld + j0 + k] : 0.0;
-    }
-    for (int e = tid; e < NB * 128; e += 256) {
-        const int k = e >> 7, i = e & 127;
-        Bs[k * BP + i] = (i0 + i < N) ? Kb[(size_t)(j0 + k) * ld + i0 + i] : 0.0;
-    }
+    const int wm = wid / (TN / 32), wn = wid % (TN / 32), g = lane >> 2, q = lane & 3;
     double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
@@ -716,6 +722,14 @@ __global__ void __launch_bounds__(256, 2) lu_update_kernel(int ld, const int32_t
             acc[mi][ni][0] = (c < N && i < N) ? cp[0] : 0.0;
             acc[mi][ni][1] = (c < N && i + 1 < N) ? cp[1] : 0.0;
         }
+    }
+    for (int e = tid; e < 64 * NB; e += T) {
+        const int c = e / NB, k = e - c * NB;
+        As[c * AP + k] = (c0 + c < N) ? Kb[(size_t)(c0 + c) * ld + j0 + k] : 0.0;
+    }
+    for (int e = tid; e < NB * TN; e += T) {
+        const int k = e / TN, i = e % TN;
+        Bs[k * BP + i] = (i0 + i < N) ? Kb[(size_t)(j0 + k) * ld + i0 + i] : 0.0;
     }
     __syncthreads();
     const double* as = As + (wm * 32 + g) * AP + q;
@@ -771,7 +785,12 @@ int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv
         int threads = ((Nmax - j0 + R - 1) / R + 31) & ~31;
         threads = threads < 256 ? 256 : (threads > 512 ? 512 : threads);
         const int grid = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
-        lu_regpanel_kernel<NB, R, 512><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork);
+        static const int dbg = getenv("GF_LU_DBG") ? atoi(getenv("GF_LU_DBG")) : 0;  // timing experiments only
+        static const int t256 = getenv("GF_LU_T256") ? atoi(getenv("GF_LU_T256")) : 0;
+        if (threads <= 256 && t256)  // 255 registers per thread: nothing spills, every load of the interchange pass in flight
+            lu_regpanel_kernel<NB, R, 256><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork, dbg);
+        else
+            lu_regpanel_kernel<NB, R, 512><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork, dbg);
         rc = gf_launch_status();
     } else {
         rc = launch_panel<NB>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s, j0, 1);
@@ -779,11 +798,18 @@ int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv
     if (rc != GF_OK) return rc;
     const int tr = Nmax - j0 - NB;
     if (tr > 0) {
+        static const int tn = getenv("GF_LU_TN") ? atoi(getenv("GF_LU_TN")) : 64;
         const int gz = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
-        dim3 grid((tr + 127) / 128, (tr + 63) / 64, gz);
-        constexpr int USMEM = (64 * (NB + 4) + NB * 132) * (int)sizeof(double);
-        cudaFuncSetAttribute(lu_update_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, USMEM);
-        lu_update_kernel<NB><<<grid, 256, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w, nwork);
+        if (tn == 64) {
+            dim3 grid((tr + 63) / 64, (tr + 63) / 64, gz);
+            constexpr int USMEM = (64 * (NB + 4) + NB * 68) * (int)sizeof(double);
+            lu_update_kernel<NB, 64><<<grid, 128, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w, nwork);
+        } else {
+            dim3 grid((tr + 127) / 128, (tr + 63) / 64, gz);
+            constexpr int USMEM = (64 * (NB + 4) + NB * 132) * (int)sizeof(double);
+            cudaFuncSetAttribute(lu_update_kernel<NB, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, USMEM);
+            lu_update_kernel<NB, 128><<<grid, 256, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w, nwork);
+        }
         rc = gf_launch_status();
     }
     return rc;
@@ -815,15 +841,20 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
     if (nwork_dev != nullptr && Nmax <= 830) return launch_panel<32>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
     // Multi-launch right-looking factorisation: per block column a pivoted panel kernel (panel resident in shared
     // memory, so its width follows the rows that are left) and the DMMA trailing update.
-    int j0 = 0;
+    int j0 = 0, nb = 8;
     while (j0 < Nmax) {
         const int rows = Nmax - j0;
+        // widest panel the rows left allow; a wider panel starts only on its own multiple (panels never straddle a
+        // 32-column block: the interchanges are not applied to the blocks left of the current one)
+        const int want = rows <= 512 ? 32 : (rows <= 1024 ? 16 : 8);
+        if (want <= nb || j0 % want == 0) nb = want;
         int rc;
-        if (rows <= 512) { rc = launch_column<32, 1>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 32; }
-        else if (rows <= 1024) { rc = launch_column<16, 2>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 16; }
-        else if (rows <= 2048) { rc = launch_column<8, 4>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 8; }
-        else { rc = launch_column<8, 0>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0); j0 += 8; }
+        if (nb == 32) rc = launch_column<32, 1>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
+        else if (nb == 16) rc = launch_column<16, 2>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
+        else if (rows <= 2048) rc = launch_column<8, 4>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
+        else rc = launch_column<8, 0>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
         if (rc != GF_OK) return rc;
+        j0 += nb;
     }
     return GF_OK;
 }
@@ -833,7 +864,7 @@ extern "C" int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const d
                            void* stream) {
     if (B <= 0 || ld <= 0 || Nmax < 0 || Nmax > ld || ldr < Nmax || !K || !piv || !rhs) return GF_ERR_ARG;
     if (nwork <= 0 || Nmax == 0) return GF_OK;
-    const size_t smem = (size_t)(Nmax + 1) * sizeof(double);
+    const size_t smem = (size_t)(Nmax + 1) * sizeof(double) + (size_t)Nmax * sizeof(int32_t);
     if (smem > 200 * 1024) return GF_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     lu_solve_kernel<<<nwork, 256, smem, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,

@@ -73,7 +73,7 @@ def test_solve_general_vs_oracle(n, m, B):
         assert rel_err(res.x[b].cpu().numpy(), ref.x) <= 1e-4  # both stop at opt_tol = 1e-6 on their own noise path
         c = refs[b].cons(res.x[b].cpu().numpy())
         assert (c >= d["cons_lb"][b] - 1e-6).all() and (c <= d["cons_ub"][b] + 1e-6).all()
-        assert abs(int(res.iterations[b].item()) - ref.iterations) <= 2  # past the rounding-noise horizon lambda differs
+        assert abs(int(res.iterations[b].item()) - ref.iterations) <= 4  # past the rounding-noise horizon lambda differs (the summation order of the LU substitution decides)
 
 
 def test_solve_general_golden_reference(golden):
