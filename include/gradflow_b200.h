@@ -255,6 +255,13 @@ int gf_band_permute(int B, int n, int m, int ld, const int32_t* perm, const int3
 
 /* ---- host-buffer entry (the reference hands its step solver host arrays: scaled_step_solver.py:76-79) ---- */
 
+/* ScaledProblem (scale.py:153-231): out[b][r][c] = ldexp(in[b][r][c], sr rw[b][r] + sc cw[b][c] + so ow[b]) for
+ * the instances of the work list; rw [B, rows], cw [B, cols], ow [B] are the integer weights of the reference's
+ * Scaling (var_weights / cons_weights / obj_weight), any of them may be NULL.  Exact (powers of two). */
+int gf_ldexp(int B, int rows, int cols, const double* in, const int32_t* rw, int sr, const int32_t* cw, int sc,
+             const int32_t* ow, int so, double* out, const int32_t* work, const int32_t* nwork_dev, int nwork,
+             void* stream);
+
 /* H [cnt, n, n] is symmetric (problem.py:174-192): copy only its lower block triangle (row blocks of `blk` rows,
  * columns up to the end of the diagonal block) from pinned host memory with one strided copy per row block, and
  * rebuild the blocks above the diagonal on the device (blk a multiple of 32). */

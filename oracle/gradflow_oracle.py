@@ -27,7 +27,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import Callable, List, Optional
+from typing import Any, Callable, List, Optional
 
 import numpy as np
 import scipy.linalg
@@ -105,6 +105,10 @@ class OracleParams:
     # plugin hook, same contract as pygradflow/step/solver/__init__.py:18-19
     step_solver: Optional[Callable] = None
     step_solver_type: str = "symmetric"  # symmetric | asymmetric | extended | standard  (params.py:50-70,235)
+    scaling_type: str = "none"  # none | grad_jac | kkt | nominal | custom  (params.py:166-195,245-250)
+    scaling: Optional[Any] = None
+    scaling_primal: Optional[np.ndarray] = None
+    scaling_dual: Optional[np.ndarray] = None
     dtype = np.float64
 
 
@@ -260,17 +264,170 @@ class ConstrainedProblem(OracleProblem):
         return self._orig(x), y, self._orig(d)
 
 
+# --------------------------------------------------------------------------
+# Power-of-two scaling (pygradflow/scale.py)
+# --------------------------------------------------------------------------
+def scale_symmetric(A):
+    """scale.py:12-45: iterative power-of-two equilibration of a symmetric matrix; returns integer exponents D.
+    The reference accumulates the column sums in an INTEGER array (`R = np.zeros(n, dtype=int); R[c] += |a|`), i.e.
+    every partial sum is truncated: restated literally."""
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    rows, cols = np.nonzero(A)                      # COO order of tocoo() on a dense-built matrix: row-major
+    data = np.abs(A[rows, cols])
+    D = np.zeros(n, dtype=int)
+    for _ in range(100):
+        R = np.zeros(n, dtype=int)
+        for k in range(len(data)):
+            R[cols[k]] += data[k]
+        R = R.astype(np.float64)
+        R[R < 1e-10] = 1.0
+        R = np.sqrt(R)
+        Rsca = 1 - np.frexp(R)[1]
+        if (Rsca == 0).all():
+            break
+        data = np.ldexp(data, Rsca[rows] + Rsca[cols])
+        D += Rsca
+    else:
+        raise Exception("Equilibration failed to converge")
+    return D
+
+
+class Scaling:
+    """scale.py:48-150: integer exponents; x_scaled = ldexp(x, var_weights), c_scaled = ldexp(c, cons_weights)."""
+
+    def __init__(self, var_weights, cons_weights, obj_weight=0):
+        self.var_weights = np.asarray(var_weights).astype(int)
+        self.cons_weights = np.asarray(cons_weights).astype(int)
+        self.obj_weight = int(obj_weight)
+
+    @staticmethod
+    def weights_from_nominal_values(values):                           # :75-77
+        return 1 - np.frexp(values)[1]
+
+    @staticmethod
+    def from_nominal_values(var_values, cons_values, obj_value=1.0):   # :67-73
+        w = Scaling.weights_from_nominal_values
+        return Scaling(w(var_values), w(cons_values), w(obj_value))
+
+    @staticmethod
+    def from_grad_jac(obj_grad, cons_jac):                             # :79-106
+        var_weights = -Scaling.weights_from_nominal_values(np.abs(obj_grad))
+        if cons_jac is None:
+            return Scaling(var_weights, np.zeros(0, dtype=int))
+        J = np.abs(_dense(cons_jac))
+        pres = np.ldexp(J, np.broadcast_to(-var_weights, J.shape))
+        max_values = np.zeros(J.shape[0], dtype=int)                   # integer array in the reference: truncation
+        for i in range(J.shape[0]):
+            for j in range(J.shape[1]):
+                if J[i, j] != 0.0:
+                    max_values[i] = max(max_values[i], pres[i, j])
+        return Scaling(var_weights, Scaling.weights_from_nominal_values(max_values))
+
+    @staticmethod
+    def from_equilibrated_kkt(lag_hess, cons_jac):                     # :108-119
+        H, J = _dense(lag_hess), _dense(cons_jac)
+        m, n = J.shape
+        K = np.zeros((n + m, n + m))
+        K[:n, :n], K[:n, n:], K[n:, :n] = H, J.T, J
+        w = scale_symmetric(K)
+        return Scaling(-w[:n], w[n:])
+
+    def scale_primal(self, x):
+        return np.ldexp(x, self.var_weights)
+
+    def unscale_primal(self, x):
+        return np.ldexp(x, -self.var_weights)
+
+    def scale_dual(self, y):
+        return np.ldexp(y, -(self.cons_weights - self.obj_weight))
+
+    def unscale_dual(self, y):
+        return np.ldexp(y, self.cons_weights - self.obj_weight)
+
+    def unscale_bounds_dual(self, d):
+        return np.ldexp(d, self.var_weights - self.obj_weight)
+
+
+class ScaledProblem(OracleProblem):
+    """scale.py:153-231."""
+
+    def __init__(self, problem, scaling):
+        self.problem, self.scaling = problem, scaling
+        vw, cw = scaling.var_weights, scaling.cons_weights
+        super().__init__(np.ldexp(problem.var_lb, vw), np.ldexp(problem.var_ub, vw), num_cons=problem.num_cons)
+        self.cons_lb = np.ldexp(problem.cons_lb, cw)
+        self.cons_ub = np.ldexp(problem.cons_ub, cw)
+
+    def _orig_x(self, x):
+        return np.ldexp(x, -self.scaling.var_weights)
+
+    def obj(self, x):
+        return np.ldexp(self.problem.obj(self._orig_x(x)), self.scaling.obj_weight)
+
+    def obj_grad(self, x):
+        g = np.ldexp(self.problem.obj_grad(self._orig_x(x)), -self.scaling.var_weights)
+        return np.ldexp(g, self.scaling.obj_weight)
+
+    def cons(self, x):
+        return np.ldexp(self.problem.cons(self._orig_x(x)), self.scaling.cons_weights)
+
+    def cons_jac(self, x):
+        J = _dense(self.problem.cons_jac(self._orig_x(x)))
+        vw, cw = self.scaling.var_weights, self.scaling.cons_weights
+        return np.ldexp(J, cw[:, None] - vw[None, :])
+
+    def lag_hess(self, x, y):
+        s = self.scaling
+        H = _dense(self.problem.lag_hess(self._orig_x(x), np.ldexp(y, s.cons_weights - s.obj_weight)))
+        return np.ldexp(H, s.obj_weight - s.var_weights[:, None] - s.var_weights[None, :])
+
+
+def create_scaling(problem, params, scaling_primal=None, scaling_dual=None):
+    """scale.py:234-280.  params.scaling_type: none | custom | nominal | grad_jac | kkt."""
+    st = params.scaling_type
+    if params.scaling is not None:
+        assert st == "custom"
+        return params.scaling
+    if st == "none":
+        return None
+    if st == "custom":
+        raise ValueError("Custom scaling requires explicit scaling")
+    if scaling_primal is None:
+        raise ValueError("Primal point required for scaling computation")
+    if st == "nominal":
+        cons_val = problem.cons(scaling_primal) if problem.num_cons > 0 else np.zeros(0)
+        return Scaling.from_nominal_values(scaling_primal, cons_val)
+    cons_jac = problem.cons_jac(scaling_primal) if problem.num_cons > 0 else np.zeros((0, problem.num_vars))
+    if st == "grad_jac":
+        return Scaling.from_grad_jac(problem.obj_grad(scaling_primal), cons_jac)
+    if st == "kkt":
+        if scaling_dual is None:
+            raise ValueError("Dual point required for KKT scaling computation")
+        return Scaling.from_equilibrated_kkt(problem.lag_hess(scaling_primal, scaling_dual), cons_jac)
+    raise ValueError(f"Unknown scaling type {st}")
+
+
 def solve_general(problem, params=None, x0=None, y0=None, record=False):
-    """Solver.solve for a problem with general constraint bounds: Transformation.create_transformed_iterate
-    (transform.py:29-54), the solve on the slack form, restore_sol (transform.py:88-104).  No scaling."""
+    """Solver.solve for a problem with general constraint bounds: Transformation (transform.py:13-104) = optional
+    power-of-two scaling (scale.py), slack transform, create_transformed_iterate (:29-54), the solve, restore_sol
+    (:90-104)."""
+    params = params if params is not None else OracleParams()
     n, m = problem.num_vars, problem.num_cons
     x = np.clip(np.zeros(n), problem.var_lb, problem.var_ub) if x0 is None else np.broadcast_to(x0, (n,)).astype(float)
     y = np.zeros(m) if y0 is None else np.broadcast_to(y0, (m,)).astype(float)
-    cp = ConstrainedProblem(problem)
+    scaling = create_scaling(problem, params, params.scaling_primal, params.scaling_dual)
+    scaled = problem if scaling is None else ScaledProblem(problem, scaling)
+    if scaling is not None:
+        x, y = scaling.scale_primal(x), scaling.scale_dual(y)
+    cp = ConstrainedProblem(scaled)
     xt, yt = cp.transform_sol(x, y)
     res = Solver(cp, params).solve(xt, yt, record=record)
     res.x_slack = res.x
     res.x, res.y, res.d = cp.restore_sol(res.x, res.y, res.d)
+    if scaling is not None:
+        res.x, res.y, res.d = scaling.unscale_primal(res.x), scaling.unscale_dual(res.y), scaling.unscale_bounds_dual(res.d)
+    res.scaling = scaling
     return res
 
 

@@ -8,7 +8,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libgradflow_b200.so")
-SOURCES = ["gf_api.cu", "gf_eval.cu", "gf_step.cu", "gf_lu.cu", "gf_ldlt.cu", "gf_linesearch.cu", "gf_xfer.cu", "gf_band.cu"]
+SOURCES = ["gf_api.cu", "gf_eval.cu", "gf_step.cu", "gf_lu.cu", "gf_ldlt.cu", "gf_linesearch.cu", "gf_xfer.cu", "gf_band.cu", "gf_scale.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xptxas=-v",

@@ -236,6 +236,15 @@ def armijo_residual(xt, yt, x0, y0, dL, cons, lb, ub, dt, res, inner, newton_tol
 SYM_BLOCK = 64  # row-block height of the symmetric transfer
 
 
+def ldexp(src, out, work: WorkList, rw=None, sr: int = 0, cw=None, sc: int = 0, ow=None, so: int = 0):
+    """out[b][r][c] = ldexp(src[b][r][c], sr rw[b][r] + sc cw[b][c] + so ow[b]); src [B, cols] or [B, rows, cols]."""
+    B = src.shape[0]
+    rows, cols = (1, src.shape[1]) if src.dim() == 2 else (src.shape[1], src.shape[2])
+    if src.dim() == 1:
+        rows, cols = 1, 1
+    _call("gf_ldexp", B, rows, cols, ptr(src), ptr(rw), sr, ptr(cw), sc, ptr(ow), so, ptr(out), *_w(work))
+
+
 def h2d_sym_lower(dst, src_host, cnt: int):
     """dst[:cnt] (device, [*, n, n]) <- lower block triangle of the pinned host tensor src_host[:cnt]."""
     n = dst.shape[1]

@@ -51,6 +51,7 @@ SIGNATURES = {
     "gf_band_factor": [_I, _I, _I, _P, _P, _P] + _WORK,
     "gf_band_solve": [_I, _I, _I, _P, _P] + _WORK,
     "gf_band_permute": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I] + _WORK,
+    "gf_ldexp": [_I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _P] + _WORK,
     "gf_h2d_sym_lower": [_P, _P, _I, _I, _I, _P],
     "gf_symmetrize_lower": [_P, _I, _I, _I, _P],
     "gf_build_worklist": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P],

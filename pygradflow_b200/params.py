@@ -45,6 +45,16 @@ class StepSolverType(enum.Enum):
     Asymmetric = enum.auto()
 
 
+class ScalingType(enum.Enum):
+    """pygradflow/params.py:166-195: how create_scaling (scale.py:234-280) chooses the power-of-two weights."""
+
+    NoScaling = enum.auto()
+    GradJac = enum.auto()
+    KKT = enum.auto()
+    Nominal = enum.auto()
+    Custom = enum.auto()
+
+
 class ActiveSetType(enum.Enum):
     """pygradflow/params.py:14-18: how the point that decides the active set is chosen (newton_control.py:60-88)."""
 
@@ -99,6 +109,10 @@ class Params:
     step_solver_type: StepSolverType = StepSolverType.Symmetric
     linear_solver_type: LinearSolverType = LinearSolverType.Auto
     penalty_update: PenaltyUpdate = PenaltyUpdate.DualNorm
+    scaling_type: ScalingType = ScalingType.NoScaling
+    scaling_primal: Optional[Any] = None
+    scaling_dual: Optional[Any] = None
+    scaling: Optional[Any] = None  # Custom: a scale.BatchedScaling or (var_weights, cons_weights[, obj_weight])
     iteration_limit: Optional[int] = None
     obj_lower_limit: float = -1e10
     inertia_correction: bool = False
@@ -107,7 +121,8 @@ class Params:
     def __post_init__(self):
         for key, cls in (("newton_type", NewtonType), ("linear_solver_type", LinearSolverType),
                          ("penalty_update", PenaltyUpdate), ("step_control_type", StepControlType),
-                         ("active_set_type", ActiveSetType), ("step_solver_type", StepSolverType)):
+                         ("active_set_type", ActiveSetType), ("step_solver_type", StepSolverType),
+                         ("scaling_type", ScalingType)):
             v = getattr(self, key)
             if not isinstance(v, cls):
                 setattr(self, key, cls[_enum_name(v)])  # accepts strings and the reference's own enums
@@ -125,7 +140,7 @@ class Params:
         """Copy the hot-path fields out of a reference ``pygradflow.params.Params`` (or any look-alike)."""
         kw = {}
         for f in Params.__dataclass_fields__:
-            if f in ("step_solver", "linear_solver_type"):
+            if f in ("step_solver", "linear_solver_type", "scaling"):
                 continue
             if hasattr(ref, f):
                 v = getattr(ref, f)

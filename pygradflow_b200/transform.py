@@ -2,7 +2,7 @@
 path, which works on equalities + variable bounds.
 
 Device twin of the reference's ``ConstrainedProblem`` (pygradflow/cons_problem.py:8-173) and of the slack part of
-``Transformation`` (pygradflow/transform.py:13-104; scaling is out of scope): one slack variable per inequality
+``Transformation`` (pygradflow/transform.py:13-104; the scaling stage is pygradflow_b200/scale.py): one slack variable per inequality
 row, c_i(x) - s_i = 0 with cl_i <= s_i <= cu_i; equality rows are shifted by -cl_i.  The wrapped family keeps
 evaluating through its own kernels; the wrapper only does the index bookkeeping (strided copies of the family's
 outputs into the augmented tensors, the constant -1 columns of the Jacobian, the zero slack block of the Hessian).
@@ -116,10 +116,14 @@ class BatchedConstrained(BatchedProblem):
 
 
 def solve_general(problem: BatchedProblem, cons_lb, cons_ub, params=None, x0=None, y0=None):
-    """``Solver(problem, params).solve(x0, y0)`` for a batch whose constraints carry bounds: initial point
-    (transform.py:29-54: None -> clip(0, lb, ub) / 0, scalars broadcast), slack transform, solve, restore."""
+    """``Solver(problem, params).solve(x0, y0)`` for a batch whose constraints carry bounds: the reference's
+    ``Transformation`` (transform.py:13-104) -- initial point (:29-54: None -> clip(0, lb, ub) / 0, scalars
+    broadcast), optional power-of-two scaling (scale.py, ``params.scaling_type``), slack transform, solve, restore."""
+    from .params import Params
+    from .scale import BatchedScaled, create_scaling
     from .solver import BatchedSolver
 
+    params = params if params is not None else Params()
     dev = problem.device
     B, n, m = problem.B, problem.n, problem.m
     f64 = dict(dtype=torch.float64, device=dev)
@@ -128,9 +132,19 @@ def solve_general(problem: BatchedProblem, cons_lb, cons_ub, params=None, x0=Non
     else:
         x = torch.as_tensor(x0, dtype=torch.float64).to(dev).expand(B, n).contiguous()
     y = torch.zeros((B, m), **f64) if y0 is None else torch.as_tensor(y0, dtype=torch.float64).to(dev).expand(B, m).contiguous()
-    cp = BatchedConstrained(problem, cons_lb, cons_ub)
+    cl = torch.as_tensor(cons_lb, dtype=torch.float64).to(dev).expand(B, m)
+    cu = torch.as_tensor(cons_ub, dtype=torch.float64).to(dev).expand(B, m)
+    scaling = create_scaling(problem, params, params.scaling_primal, params.scaling_dual)
+    if scaling is not None:                                             # transform.py:56-64, 76-88
+        problem = BatchedScaled(problem, scaling)
+        cl, cu = torch.ldexp(cl, scaling.cons_weights), torch.ldexp(cu, scaling.cons_weights)   # scale.py:161-162
+        x, y = scaling.scale_primal(x).contiguous(), scaling.scale_dual(y).contiguous()
+    cp = BatchedConstrained(problem, cl, cu)
     xt, yt = cp.transform_sol(x, y)
     res = BatchedSolver(cp, params).solve(xt, yt)
     res.x_slack = res.x
     res.x, res.y = cp.restore_sol(res.x, res.y)
+    if scaling is not None:                                             # transform.py:90-104
+        res.x, res.y = scaling.unscale_primal(res.x), scaling.unscale_dual(res.y)
+    res.scaling = scaling
     return res

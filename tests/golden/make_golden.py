@@ -370,6 +370,56 @@ def golden_constrained():
     np.savez_compressed(os.path.join(HERE, "constrained.npz"), **out)
 
 
+class RefGeneralQPFresh(RefGeneralQP):
+    """Returns NEW matrices from every callback.  The reference's ScaledProblem.cons_jac (scale.py:196-214) rescales
+    `jac_orig.tocoo().data` in place, and csr.tocoo() shares the data array with the caller's matrix: a Problem that
+    hands out its stored Jacobian (RefGeneralQP) has it rescaled again on every evaluation and the solve breaks down
+    (lambda runs into lamb_max).  The reference's own fixtures build their matrices per call, as this class does."""
+
+    def cons_jac(self, x):
+        return self.A.copy()
+
+    def lag_hess(self, x, _):
+        return self.H.copy()
+
+
+def golden_scaling():
+    """Power-of-two scaling (scale.py) through the reference's Transformation: the weights create_scaling computes
+    and Solver.solve with Params(scaling_type=...) on general QPs and on the reference's HS71Constrained fixture."""
+    from pygradflow.params import ScalingType
+    from pygradflow.scale import Scaling, create_scaling
+
+    out = {}
+    cases = []
+    for (n, m, k) in [(16, 8, 0), (24, 12, 1)]:
+        d = synth.general_qp_instance(k, n, m)
+        cases.append((f"gqp_n{n}_m{m}_k{k}", lambda d=d: RefGeneralQPFresh(d), d["x0"], d["y0"],
+                      np.linspace(0.3, 2.0, n), np.linspace(-1.0, 1.0, m)))
+    hsmod = _load_ref_fixture("hs71_cons")
+    cases.append(("hs71_cons", lambda: hsmod.HS71Constrained(), np.array([1.0, 5.0, 5.0, 1.0]), np.zeros(2),
+                  np.array([1.0, 5.0, 5.0, 1.0]), np.array([0.5, -0.25])))
+    for name, make, x0, y0, sp_, sd_ in cases:
+        for kind in ("GradJac", "KKT", "Nominal", "Custom"):
+            prob = make()
+            kw = dict(scaling_type=ScalingType[kind], scaling_primal=sp_, scaling_dual=sd_)
+            if kind == "Custom":
+                rng = np.random.default_rng(len(name))
+                kw["scaling"] = Scaling(rng.integers(-3, 4, prob.num_vars), rng.integers(-3, 4, prob.num_cons),
+                                        int(rng.integers(-2, 3)))
+            params = params_for("Simplified", **kw)
+            sc = create_scaling(prob, params, sp_, sd_)
+            try:
+                res = trace_solve(prob, params, x0, y0, keep_every=4)
+                res["failed"] = np.bool_(False)
+            except Exception as err:  # solver.py:323-326: lambda ran into lamb_max
+                res = dict(failed=np.bool_(True), error=np.str_(str(err)[:60]))
+            res.update(var_weights=np.asarray(sc.var_weights, dtype=np.int64),
+                       cons_weights=np.asarray(sc.cons_weights, dtype=np.int64), obj_weight=np.int64(sc.obj_weight),
+                       scaling_primal=sp_, scaling_dual=sd_)
+            out.update(flat(f"{name}/{kind}", res))
+    np.savez_compressed(os.path.join(HERE, "scaling.npz"), **out)
+
+
 def golden_controllers():
     """The other Newton-based step controllers (step_control.py:123-150): ResiduumRatio, Exact, Fixed."""
     from pygradflow.params import StepControlType
@@ -446,6 +496,7 @@ if __name__ == "__main__":
     golden_controllers()
     golden_active_set_types()
     golden_step_solvers()
+    golden_scaling()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -246,6 +246,72 @@ def test_step_solver_formulations(golden, kind, prob):
     assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8
 
 
+SCALING = {"GradJac": "grad_jac", "KKT": "kkt", "Nominal": "nominal", "Custom": "custom"}
+
+
+def _scaling_case(g, name, kind):
+    key = f"{name}/{kind}"
+    if name.startswith("gqp"):
+        n, m, k = (int(t[1:]) for t in name.split("_")[1:])
+        d = synth.general_qp_instance(k, n, m)
+        p = orc.GeneralQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"], d["cons_lb"], d["cons_ub"])
+        x0, y0 = d["x0"], d["y0"]
+    else:
+        p, x0, y0 = orc.HS71Constrained(), np.array([1.0, 5.0, 5.0, 1.0]), np.zeros(2)
+    sc = None
+    if kind == "Custom":
+        sc = orc.Scaling(g[f"{key}/var_weights"], g[f"{key}/cons_weights"], int(g[f"{key}/obj_weight"]))
+    params = orc.OracleParams(scaling_type=SCALING[kind], scaling=sc, scaling_primal=g[f"{key}/scaling_primal"],
+                              scaling_dual=g[f"{key}/scaling_dual"])
+    return key, p, params, x0, y0
+
+
+@pytest.mark.parametrize("kind", list(SCALING))
+@pytest.mark.parametrize("name", ["gqp_n16_m8_k0", "gqp_n24_m12_k1", "hs71_cons"])
+def test_scaling_weights_and_solve(golden, name, kind):
+    """scale.py (create_scaling, ScaledProblem, Transformation.transform_sol / restore_sol) against the reference:
+    identical integer weights; same status and solution.  On the well-conditioned HS71 runs the whole trace and
+    the iteration counts are identical; the scaled random QPs start with a dozen rejected steps on nearly singular
+    systems (the oracle with LAPACK instead of SuperLU already takes a different path there), so only what survives
+    that is compared."""
+    g = golden("scaling")
+    key, p, params, x0, y0 = _scaling_case(g, name, kind)
+    sc = orc.create_scaling(p, params, params.scaling_primal, params.scaling_dual)
+    assert np.array_equal(sc.var_weights, g[f"{key}/var_weights"])
+    assert np.array_equal(sc.cons_weights, g[f"{key}/cons_weights"])
+    assert sc.obj_weight == int(g[f"{key}/obj_weight"])
+    res = orc.solve_general(p, params, x0, y0, record=True)
+    assert res.status == int(g[f"{key}/status"]) == 1
+    assert rel_err(res.x, g[f"{key}/x"]) <= 2e-6
+    assert rel_err(res.y, g[f"{key}/y"]) <= 1e-4
+    if name == "hs71_cons" and kind != "Nominal":
+        assert res.iterations == int(g[f"{key}/iterations"])
+        assert [t["accept"] for t in res.trace] == list(g[f"{key}/accepts"])
+        for row, i in enumerate(g[f"{key}/trace_idx"]):
+            assert rel_err(res.trace[i]["x"], g[f"{key}/trace_x"][row]) <= 1e-8, (key, i)
+        assert rel_err(res.d, g[f"{key}/d"]) <= 1e-6
+
+
+def test_scaled_problem_callbacks_exact():
+    """ScaledProblem (scale.py:153-231) is exact in floating point (ldexp): the scaled callbacks equal the unscaled
+    ones times the corresponding powers of two, bit for bit; zero weights are the identity (test_scale.py:22-48)."""
+    p = orc.HS71Constrained()
+    rng = np.random.default_rng(0)
+    sc = orc.Scaling(np.array([1, 2, 3, -4]), np.array([3, 2]), 4)      # test_scale.py:51-60 (first four weights)
+    sp_ = orc.ScaledProblem(p, sc)
+    x, y = rng.uniform(1.0, 5.0, 4), rng.standard_normal(2)
+    xs, ys = sc.scale_primal(x), sc.scale_dual(y)
+    assert sp_.obj(xs) == p.obj(x) * 2.0 ** 4                           # test_scale.py:63-80
+    assert np.array_equal(sp_.obj_grad(xs), p.obj_grad(x) * 2.0 ** (4 - sc.var_weights))
+    assert np.array_equal(sp_.cons(xs), p.cons(x) * 2.0 ** sc.cons_weights)
+    J = np.asarray(p.cons_jac(x).todense() if hasattr(p.cons_jac(x), "todense") else p.cons_jac(x))
+    assert np.array_equal(sp_.cons_jac(xs), J * 2.0 ** (sc.cons_weights[:, None] - sc.var_weights[None, :]))
+    z = orc.ScaledProblem(p, orc.Scaling(np.zeros(4, dtype=int), np.zeros(2, dtype=int)))
+    assert z.obj(x) == p.obj(x) and np.array_equal(z.obj_grad(x), p.obj_grad(x))
+    assert np.array_equal(z.lag_hess(x, y), np.asarray(p.lag_hess(x, y)))
+    assert np.array_equal(sc.unscale_primal(xs), x) and np.array_equal(sc.unscale_dual(ys), y)
+
+
 @pytest.mark.parametrize("newton", ["Simplified", "Full"])
 @pytest.mark.parametrize("kind", ["Smallest", "Explicit"])
 def test_tau_active_set_types(golden, kind, newton):
