@@ -846,11 +846,13 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
         const int rows = Nmax - j0;
         // widest panel the rows left allow; a wider panel starts only on its own multiple (panels never straddle a
         // 32-column block: the interchanges are not applied to the blocks left of the current one)
-        const int want = rows <= 512 ? 32 : (rows <= 1024 ? 16 : 8);
+        // (the panel lives in registers up to 512 R rows, in shared memory -- 16 wide up to 1700 rows -- beyond)
+        const int want = rows <= 512 ? 32 : (rows <= 1700 ? 16 : 8);
         if (want <= nb || j0 % want == 0) nb = want;
         int rc;
         if (nb == 32) rc = launch_column<32, 1>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
-        else if (nb == 16) rc = launch_column<16, 2>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
+        else if (nb == 16 && rows <= 1024) rc = launch_column<16, 2>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
+        else if (nb == 16) rc = launch_column<16, 0>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
         else if (rows <= 2048) rc = launch_column<8, 4>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
         else rc = launch_column<8, 0>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
         if (rc != GF_OK) return rc;
