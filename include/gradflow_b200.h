@@ -206,8 +206,9 @@ int gf_dr_first(int B, const int32_t* status, const int32_t* info, const double*
 int gf_dr_second(int B, const double* dt, const double* diff1, const double* diff2, double theta_max,
                  double log_theta_ref, double K_P, double K_I, double lamb_min, double lamb_inc, double* err_sum,
                  int32_t* phase, double* lamb_next, double* theta, void* stream);
-/* End of the outer iteration (solver.py:318-378): lamb_max guard, DualNormUpdate (penalty.py:59-74) or
- * constant penalty, iterate <- accepted Newton iterate, counters. */
+/* End of the outer iteration (solver.py:318-378): lamb_max guard, penalty update (dual_norm_update = 0: constant,
+ * 1: DualNormUpdate penalty.py:46-74, 2: DualEquilibration penalty.py:77-113), iterate <- accepted Newton iterate,
+ * counters. */
 int gf_commit(int B, int n, int m, const int32_t* phase, const double* lamb_next, double lamb_max,
               int dual_norm_update, const double* xm, const double* ym, const double* gm, const double* cm,
               const double* om, const double* xf, const double* yf, const double* gf, const double* cf,

@@ -97,7 +97,7 @@ class OracleParams:
     step_control_type: str = "distance_ratio"  # distance_ratio | residuum_ratio | exact | fixed
     active_set_type: str = "standard"  # standard | explicit | smallest | largest  (params.py:14-18,225-227)
     active_set_tau: Optional[float] = None
-    penalty_update: str = "dual_norm"  # dual_norm | constant
+    penalty_update: str = "dual_norm"  # dual_norm | constant | dual_equilibration
     iteration_limit: Optional[int] = None
     obj_lower_limit: float = -1e10
     inertia_correction: bool = False
@@ -1516,7 +1516,17 @@ class Penalty:
     def update(self, next_iterate):
         if self.params.penalty_update == "constant":
             return self.params.rho
-        if self.problem.num_cons == 0:
+        if self.params.penalty_update == "dual_equilibration":         # penalty.py:77-113
+            cons = next_iterate.cons
+            yprod = abs(np.dot(next_iterate.y, cons))
+            viol = 1.0 / 2.0 * np.dot(cons, cons)
+            if viol == 0.0:
+                return self.rho
+            target_rho = 0.01 * yprod / viol
+            if self.rho < target_rho:
+                self.rho = max(self.rho * 10.0, target_rho)
+            return self.rho
+        if self.problem.num_cons == 0:                                  # penalty.py:46-74
             return self.rho
         ynorm = float(np.max(np.abs(next_iterate.y)))
         if ynorm >= 10.0 * self.rho:

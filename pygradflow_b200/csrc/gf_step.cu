@@ -453,7 +453,8 @@ __global__ void dr_second_kernel(int B, const double* __restrict__ dt, const dou
 }
 
 // End of an outer iteration (solver.py:318-378): lambda hand-over, lamb_max guard, penalty update
-// (penalty.py:59-74, DualNorm or constant), iterate <- accepted Newton iterate, counters.
+// (penalty.py:36-113; dual_norm_update = 0 constant, 1 DualNorm, 2 DualEquilibration), iterate <- accepted Newton
+// iterate, counters.
 __global__ void commit_kernel(int n, int m, const int32_t* __restrict__ phase, const double* __restrict__ lamb_next,
                               double lamb_max, int dual_norm_update, const double* __restrict__ xm,
                               const double* __restrict__ ym, const double* __restrict__ gm,
@@ -479,7 +480,7 @@ __global__ void commit_kernel(int n, int m, const int32_t* __restrict__ phase, c
         const double* ys = acc_mid ? ym : yf;
         const double* gs = acc_mid ? gm : gf;
         const double* cs = acc_mid ? cm : cf;
-        double ymax = 0.0;
+        double ymax = 0.0, yc = 0.0, cc = 0.0;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const size_t o = (size_t)b * n + i;
             x[o] = xs[o];
@@ -487,17 +488,29 @@ __global__ void commit_kernel(int n, int m, const int32_t* __restrict__ phase, c
         }
         for (int j = threadIdx.x; j < m; j += blockDim.x) {
             const size_t o = (size_t)b * m + j;
-            const double yy = ys[o];
+            const double yy = ys[o], cj = cs[o];
             y[o] = yy;
-            cons[o] = cs[o];
+            cons[o] = cj;
             ymax = fmax(ymax, fabs(yy));
+            yc += yy * cj;
+            cc += cj * cj;
         }
         ymax = block_max(ymax, red);
+        if (dual_norm_update == 2) {  // uniform per launch
+            yc = block_sum(yc, red);
+            cc = block_sum(cc, red);
+        }
         if (threadIdx.x == 0) {
             obj[b] = acc_mid ? om[b] : of[b];
-            if (dual_norm_update && m > 0) {
-                const double r = rho[b];
+            const double r = rho[b];
+            if (dual_norm_update == 1 && m > 0) {          // DualNormUpdate, penalty.py:59-74
                 if (ymax >= 10.0 * r) rho[b] = fmin(ymax, 10.0 * r);
+            } else if (dual_norm_update == 2) {            // DualEquilibration, penalty.py:90-113
+                const double viol = 0.5 * cc;
+                if (viol != 0.0) {
+                    const double target = 0.01 * fabs(yc) / viol;
+                    if (r < target) rho[b] = fmax(r * 10.0, target);
+                }
             }
             accepted[b] += 1;
         }

@@ -194,7 +194,7 @@ def commit(phase, lamb_next, lamb_max, dual_norm_update, mid, fin, cur, lamb, rh
     """mid / fin / cur: tuples (x, y, grad, cons, obj)."""
     B, n = cur[0].shape
     m = 0 if cur[1] is None else cur[1].shape[1]
-    _call("gf_commit", B, n, m, ptr(phase), ptr(lamb_next), lamb_max, 1 if dual_norm_update else 0,
+    _call("gf_commit", B, n, m, ptr(phase), ptr(lamb_next), lamb_max, int(dual_norm_update),
           *[ptr(t) for t in mid], *[ptr(t) for t in fin], *[ptr(t) for t in cur], ptr(lamb), ptr(rho), ptr(iters),
           ptr(accepted), ptr(status), _stream())
 

@@ -75,10 +75,12 @@ class StepControlType(enum.Enum):
 
 
 class PenaltyUpdate(enum.Enum):
-    """pygradflow/params.py:133-139 (only the two strategies on the named path)."""
+    """pygradflow/params.py:122-128: the strategies that always accept the step (penalty.py:36-113); ParetoDecrease
+    and the filters, which may reject it, are out of scope."""
 
     Constant = enum.auto()
     DualNorm = enum.auto()
+    DualEquilibration = enum.auto()
 
 
 def _enum_name(value) -> str:
@@ -145,7 +147,7 @@ class Params:
             if hasattr(ref, f):
                 v = getattr(ref, f)
                 if f == "penalty_update" and _enum_name(v) not in PenaltyUpdate.__members__:
-                    raise ValueError(f"penalty_update={_enum_name(v)} is outside the B200 path (Constant / DualNorm)")
+                    raise ValueError(f"penalty_update={_enum_name(v)} is outside the B200 path (Constant / DualNorm / DualEquilibration)")
                 if f == "step_solver_type" and _enum_name(v) not in StepSolverType.__members__:
                     raise ValueError(f"step_solver_type={_enum_name(v)} is outside the B200 path")
                 if f == "step_control_type" and _enum_name(v) not in StepControlType.__members__:

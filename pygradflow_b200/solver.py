@@ -214,7 +214,7 @@ class BatchedSolver:
         if on_iteration is not None:
             on_iteration(outer, self)
         # ---- accept / reject, penalty, counters (solver.py:318-378)
-        dual_norm = prm.penalty_update == PenaltyUpdate.DualNorm
+        dual_norm = {PenaltyUpdate.Constant: 0, PenaltyUpdate.DualNorm: 1, PenaltyUpdate.DualEquilibration: 2}[prm.penalty_update]
         K.commit(self.phase, self.lamb_next, prm.lamb_max, dual_norm, self.mid, self.fin, self.cur, self.lamb,
                  self.rho, self.iters, self.accepted, self.status)
 

@@ -474,6 +474,25 @@ def golden_step_solvers():
     np.savez_compressed(os.path.join(HERE, "step_solvers.npz"), **out)
 
 
+def golden_penalty():
+    """PenaltyUpdate.DualEquilibration (penalty.py:77-113) and Constant through Solver.solve."""
+    from pygradflow.params import PenaltyUpdate
+
+    out = {}
+    for kind in ("DualEquilibration", "Constant"):
+        for newton in ("Simplified", "Full"):
+            for (n, m, k) in [(16, 8, 0), (32, 16, 2)]:
+                d = synth.qp_instance(k, n, m)
+                try:
+                    res = trace_solve(RefQP(d), params_for(newton, penalty_update=PenaltyUpdate[kind], iteration_limit=300), d["x0"], d["y0"],
+                                      keep_every=4)
+                    res["failed"] = np.bool_(False)
+                except Exception as err:  # solver.py:323-326: lambda ran into lamb_max
+                    res = dict(failed=np.bool_(True), error=np.str_(str(err)[:60]))
+                out.update(flat(f"{kind}/{newton}/qp_n{n}_m{m}_k{k}", res))
+    np.savez_compressed(os.path.join(HERE, "penalty.npz"), **out)
+
+
 def golden_ocp():
     """cfg4-style discretised optimal-control problems (small): full traces of the real reference."""
     out = {}
@@ -497,6 +516,7 @@ if __name__ == "__main__":
     golden_active_set_types()
     golden_step_solvers()
     golden_scaling()
+    golden_penalty()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

