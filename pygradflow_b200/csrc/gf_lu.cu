@@ -13,11 +13,15 @@
 // interchange of a strided storage column costs a 32-byte sector per element, and the left part is half of them.
 // gf_lu_solve applies the interchanges block by block accordingly; the factors are only meaningful to it.
 //
-//   lu_warp_kernel   N <= 32: one warp per matrix, matrix resident in registers, pivoting by warp shuffles.
-//   lu_smem_kernel   N <= ~110: whole matrix resident in shared memory, one CTA per matrix (cfg2, n=64).
-//   lu_panel_kernel  larger N: right-looking blocked, NB-wide pivoted panel in shared memory, TRSM +
-//                    register-tiled trailing update streamed through L2/HBM.  Robust general path; the
-//                    throughput path for quasi-definite K is the LDL' in gf_ldlt.cu.
+//   lu_warp_kernel     N <= 32: one warp per matrix, matrix resident in registers, pivoting by warp shuffles.
+//   lu_rows_kernel     N <= 64: two warps per matrix, rows resident in registers, pivot row through shared memory
+//                      (cfg2, n = 64).
+//   lu_smem_kernel     N <= ~110: whole matrix resident in shared memory, one CTA per matrix.
+//   lu_regpanel_kernel larger N, per block column: pivoted panel resident in registers (thread per row), the
+//                      interchanges of the other storage rows and U12; then lu_update_kernel, the right-looking
+//                      trailing update on the FP64 tensor pipe.  (lu_panel_kernel: the shared-memory panel, kept for
+//                      more than 2048 rows, 1024 < rows <= 1700, and as the single-launch fallback-list path.)
+//                      Robust general path; the throughput path for quasi-definite K is the LDL' in gf_ldlt.cu.
 //   lu_solve_kernel  blocked substitution, factors streamed once (HBM-bound).
 #include <cstdlib>
 #include "gf_common.cuh"
@@ -183,6 +187,96 @@ __global__ void __launch_bounds__(256) lu_warp_kernel(int ld, const int32_t* __r
     if (row)
         for (int c = 0; c < N; c++) Kb[(size_t)c * ld + pos] = stage[c * 32 + lane];
     if (lane == 0) info[b] = sinfo;
+}
+
+// 32 < N <= 64: one CTA of two warps per matrix, thread t owns row t in a rotating register file (the current column
+// is always a[0], as in lu_warp_kernel), but the pivot row travels through shared memory (one staged candidate row per
+// warp, one block barrier per column) instead of N shuffles per column.  Factor layout as everywhere: the
+// interchanges of the second 32-column block are not applied to the first one (pos32).
+template <int NMAX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) lu_rows_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                             double* __restrict__ K, int32_t* __restrict__ piv,
+                                                             int32_t* __restrict__ info, GfWork work, int nwork) {
+    constexpr int T = WARPS * 32;
+    constexpr int NONE = 1 << 20;
+    extern __shared__ double rsm[];
+    double* stage = rsm;                       // NMAX x T
+    double* wrow = rsm + NMAX * T;             // 2 x WARPS x NMAX
+    __shared__ double wval[2][WARPS];
+    __shared__ int wpos[2][WARPS];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+#pragma unroll 1
+    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int b = gf_instance(work, wi);
+        if (b < 0) return;
+        const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+        double* Kb = K + (size_t)b * ld * ld;
+        int32_t* pb = piv + (size_t)b * ld;
+        const bool row = t < N;
+        double a[NMAX];
+#pragma unroll
+        for (int c = 0; c < NMAX; c++) a[c] = (row && c < N) ? Kb[(size_t)c * ld + t] : 0.0;
+        int pos = t, pos32 = t;
+        int32_t sinfo = 0;
+#pragma unroll 1
+        for (int j = 0; j < N; j++) {
+            if (j == 32) pos32 = pos;
+            double v = fabs(a[0]);
+            int idx = pos;
+            if (!(row && pos >= j && v >= 0.0)) { v = -1.0; idx = NONE; }
+            double bv = v;
+            int bi = idx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            const int buf = j & 1;
+            if (bi == NONE) {
+                if (lane == 0) { wval[buf][wid] = -1.0; wpos[buf][wid] = NONE; }
+            } else if (idx == bi) {
+                wval[buf][wid] = bv;
+                wpos[buf][wid] = bi;
+                double* wr = wrow + (size_t)(buf * WARPS + wid) * NMAX;
+#pragma unroll
+                for (int c = 0; c < NMAX; c++) wr[c] = a[c];
+            }
+            __syncthreads();
+            bv = wval[buf][0];
+            bi = wpos[buf][0];
+            int bw = 0;
+#pragma unroll
+            for (int w2 = 1; w2 < WARPS; w2++) {
+                const double ov = wval[buf][w2];
+                const int oi = wpos[buf][w2];
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bw = w2; }
+            }
+            const int p = bi < NONE ? bi : j;
+            record_pivot(bv, j, &sinfo);
+            if (t == 0) pb[j] = p;
+            if (pos == p) pos = j;
+            else if (pos == j) pos = p;
+            const double* pr = wrow + (size_t)(buf * WARPS + bw) * NMAX;
+            const double pv = bi < NONE ? pr[0] : 0.0;
+            const bool below = row && pos > j && pv != 0.0;
+            double l = 0.0;
+            if (below) {
+                l = a[0] / pv;
+                a[0] = l;
+            }
+            stage[j * T + t] = a[0];  // final: L entry below the pivot, U entry on and above it
+#pragma unroll
+            for (int c = 1; c < NMAX; c++) a[c - 1] = below ? fma(-l, pr[c], a[c]) : a[c];
+            a[NMAX - 1] = 0.0;
+        }
+        if (N <= 32) pos32 = pos;
+        if (row) {
+            for (int c = 0; c < N; c++) Kb[(size_t)c * ld + (c < 32 ? pos32 : pos)] = stage[c * T + t];
+        }
+        if (t == 0) info[b] = sinfo;
+        __syncthreads();
+    }
 }
 
 template <int NMAX>
@@ -827,6 +921,13 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
     if (Nmax <= 8) return launch_warp_lu<8>(ld, Nmax, Nvec, K, piv, info, w, nwork, s);
     if (Nmax <= 16) return launch_warp_lu<16>(ld, Nmax, Nvec, K, piv, info, w, nwork, s);
     if (Nmax <= 32) return launch_warp_lu<32>(ld, Nmax, Nvec, K, piv, info, w, nwork, s);
+    if (Nmax <= 64) {  // register-resident rows, two warps per matrix
+        constexpr int RSMEM = (64 * 64 + 2 * 2 * 64) * (int)sizeof(double);
+        cudaFuncSetAttribute(lu_rows_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM);
+        const int grid = nwork < 148 * 6 ? nwork : 148 * 6;
+        lu_rows_kernel<64, 2><<<grid, 64, RSMEM, s>>>(ld, Nvec, Nmax, K, piv, info, w, nwork);
+        return gf_launch_status();
+    }
     const size_t full = (size_t)Nmax * (Nmax | 1) * sizeof(double);
     if (full <= 100 * 1024) {
         if (full > 48 * 1024) cudaFuncSetAttribute(lu_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)full);

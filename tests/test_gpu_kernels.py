@@ -220,7 +220,7 @@ def test_lu_golden_kkt(K, golden, N):
 
 
 @pytest.mark.parametrize("sizes", [[1, 2, 3, 5, 17, 31, 32], [32] * 19 + [7, 1], [1, 2, 3, 5, 17, 31, 32, 33],
-                                   [64, 63, 65, 100, 112], [113, 150, 257], [768, 700, 333], [1000, 530, 513, 40],
+                                   [64, 63, 40, 33, 7], [64, 63, 65, 100, 112], [113, 150, 257], [768, 700, 333], [1000, 530, 513, 40],
                                    [1100, 1030], [2100, 90]])
 def test_lu_ragged_batch_vs_lapack(K, sizes):
     """Ragged orders in one batch (warp-per-matrix register kernel, shared-memory kernel, blocked panel kernel +
@@ -250,7 +250,7 @@ def test_lu_singular_and_nonfinite_info(K):
     assert info[0] > 0 and info[1] == 1 and info[2] != 0 and info[3] == 0
 
 
-@pytest.mark.parametrize("N", [150, 300, 600, 1100])
+@pytest.mark.parametrize("N", [50, 64, 150, 300, 600, 1100])
 def test_lu_blocked_singular_and_nonfinite_info(K, N):
     """info of the multi-launch path (register-resident panels): a zero column reports its 1-based index like
     getrf, a NaN reports -1, a regular matrix in the same batch is untouched by its neighbours."""
