@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--stages", type=int, default=128)
     ap.add_argument("--linear", default="Auto")
     ap.add_argument("--newton", default="Simplified")
+    ap.add_argument("--step-solver", default="Symmetric", help="Symmetric | Asymmetric | Extended (full-order LU)")
     ap.add_argument("--check", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true", help="run every outer iteration eagerly (no CUDA-graph replay)")
     ap.add_argument("--out", default=None)
@@ -53,7 +54,8 @@ def main():
         prob = BatchedQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
         x0, y0 = d["x0"], d["y0"]
     gen_s = time.perf_counter() - t0
-    params = Params(linear_solver_type=LinearSolverType[args.linear], newton_type=NewtonType[args.newton])
+    params = Params(linear_solver_type=LinearSolverType[args.linear], newton_type=NewtonType[args.newton],
+                    step_solver_type=args.step_solver)
     solver = BatchedSolver(prob, params, use_graph=not args.no_graph)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -62,7 +64,8 @@ def main():
     wall = time.perf_counter() - t0
     st = res.status.cpu().numpy()
     it = res.iterations.cpu().numpy()
-    out = dict(cfg=args.cfg, B=B, n=n, m=m, linear=solver.engine.linear.name, newton=args.newton, wall_s=wall,
+    out = dict(cfg=args.cfg, B=B, n=n, m=m, linear=solver.engine.linear.name, newton=args.newton,
+               step_solver=args.step_solver, wall_s=wall,
                solves_per_s=B / wall, newton_steps=res.newton_steps, newton_steps_per_s=res.newton_steps / wall,
                outer_iterations=res.outer_iterations, ms_per_outer=1e3 * wall / max(1, res.outer_iterations),
                status_counts={int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
@@ -84,7 +87,7 @@ def main():
             else:
                 p = orc.DenseQP(d["H"][b], d["A"][b], d["g"][b], d["b"][b], d["lb"][b], d["ub"][b])
                 t1 = time.perf_counter()
-                ref = orc.Solver(p, orc.OracleParams()).solve(d["x0"][b], d["y0"][b])
+                ref = orc.Solver(p, orc.OracleParams(step_solver_type=args.step_solver.lower())).solve(d["x0"][b], d["y0"][b])
             cpu_s = time.perf_counter() - t1
             xg = res.x[b].cpu().numpy()
             chk.append(dict(instance=b, status_gpu=int(st[b]), status_cpu=int(ref.status), iters_gpu=int(it[b]),
