@@ -449,8 +449,7 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
 template <int NB, int R, int TMAX>
 __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                            double* __restrict__ K, int32_t* __restrict__ piv,
-                                                           int32_t* __restrict__ info, GfWork work, int j0, int nwork,
-                                                           int dbg) {
+                                                           int32_t* __restrict__ info, GfWork work, int j0, int nwork) {
     constexpr int NW = TMAX / 32;
     constexpr int NONE = 1 << 20;
     __shared__ double wrow[2][NW][NB];
@@ -478,10 +477,9 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
                 a[r][c] = (pos[r] < rows && c < jb) ? Kb[(size_t)(j0 + c) * ld + j0 + pos[r]] : 0.0;
         }
         int32_t sinfo = j0 == 0 ? 0 : info[b];
-        if ((dbg & 1) && t < NB) spiv[t] = t;
 #pragma unroll
         for (int jj = 0; jj < NB; jj++) {
-            if (jj < jb && !(dbg & 1)) {
+            if (jj < jb) {
                 double v = -1.0;
                 int idx = NONE, rs = 0;
 #pragma unroll
@@ -561,7 +559,7 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
         // ---- interchanges on the storage rows outside the panel + U12
 #pragma unroll 1
         for (int c = (j0 & ~31) + t; c < N; c += T) {  // not the earlier 32-column blocks
-            if ((c >= j0 && c < j0 + jb) || (dbg & 2)) continue;
+            if (c >= j0 && c < j0 + jb) continue;
             double* rowp = Kb + (size_t)c * ld + j0;
             // all loads of the row are issued before the first dependent use: the entering values (gather by src[])
             // and the old values of the panel range (contiguous), which is where every leaving value comes from
@@ -579,7 +577,7 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
                     if (sp != p) rowp[p] = uo[sp];
                 }
             }
-            if (c >= j0 + jb && !(dbg & 4)) {
+            if (c >= j0 + jb) {
 #pragma unroll
                 for (int k = 1; k < NB; k++) {
                     double sacc = u[k];
@@ -879,12 +877,7 @@ int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv
         int threads = ((Nmax - j0 + R - 1) / R + 31) & ~31;
         threads = threads < 256 ? 256 : (threads > 512 ? 512 : threads);
         const int grid = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
-        static const int dbg = getenv("GF_LU_DBG") ? atoi(getenv("GF_LU_DBG")) : 0;  // timing experiments only
-        static const int t256 = getenv("GF_LU_T256") ? atoi(getenv("GF_LU_T256")) : 0;
-        if (threads <= 256 && t256)  // 255 registers per thread: nothing spills, every load of the interchange pass in flight
-            lu_regpanel_kernel<NB, R, 256><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork, dbg);
-        else
-            lu_regpanel_kernel<NB, R, 512><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork, dbg);
+        lu_regpanel_kernel<NB, R, 512><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork);
         rc = gf_launch_status();
     } else {
         rc = launch_panel<NB>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s, j0, 1);
