@@ -898,10 +898,11 @@ __global__ void __launch_bounds__(256) ldlt_solve_kernel(int ld, const int32_t* 
 // Two internal streams per device: a large batch is factorised in two halves whose block-column launches
 // interleave, so the tail of one half's launch (few long chain CTAs left) is filled by the other half's CTAs.
 namespace {
+constexpr int LDLT_MAX_LANES = 4;
 struct LdltLanes {
-    cudaStream_t s[2];    // chain (or whole-column) stream of each half batch
-    cudaStream_t sp[2];   // panel stream of each half batch (split mode)
-    cudaEvent_t fork, join[2], evc[2], evp[2];
+    cudaStream_t s[LDLT_MAX_LANES];    // chain (or whole-column) stream of each part of the batch
+    cudaStream_t sp[LDLT_MAX_LANES];   // panel stream of each part (split mode)
+    cudaEvent_t fork, join[LDLT_MAX_LANES], evc[LDLT_MAX_LANES], evp[LDLT_MAX_LANES];
     bool ok;
 };
 LdltLanes* ldlt_lanes() {
@@ -915,7 +916,7 @@ LdltLanes* ldlt_lanes() {
     if (!made[dev]) {
         made[dev] = true;
         L.ok = true;
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < LDLT_MAX_LANES; i++) {
             L.ok = L.ok && cudaStreamCreateWithFlags(&L.s[i], cudaStreamNonBlocking) == cudaSuccess;
             L.ok = L.ok && cudaStreamCreateWithFlags(&L.sp[i], cudaStreamNonBlocking) == cudaSuccess;
             L.ok = L.ok && cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming) == cudaSuccess;
@@ -946,20 +947,29 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
 #endif
     cudaFuncSetAttribute(ldlt_diag0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
     cudaFuncSetAttribute(ldlt_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM);
-    static const bool lanes_on = [] { const char* e = getenv("GF_LDLT_LANES"); return e == nullptr || e[0] != '0'; }();
-    LdltLanes* L = (lanes_on && nwork >= LDLT_SPLIT_MIN && nblk > 2) ? ldlt_lanes() : nullptr;
+    // GF_LDLT_LANES: 0 = one stream, 2 (default) .. 4 = parts of the batch whose launches interleave
+    static const int lanes_req = [] {
+        const char* e = getenv("GF_LDLT_LANES");
+        const int v = e == nullptr ? 2 : atoi(e);
+        return v < 2 ? 1 : (v > LDLT_MAX_LANES ? LDLT_MAX_LANES : v);
+    }();
+    LdltLanes* L = (lanes_req > 1 && nwork >= LDLT_SPLIT_MIN && nblk > 2) ? ldlt_lanes() : nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (L != nullptr && (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) L = nullptr;
-    const int nlane = L != nullptr ? 2 : 1;
-    const int half = (nwork + 1) / 2;
-    const int off[2] = {0, L != nullptr ? half : 0}, cnt[2] = {L != nullptr ? half : nwork, nwork - half};
-    cudaStream_t st[2] = {L != nullptr ? L->s[0] : s, L != nullptr ? L->s[1] : s};
+    static const bool split_on = [] { const char* e = getenv("GF_LDLT_P64"); return e != nullptr && e[0] == '1'; }();
+    const int nlane = L != nullptr ? (split_on ? 2 : lanes_req) : 1;
+    int off[LDLT_MAX_LANES], cnt[LDLT_MAX_LANES];
+    cudaStream_t st[LDLT_MAX_LANES];
+    for (int i = 0; i < nlane; i++) {
+        off[i] = (int)((long)nwork * i / nlane);
+        cnt[i] = (int)((long)nwork * (i + 1) / nlane) - off[i];
+        st[i] = L != nullptr ? L->s[i] : s;
+    }
     if (L != nullptr) {
         cudaEventRecord(L->fork, s);
-        for (int i = 0; i < 2; i++) cudaStreamWaitEvent(L->s[i], L->fork, 0);
+        for (int i = 0; i < nlane; i++) cudaStreamWaitEvent(L->s[i], L->fork, 0);
     }
     // opt-in experiment (GF_LDLT_P64=1): +2 % on uniform batches, nothing on the ragged bench batch
-    static const bool split_on = [] { const char* e = getenv("GF_LDLT_P64"); return e != nullptr && e[0] == '1'; }();
     if (L != nullptr && split_on) {
         // Split mode: per half batch a chain stream (chain CTAs only, 2 per SM) and a panel stream (64-row panel tiles,
         // 3 per SM).  chain(k) needs panel(k-1); panel(k) needs chain(k-1) (the diagonal block of column k).
@@ -1001,7 +1011,7 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
     }
     }
     if (L != nullptr) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < nlane; i++) {
             cudaEventRecord(L->join[i], L->s[i]);
             cudaStreamWaitEvent(s, L->join[i], 0);
         }
