@@ -1183,16 +1183,21 @@ class StandardStepSolver:
         self.solver = None
         self.K = None
 
-    def solve(self, iterate):
+    def matrix(self):
+        """implicit_func.py:163-187 with the frozen derivatives."""
         n, m, dt = self.n, self.m, self.dt
+        keep = np.logical_not(self.active_set).astype(np.float64)[:, None]
+        K = np.zeros((n + m, n + m))
+        K[:n, :n] = np.eye(n) + keep * (dt * self.hess)
+        K[:n, n:] = keep * (dt * self.jac.T)
+        K[n:, :n] = -dt * self.jac
+        K[n:, n:] = np.eye(m)
+        return K
+
+    def solve(self, iterate):
+        n, m = self.n, self.m
         if self.K is None:
-            keep = np.logical_not(self.active_set).astype(np.float64)[:, None]
-            K = np.zeros((n + m, n + m))
-            K[:n, :n] = np.eye(n) + keep * (dt * self.hess)
-            K[:n, n:] = keep * (dt * self.jac.T)
-            K[n:, :n] = -dt * self.jac
-            K[n:, n:] = np.eye(m)
-            self.K = K
+            self.K = self.matrix()
         rhs = self._func.value_at(iterate, self.rho, self.active_set)
         try:
             if self.solver is None:

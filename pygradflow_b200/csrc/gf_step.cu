@@ -222,7 +222,9 @@ __global__ void kkt_rhs_kernel(int n, int m, int ld, const double* __restrict__ 
 //   GF_FORM_ASYMMETRIC (asymmetric_step_solver.py:77-104): rows of [[H + lamb I, J'], [J, -lamb fact I]] in the
 //       natural order, the row of every active variable overwritten by the unit row (:37-75);
 //   GF_FORM_EXTENDED (extended_step_solver.py:39-83): (selector rows of the active variables, ascending; the
-//       inactive rows of [H + lamb I, J'], ascending; [J, -lamb fact I]).
+//       inactive rows of [H + lamb I, J'], ascending; [J, -lamb fact I]);
+//   GF_FORM_STANDARD (standard_step_solver.py:40-53 + implicit_func.py:163-199): the derivative of the UNSCALED implicit
+//       function, [[I + P_I dt H, P_I dt J'], [-dt J, I]] with H = H_rho handed in by the caller.
 // One warp per row, rows of K written coalesced.
 template <int ROWS>
 __global__ void kkt_full_kernel(int n, int m, int ld, int form, const double* __restrict__ H,
@@ -248,10 +250,16 @@ __global__ void kkt_full_kernel(int n, int m, int ld, int form, const double* __
         const int r = r0 + rr;
         if (r >= N) break;
         double* out = Kb + (size_t)r * ld;
+        const double dtb = dt[b];
         if (r >= n) {
             const double* src = Jb + (size_t)(r - n) * n;
-            for (int c = lane; c < n; c += 32) out[c] = __ldg(src + c);
-            for (int c = n + lane; c < N; c += 32) out[c] = (c == r) ? corner : 0.0;
+            if (form == GF_FORM_STANDARD) {  // [-dt J, I]  (implicit_func.py:185-186)
+                for (int c = lane; c < n; c += 32) out[c] = -__dmul_rn(dtb, __ldg(src + c));
+                for (int c = n + lane; c < N; c += 32) out[c] = (c == r) ? 1.0 : 0.0;
+            } else {
+                for (int c = lane; c < n; c += 32) out[c] = __ldg(src + c);
+                for (int c = n + lane; c < N; c += 32) out[c] = (c == r) ? corner : 0.0;
+            }
             continue;
         }
         int unit = -1, hrow = -1;  // unit row e_unit, or row hrow of [H + lamb I, J']
@@ -264,6 +272,14 @@ __global__ void kkt_full_kernel(int n, int m, int ld, int form, const double* __
         }
         if (unit >= 0) {
             for (int c = lane; c < N; c += 32) out[c] = (c == unit) ? 1.0 : 0.0;
+        } else if (form == GF_FORM_STANDARD) {  // [I + dt H_rho, dt J'] on the inactive rows (implicit_func.py:176-183)
+            const double* src = Hb + (size_t)hrow * n;
+            for (int c = lane; c < n; c += 32) {
+                double v = __dmul_rn(dtb, __ldg(src + c));
+                if (c == hrow) v = __dadd_rn(1.0, v);
+                out[c] = v;
+            }
+            for (int c = lane; c < m; c += 32) out[n + c] = __dmul_rn(dtb, __ldg(Jb + (size_t)c * n + hrow));
         } else {
             const double* src = Hb + (size_t)hrow * n;
             for (int c = lane; c < n; c += 32) {
@@ -292,6 +308,11 @@ __global__ void kkt_full_rhs_kernel(int n, int m, int ld, int form, const int32_
     const int32_t* pb = perm + (size_t)b * n;
     const uint8_t* ab = active + (size_t)b * n;
     double* out = rhs + (size_t)b * ld;
+    if (form == GF_FORM_STANDARD) {  // rhs = F of the unscaled implicit function (standard_step_solver.py:63)
+        for (int r = threadIdx.x; r < n + m; r += blockDim.x) out[r] = Fb[r];
+        for (int c = n + m + threadIdx.x; c < ld; c += blockDim.x) out[c] = 0.0;
+        return;
+    }
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
         if (form == GF_FORM_EXTENDED) out[r] = r < nA ? __dmul_rn(dtb, Fb[pb[nI + r]]) : Fb[pb[r - nA]];
         else out[r] = ab[r] ? __dmul_rn(dtb, Fb[r]) : Fb[r];
@@ -639,7 +660,7 @@ extern "C" int gf_kkt_assemble_full(int B, int n, int m, int ld, int form, const
                                     int nwork, void* stream) {
     if (B <= 0 || n <= 0 || m < 0 || ld < n + m || !H || !perm || !nI || !active || !dt || !rho || !K) return GF_ERR_ARG;
     if (m > 0 && !J) return GF_ERR_ARG;
-    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED) return GF_ERR_UNSUPPORTED;
+    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED && form != GF_FORM_STANDARD) return GF_ERR_UNSUPPORTED;
     if (nwork <= 0) return GF_OK;
     constexpr int ROWS = 16;
     dim3 grid((n + m + ROWS - 1) / ROWS, nwork);
@@ -652,7 +673,7 @@ extern "C" int gf_kkt_rhs_full(int B, int n, int m, int ld, int form, const int3
                                const uint8_t* active, const double* F, const double* dt, const double* rho,
                                double* rhs, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream) {
     if (B <= 0 || n <= 0 || m < 0 || ld < n + m || !perm || !nI || !active || !F || !dt || !rho || !rhs) return GF_ERR_ARG;
-    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED) return GF_ERR_UNSUPPORTED;
+    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED && form != GF_FORM_STANDARD) return GF_ERR_UNSUPPORTED;
     if (nwork <= 0) return GF_OK;
     kkt_full_rhs_kernel<<<nwork, pick_threads(n + m), 0, (cudaStream_t)stream>>>(n, m, ld, form, perm, nI, active, F, dt,
                                                                                  rho, rhs, GfWork{work, nwork_dev});

@@ -35,12 +35,14 @@ class KKTEngine:
                  formulation: StepSolverType = StepSolverType.Symmetric):
         """band: optional (order, half_bandwidth) of the family's KKT ordering (BatchedProblem.kkt_band).
         formulation: Symmetric = the reduced KKT system; Asymmetric / Extended = the full-order unsymmetric systems
-        of asymmetric_step_solver.py / extended_step_solver.py (always pivoted LU, order n + m for every instance)."""
+        of asymmetric_step_solver.py / extended_step_solver.py, Standard = the derivative of the unscaled implicit
+        function (standard_step_solver.py; the caller hands in H_rho and the unscaled residual) -- always pivoted LU,
+        order n + m for every instance."""
         self.B, self.n, self.m = B, n, m
         self.device = device
         N = n + m
         self.form = {StepSolverType.Symmetric: K.FORM_SYMMETRIC, StepSolverType.Asymmetric: K.FORM_ASYMMETRIC,
-                     StepSolverType.Extended: K.FORM_EXTENDED}[formulation]
+                     StepSolverType.Extended: K.FORM_EXTENDED, StepSolverType.Standard: K.FORM_STANDARD}[formulation]
         if self.form != K.FORM_SYMMETRIC:
             if linear not in (LinearSolverType.Auto, LinearSolverType.LU):
                 raise ValueError(f"step_solver_type={formulation.name} has an unsymmetric matrix: LU only")
@@ -69,6 +71,7 @@ class KKTEngine:
             self.perm_id = torch.arange(n, **i32).repeat(B, 1).contiguous()
             self.n_full = torch.full((B,), n, **i32)
             self.N_full = torch.full((B,), N, **i32)
+            self.zero_rho = torch.zeros((B,), **f64)
         # Optional (LDL'): gather K inside the factorisation kernels instead of writing it first (gf_kkt_ldlt_factor).
         # Bit-identical, but the dependent index -> H loads in every tile prologue cost the factorisation 2.9 ms while
         # the saved assembly is 3.3 ms (cfg3): the step gains 1 %, the DMMA kernels lose 10 % -- off by default.
@@ -193,8 +196,10 @@ class KKTEngine:
             # asymmetric_step_solver.py:140-173 / extended_step_solver.py:85-112: the solution is (dx, sy) itself
             K.kkt_rhs_full(self.n, self.m, self.perm, self.nI, self.active, F, dt, rho, self.rhs, self.form, work)
             self.solve(self.rhs, work)
-            K.step_finish(xbase, ybase, self.rhs, self.perm_id, self.n_full, F, dt, rho, lb, ub, xn, yn, dx, dy, diff,
-                          work)
+            # Standard: the solution is (dx, dy) itself (standard_step_solver.py:78-79): rho = 0 makes the dy formula
+            # of gf_step_finish, fact (sy - rho F_y), the identity exactly
+            K.step_finish(xbase, ybase, self.rhs, self.perm_id, self.n_full, F, dt,
+                          self.zero_rho if self.form == K.FORM_STANDARD else rho, lb, ub, xn, yn, dx, dy, diff, work)
             return
         K.kkt_rhs(H, J, self.perm, self.nI, F, dt, rho, self.rhs, work)
         self.solve(self.rhs, work)

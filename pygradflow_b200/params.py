@@ -37,9 +37,10 @@ class LinearSolverType(enum.Enum):
 class StepSolverType(enum.Enum):
     """pygradflow/params.py:50-70: formulation of the Newton step system (step/solver/__init__.py:12-31).  Symmetric
     is the reduced quasi-definite KKT system (LDL' or LU); Asymmetric and Extended are the full-order unsymmetric
-    systems of asymmetric_step_solver.py / extended_step_solver.py (pivoted LU).  Standard (the unscaled implicit
-    function) is restated in the oracle only."""
+    systems of asymmetric_step_solver.py / extended_step_solver.py, Standard the derivative of the unscaled implicit
+    function with H_rho = H + rho J'J (standard_step_solver.py) -- all three through the pivoted LU."""
 
+    Standard = enum.auto()
     Extended = enum.auto()
     Symmetric = enum.auto()
     Asymmetric = enum.auto()

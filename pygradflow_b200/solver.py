@@ -23,7 +23,7 @@ import torch
 from . import kernels as K
 from .engine import KKTEngine
 from .kernels import WorkList
-from .params import ActiveSetType, NewtonType, Params, PenaltyUpdate, StepControlType
+from .params import ActiveSetType, NewtonType, Params, PenaltyUpdate, StepControlType, StepSolverType
 from .problem import BatchedProblem
 
 PHASE_SECOND = 1
@@ -60,6 +60,10 @@ class BatchedSolver:
         B, n, m, dev = p.B, p.n, p.m, p.device
         self.engine = KKTEngine(B, n, m, dev, self.params.linear_solver_type, band=problem.kkt_band(),
                                 formulation=self.params.step_solver_type)
+        # StandardStepSolver works on the unscaled implicit function (its own active-set test, F and F')
+        self._standard = self.params.step_solver_type == StepSolverType.Standard
+        self._scaled = not self._standard
+        self._Hrho = [None, None]
         f64 = dict(dtype=torch.float64, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
 
@@ -98,9 +102,13 @@ class BatchedSolver:
             self.Jbuf = [torch.zeros((B, m, n), **f64) for _ in range(3 if exact else 2)]
         if not p.hess_constant:
             self.Hbuf = [torch.zeros((B, n, n), **f64) for _ in range(2)]
+        if self._standard and m > 0:
+            self._Hrho = [torch.empty((B, n, n), **f64) for _ in range(2)]
         self.newton_step_count = torch.zeros((1,), dtype=torch.int64, device=dev)
         self.globalized = None
         if self.params.newton_type == NewtonType.Globalized:
+            if self._standard:
+                raise ValueError("NewtonType.Globalized is built on the scaled step formulations only")
             from .globalized import GlobalizedStepper
 
             # newton.py:218-304; the line search reads its state back per trial, so this mode runs eagerly
@@ -230,7 +238,7 @@ class BatchedSolver:
         lb, ub = prob.var_lb, prob.var_ub
         tau = self._compute_tau()
         K.residual(x, self._y(self.cur), x, self._y(self.cur), self.dL0, self._cons(self.cur), lb, ub, self.dt,
-                   True, 0, eng.active, self.F, None, run, tau=tau)
+                   self._scaled, 0, eng.active, self.F, None, run, tau=tau)
         xm, ym, gm, cm, om = self.mid
         ls_failed = None
         if self.globalized is not None:
@@ -240,13 +248,29 @@ class BatchedSolver:
             ls_failed = (st == 2) & (eng.info == 0)  # a failed factorisation is a rejected step, not a failed search
             self._H0 = None
         else:
-            self._H0 = prob.lag_hess(x, self._y(self.cur), self.Hbuf[0], run)
+            self._H0 = self._hess(self.cur, J0, 0, run)
             eng.update_active_set(run)
             eng.factor(self._H0, J0, self.dt, self.rho, run)
             eng.step(self._H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
                      ym if m > 0 else None, self.diff1, run)
         self._eval_point(self.mid, self.dLm, 1, self.mid_norm, run)
         return ls_failed
+
+    def _hess(self, pt, J, slot, work):
+        """Hessian block the step solver factorises at `pt`: aug_lag_deriv_xx(rho = 0) = lag_hess(x, y) for the scaled
+        formulations (scaled_step_solver.py:80-83), aug_lag_deriv_xx(rho) = lag_hess(x, y + rho c) + rho J'J for the
+        Standard one (standard_step_solver.py:50-53, iterate.py:103-110)."""
+        prob = self.problem
+        if not self._standard:
+            return prob.lag_hess(pt[0], self._y(pt), self.Hbuf[slot], work)
+        if prob.m == 0:
+            return prob.lag_hess(pt[0], None, self.Hbuf[slot], work)
+        ymod = torch.addcmul(pt[1], self.rho[:, None], pt[3])
+        H = prob.lag_hess(pt[0], ymod, self.Hbuf[slot], work)
+        out = self._Hrho[slot]
+        torch.bmm(J.transpose(1, 2), J, out=out)          # plain batched GEMM (cuBLAS): J'J
+        out.mul_(self.rho[:, None, None]).add_(H)
+        return out
 
     def _compute_tau(self):
         """NewtonController.compute_tau / tau_vals (newton_control.py:40-88) at the current iterate, per instance."""
@@ -305,17 +329,17 @@ class BatchedSolver:
             # Full: active set + derivatives at src (newton.py:83-89); ActiveSet: active set at src,
             # derivatives frozen (newton.py:205-215).  Refactoring with an unchanged active set
             # reproduces the same factor, so it is done unconditionally.
-            K.residual(src[0], self._y(src), x, y, dL_src, self._cons(src), lb, ub, self.dt, True, 0, eng.active,
-                       self.F, None, work, tau=self._tau)
+            K.residual(src[0], self._y(src), x, y, dL_src, self._cons(src), lb, ub, self.dt, self._scaled, 0,
+                       eng.active, self.F, None, work, tau=self._tau)
             if full:
-                Hs = prob.lag_hess(src[0], self._y(src), self.Hbuf[1], work)
+                Hs = self._hess(src, J_src, 1, work)
                 Js = J_src
             eng.update_active_set(work)
             eng.factor(Hs, Js, self.dt, self.rho, work)
             # a failed refactorisation rejects the step like the first one would (step_control.py:102-104)
         else:
-            K.residual(src[0], self._y(src), x, y, dL_src, self._cons(src), lb, ub, self.dt, True, 1, eng.active,
-                       self.F, None, work)
+            K.residual(src[0], self._y(src), x, y, dL_src, self._cons(src), lb, ub, self.dt, self._scaled, 1,
+                       eng.active, self.F, None, work)
         eng.step(Hs, Js, src[0], self._y(src), self.F, self.dt, self.rho, lb, ub, dst[0],
                  dst[1] if m > 0 else None, diff, work)
         return None

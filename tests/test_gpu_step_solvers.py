@@ -1,5 +1,5 @@
-"""The full-order unsymmetric formulations of the Newton step (step/solver/__init__.py:12-31: Asymmetric, Extended)
-as assembly modes of the batched engine: matrices and right-hand sides bit for bit against the oracle's restatement
+"""The full-order unsymmetric formulations of the Newton step (step/solver/__init__.py:12-31: Asymmetric, Extended,
+Standard) as assembly modes of the batched engine: matrices and right-hand sides bit for bit against the oracle's restatement
 of asymmetric_step_solver.py / extended_step_solver.py, whole solves per instance against the oracle and against
 traces of the REAL reference (tests/golden/step_solvers.npz)."""
 
@@ -26,7 +26,7 @@ def _params(kind, newton="Simplified", **kw):
     return Params(step_solver_type=StepSolverType[kind], newton_type=NewtonType[newton], **kw)
 
 
-@pytest.mark.parametrize("kind", ["Asymmetric", "Extended"])
+@pytest.mark.parametrize("kind", ["Asymmetric", "Extended", "Standard"])
 @pytest.mark.parametrize("n,m,B", [(16, 8, 6), (40, 0, 5), (70, 33, 4)])
 def test_full_order_system_bitwise(kind, n, m, B):
     """K and rhs of gf_kkt_assemble_full / gf_kkt_rhs_full == AsymmetricStepSolver / ExtendedStepSolver of the oracle
@@ -60,7 +60,8 @@ def test_full_order_system_bitwise(kind, n, m, B):
     eng.solve(eng.rhs, w)
     sol = eng.rhs.cpu().numpy()
     assert (eng.info.cpu().numpy() == 0).all()
-    cls = {"Asymmetric": orc.AsymmetricStepSolver, "Extended": orc.ExtendedStepSolver}[kind]
+    cls = {"Asymmetric": orc.AsymmetricStepSolver, "Extended": orc.ExtendedStepSolver,
+           "Standard": orc.StandardStepSolver}[kind]
     for b in range(B):
         p = orc.DenseQP(d["H"][b], d["A"][b], d["g"][b], d["b"][b], d["lb"][b], d["ub"][b])
         it = orc.Iterate(p, orc.OracleParams(), d["x0"][b], d["y0"][b])
@@ -69,14 +70,17 @@ def test_full_order_system_bitwise(kind, n, m, B):
         A = active[b]
         lamb = 1.0 / dt[b]
         fact = 1.0 / (1.0 + lamb * rho[b])
-        Kref, rref = s.full_system(dt[b] * F[b, :n][A], F[b, :n][~A], fact * F[b, n:])
+        if kind == "Standard":  # the matrix of the unscaled function on the handed-in H (= H_rho), rhs = F
+            Kref, rref = s.matrix(), F[b]
+        else:
+            Kref, rref = s.full_system(dt[b] * F[b, :n][A], F[b, :n][~A], fact * F[b, n:])
         assert np.array_equal(Kd[b, : n + m, : n + m], Kref), (kind, b)
         assert np.array_equal(rhs_d[b, : n + m], rref), (kind, b)
         assert rel_err(sol[b, : n + m], np.linalg.solve(Kref, rref)) <= 1e-10 * max(1.0, np.linalg.cond(Kref) * 1e-4)
 
 
 @pytest.mark.parametrize("newton", ["Simplified", "Full"])
-@pytest.mark.parametrize("kind", ["Asymmetric", "Extended"])
+@pytest.mark.parametrize("kind", ["Asymmetric", "Extended", "Standard"])
 def test_formulations_qp_vs_oracle(kind, newton):
     from pygradflow_b200.problem import BatchedQP
     from pygradflow_b200.solver import BatchedSolver
@@ -98,7 +102,7 @@ def test_formulations_qp_vs_oracle(kind, newton):
         assert rel_err(res.y[b].cpu().numpy(), ref.y) <= 1e-8
 
 
-@pytest.mark.parametrize("kind", ["Asymmetric", "Extended"])
+@pytest.mark.parametrize("kind", ["Asymmetric", "Extended", "Standard"])
 def test_formulations_golden_reference(golden, kind):
     """Against Solver.solve of the real reference with Params(step_solver_type=...)."""
     from pygradflow_b200.problem import BatchedQP, BatchedRosenbrock
@@ -143,7 +147,7 @@ def test_formulations_agree_with_symmetric_at_cfg3_shape():
     d = synth.qp_batch(range(B), n, m)
     prob = BatchedQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
     ref = BatchedSolver(prob, _params("Symmetric")).solve(d["x0"], d["y0"])
-    for kind in ("Asymmetric", "Extended"):
+    for kind in ("Asymmetric", "Extended", "Standard"):
         res = BatchedSolver(prob, _params(kind)).solve(d["x0"], d["y0"])
         assert torch.equal(res.status, ref.status)
         assert torch.equal(res.iterations, ref.iterations), kind
