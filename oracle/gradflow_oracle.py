@@ -945,6 +945,49 @@ class OracleLUSolver:
         return None
 
 
+class ConditionEstimator:
+    """step/cond_estimate.py:13-114 (Dixon): 1/cond_2 from power iterations on A'A and (A'A)^-1, the latter through
+    solve(trans=True) / solve of the factorised matrix; random start vectors from default_rng(42)."""
+
+    def __init__(self, mat, linear_solver, min_prob=0.99, factor=10.0):
+        self.mat = np.asarray(mat, dtype=np.float64)
+        self.size = self.mat.shape[0]
+        self.linear_solver = linear_solver
+        self.min_prob, self.factor = min_prob, factor
+        self.rng = np.random.default_rng(seed=42)
+
+    def required_its(self):                                            # :41-43
+        f = (1.0 - self.min_prob) / 1.6 * math.pow(self.size, -0.5)
+        return -2 * math.ceil(math.log(f, self.factor))
+
+    def _random_vec(self):                                             # :45-57
+        vec = self.rng.normal(size=self.size)
+        while not (vec != 0.0).any():
+            vec = self.rng.normal(size=self.size)
+        return vec / np.linalg.norm(vec)
+
+    def estimate_rcond(self):                                          # :59-114
+        mat, ls = self.mat, self.linear_solver
+        num_its = self.required_its()
+        x, y = self._random_vec(), self._random_vec()
+        xprod, yprod = np.copy(x), np.copy(y)
+        xfac = yfac = 1.0
+        for _ in range(num_its):
+            xprod = mat.T @ (mat @ xprod)
+            yprod = ls.solve(ls.solve(yprod, trans=True))
+            xnorm, ynorm = float(np.linalg.norm(xprod)), float(np.linalg.norm(yprod))
+            xfac *= xnorm
+            xprod /= xnorm
+            yfac *= ynorm
+            yprod /= ynorm
+        pow_fac = 1.0 / (2.0 * num_its)
+        xdot = math.pow(x.dot(xprod) * xfac, pow_fac)
+        ydot = math.pow(y.dot(yprod) * yfac, pow_fac)
+        if np.isinf(xdot) or np.isinf(ydot) or np.isinf(xdot * ydot):
+            return 0.0
+        return 1.0 / (xdot * ydot)
+
+
 # --------------------------------------------------------------------------
 # Step result / step solver (pygradflow/step/solver/*.py)
 # --------------------------------------------------------------------------

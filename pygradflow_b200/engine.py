@@ -186,6 +186,65 @@ class KKTEngine:
         K.ldlt_solve(self.K, Nmax, self.Nvec, rhs, self._ok)  # symmetric: trans is irrelevant
         K.lu_solve(self.K, Nmax, self.Nvec, self.piv, rhs, trans, self._fb)
 
+    def estimate_rcond(self, H, J, dt, rho, work: Optional[WorkList] = None) -> torch.Tensor:
+        """``StepSolver.estimate_rcond`` (step_solver.py:100-113) = Dixon's estimator (step/cond_estimate.py:13-114) for
+        every instance of the batch, on the CURRENT factorisation: power iterations on A'A (two batched matrix-vector
+        products with a re-assembled copy of the matrix) and on its inverse (``solve(trans=True)`` then ``solve``),
+        start vectors from ``default_rng(42)`` exactly as the reference draws them.  A diagnostic (``report_rcond``):
+        it keeps a second matrix buffer and reads the orders back to the host."""
+        if self.linear == LinearSolverType.Banded:
+            raise NotImplementedError("report_rcond is not available with the banded factorisation")
+        import numpy as np
+
+        B, ld, dev = self.B, self.ld, self.device
+        work = work if work is not None else WorkList.all(B)
+        f64 = dict(dtype=torch.float64, device=dev)
+        if getattr(self, "Kmat", None) is None:
+            self.Kmat = torch.zeros((B, ld, ld), **f64)
+        else:
+            self.Kmat.zero_()
+        if self.form != K.FORM_SYMMETRIC:
+            K.kkt_assemble_full(H, J, self.perm, self.nI, self.active, dt, rho, self.Kmat, self.form, work)
+        else:
+            K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.Kmat, 1, False, work)
+        Nb = self._order().to(torch.int64)                                  # [B]
+        Nh = Nb.cpu().numpy().astype(np.float64)
+        Nmax = int(Nh.max()) if B > 0 else 0
+        col = torch.arange(ld, device=dev)[None, :]
+        valid = col < Nb[:, None]
+        z = torch.as_tensor(np.random.default_rng(seed=42).normal(size=2 * max(Nmax, 1)), **f64)
+        zero = torch.zeros((), **f64)
+        x = torch.where(valid, z[col.clamp(max=z.numel() - 1)].expand(B, ld), zero)
+        y = torch.where(valid, z[(col + Nb[:, None]).clamp(max=z.numel() - 1)], zero)
+        x = x / torch.linalg.vector_norm(x, dim=1, keepdim=True).clamp_min(1e-300)
+        y = y / torch.linalg.vector_norm(y, dim=1, keepdim=True).clamp_min(1e-300)
+        with np.errstate(divide="ignore"):
+            its_h = -2 * np.ceil(np.log((1.0 - 0.99) / 1.6 * np.power(np.maximum(Nh, 1.0), -0.5)) / np.log(10.0))
+        its = torch.as_tensor(its_h, **f64)
+        xprod, yprod = x.clone(), y.clone()
+        xfac, yfac = torch.ones((B,), **f64), torch.ones((B,), **f64)
+        Kt = self.Kmat.transpose(1, 2)
+        for k in range(int(its_h.max()) if B > 0 else 0):
+            live = (its > k)[:, None]
+            xn = torch.bmm(Kt, torch.bmm(self.Kmat, xprod.unsqueeze(2))).squeeze(2)
+            xn = torch.where(valid, xn, zero)
+            buf = yprod.clone()
+            self.solve(buf, work, trans=True)
+            self.solve(buf, work, trans=False)
+            yn = torch.where(valid, buf, zero)
+            xnorm = torch.linalg.vector_norm(xn, dim=1)
+            ynorm = torch.linalg.vector_norm(yn, dim=1)
+            xfac = torch.where(live[:, 0], xfac * xnorm, xfac)
+            yfac = torch.where(live[:, 0], yfac * ynorm, yfac)
+            xprod = torch.where(live, xn / xnorm[:, None], xprod)
+            yprod = torch.where(live, yn / ynorm[:, None], yprod)
+        pw = 1.0 / (2.0 * its.clamp_min(1.0))
+        xdot = torch.pow((x * xprod).sum(dim=1) * xfac, pw)
+        ydot = torch.pow((y * yprod).sum(dim=1) * yfac, pw)
+        cond = xdot * ydot
+        rc = torch.where(torch.isinf(xdot) | torch.isinf(ydot) | torch.isinf(cond), torch.zeros_like(cond), 1.0 / cond)
+        return rc
+
     def _order(self):
         """Per-instance order of the system handed to the LU: |I| + m (reduced) or n + m (full-order formulations)."""
         return self.Nvec if self.form == K.FORM_SYMMETRIC else self.N_full

@@ -39,6 +39,7 @@ class BatchedResult:
     lamb: torch.Tensor
     rho: torch.Tensor
     total_res: torch.Tensor
+    rcond: Optional[torch.Tensor]   # report_rcond: Dixon estimate of the last KKT matrix each instance factorised
     outer_iterations: int       # lock-step iterations executed by the batch
     newton_steps: int           # instance-level Newton-KKT steps executed (sum over instances)
 
@@ -105,6 +106,10 @@ class BatchedSolver:
         if self._standard and m > 0:
             self._Hrho = [torch.empty((B, n, n), **f64) for _ in range(2)]
         self.newton_step_count = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.rcond = None
+        if self.params.report_rcond:  # reads sizes back to the host: no graph replay in this mode
+            self.rcond = torch.full((B,), float("nan"), **f64)
+            self.use_graph = False
         self.globalized = None
         if self.params.newton_type == NewtonType.Globalized:
             if self._standard:
@@ -189,7 +194,8 @@ class BatchedSolver:
         return BatchedResult(
             x=x.clone(), y=y.clone(), status=self.status.clone(), iterations=self.iters.clone(),
             accepted_steps=self.accepted.clone(), lamb=self.lamb.clone(), rho=self.rho.clone(),
-            total_res=self.total_res.clone(), outer_iterations=int(self.iters.max().item()),
+            total_res=self.total_res.clone(), rcond=None if self.rcond is None else self.rcond.clone(),
+            outer_iterations=int(self.iters.max().item()),
             newton_steps=int(self.newton_step_count.item()),
         )
 
@@ -251,6 +257,9 @@ class BatchedSolver:
             self._H0 = self._hess(self.cur, J0, 0, run)
             eng.update_active_set(run)
             eng.factor(self._H0, J0, self.dt, self.rho, run)
+            if self.rcond is not None:  # step_solver.py:100-113, every time a step solver factorises (diagnostic)
+                est = eng.estimate_rcond(self._H0, J0, self.dt, self.rho, run)
+                self.rcond.copy_(torch.where((self.status == 0) & (eng.info == 0), est, self.rcond))
             eng.step(self._H0, J0, x, self._y(self.cur), self.F, self.dt, self.rho, lb, ub, xm,
                      ym if m > 0 else None, self.diff1, run)
         self._eval_point(self.mid, self.dLm, 1, self.mid_norm, run)

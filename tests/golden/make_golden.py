@@ -493,6 +493,25 @@ def golden_penalty():
     np.savez_compressed(os.path.join(HERE, "penalty.npz"), **out)
 
 
+def golden_rcond():
+    """ConditionEstimator (step/cond_estimate.py) on the reference's LUSolver: the 5x5 fixtures of
+    tests/pygradflow/test_linear_solver.py and cfg5-style KKT matrices."""
+    from pygradflow.linear_solver.lu_solver import LUSolver
+    from pygradflow.step.cond_estimate import ConditionEstimator
+
+    g = np.load(os.path.join(HERE, "linear_solver.npz"))
+    out = {}
+    mats = {name: g[f"{name}/mat"] for name in ("indef", "posdef", "negdef")}
+    for N in (12, 48, 96, 200):
+        mats[f"kkt{N}"] = synth.kkt_instance(N)[0]
+    for name, mat in mats.items():
+        sm = sps.csc_matrix(mat)
+        est = ConditionEstimator(sm, LUSolver(sm), Params())
+        out[f"{name}/rcond"] = np.float64(est.estimate_rcond())
+        out[f"{name}/its"] = np.int32(est._required_its())
+    np.savez_compressed(os.path.join(HERE, "rcond.npz"), **out)
+
+
 def golden_ocp():
     """cfg4-style discretised optimal-control problems (small): full traces of the real reference."""
     out = {}
@@ -517,6 +536,7 @@ if __name__ == "__main__":
     golden_step_solvers()
     golden_scaling()
     golden_penalty()
+    golden_rcond()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -426,3 +426,13 @@ def test_func_zero_at_origin():
     p = orc.HS71()
     it = orc.Iterate(p, orc.OracleParams(), np.array([1.0, 5.0, 5.0, 1.0, 0.0]), np.zeros(2))
     assert np.allclose(orc.ImplicitFunc(p, it, 1e-12).value_at(it, 1.0), 0.0, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["indef", "posdef", "negdef", "kkt12", "kkt48", "kkt96", "kkt200"])
+def test_condition_estimator(golden, name):
+    """step/cond_estimate.py:13-114 (Dixon) on the reference's LUSolver: same estimate, to the last bits."""
+    g, ls = golden("rcond"), golden("linear_solver")
+    mat = ls[f"{name}/mat"] if not name.startswith("kkt") else synth.kkt_instance(int(name[3:]))[0]
+    est = orc.ConditionEstimator(mat, orc.OracleLUSolver(mat))
+    assert est.required_its() == int(g[f"{name}/its"])
+    assert abs(est.estimate_rcond() - float(g[f"{name}/rcond"])) <= 1e-13 * float(g[f"{name}/rcond"])
