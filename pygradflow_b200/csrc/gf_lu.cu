@@ -65,6 +65,22 @@ __device__ __forceinline__ void record_pivot(double absmax, int col, int32_t* in
     }
 }
 
+// Warp arg-max of |value| for the pivot search, on the integer pipe: a non-negative double orders like its bit
+// pattern, so the maximum is found with three redux.sync (high word, low word among the high-word winners, smallest
+// position among the value winners) instead of five dependent rounds of 64-bit shuffles and FP64 compares -- the
+// search sits on the critical path of every pivot column.  v < 0 (with idx == none) marks an excluded lane; ties go
+// to the smaller position; all lanes excluded -> bv = -1, bi = none.
+__device__ __forceinline__ void warp_pivot_search(double v, int idx, int none, double& bv, int& bi) {
+    const unsigned long long key = idx == none ? 0ull : (unsigned long long)__double_as_longlong(v) + 1ull;
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool ismax = hi == mhi && lo == mlo;
+    bi = (int)__reduce_min_sync(0xffffffffu, ismax ? (unsigned)idx : (unsigned)none);
+    const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+    bv = mk == 0ull ? -1.0 : __longlong_as_double((long long)(mk - 1ull));
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void lu_smem_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, double* __restrict__ K,
                                int32_t* __restrict__ piv, int32_t* __restrict__ info, GfWork work) {
@@ -189,17 +205,21 @@ __global__ void __launch_bounds__(256) lu_warp_kernel(int ld, const int32_t* __r
     if (lane == 0) info[b] = sinfo;
 }
 
-// 32 < N <= 64: one CTA of two warps per matrix, thread t owns row t in a rotating register file (the current column
-// is always a[0], as in lu_warp_kernel), but the pivot row travels through shared memory (one staged candidate row per
-// warp, one block barrier per column) instead of N shuffles per column.  Factor layout as everywhere: the
-// interchanges of the second 32-column block are not applied to the first one (pos32).
+// 32 < N <= 64: one CTA of two warps per matrix, thread t owns row t in registers, the pivot row travels through
+// shared memory (one staged candidate row per warp, one block barrier per column) instead of N shuffles per column.
+// Columns are processed in groups of eight with static register indices; after a group the register file is shifted
+// down by eight, so the code stays a compact loop (a full unroll is 64 x the column body) at 14 register moves per
+// column.  Factor layout as everywhere: the interchanges of the second 32-column block are not applied to the first
+// one (pos32).
 template <int NMAX, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) lu_rows_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                              double* __restrict__ K, int32_t* __restrict__ piv,
                                                              int32_t* __restrict__ info, GfWork work, int nwork) {
     constexpr int T = WARPS * 32;
     constexpr int NONE = 1 << 20;
-    extern __shared__ double rsm[];
+    constexpr int G = 8;
+    static_assert(NMAX % G == 0, "group size");
+    extern __shared__ __align__(16) double rsm[];
     double* stage = rsm;                       // NMAX x T
     double* wrow = rsm + NMAX * T;             // 2 x WARPS x NMAX
     __shared__ double wval[2][WARPS];
@@ -219,56 +239,71 @@ __global__ void __launch_bounds__(WARPS * 32) lu_rows_kernel(int ld, const int32
         int pos = t, pos32 = t;
         int32_t sinfo = 0;
 #pragma unroll 1
-        for (int j = 0; j < N; j++) {
-            if (j == 32) pos32 = pos;
-            double v = fabs(a[0]);
-            int idx = pos;
-            if (!(row && pos >= j && v >= 0.0)) { v = -1.0; idx = NONE; }
-            double bv = v;
-            int bi = idx;
+        for (int j0 = 0; j0 < N; j0 += G) {
+            if (j0 == 32) pos32 = pos;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            const int buf = j & 1;
-            if (bi == NONE) {
-                if (lane == 0) { wval[buf][wid] = -1.0; wpos[buf][wid] = NONE; }
-            } else if (idx == bi) {
-                wval[buf][wid] = bv;
-                wpos[buf][wid] = bi;
-                double* wr = wrow + (size_t)(buf * WARPS + wid) * NMAX;
+            for (int jj = 0; jj < G; jj++) {
+                const int j = j0 + jj;
+                if (j < N) {  // uniform
+                    double v = fabs(a[jj]);
+                    int idx = pos;
+                    if (!(row && pos >= j && v >= 0.0)) { v = -1.0; idx = NONE; }
+                    double bv;
+                    int bi;
+                    warp_pivot_search(v, idx, NONE, bv, bi);
+                    const int buf = jj & 1;
+                    double2* wr = reinterpret_cast<double2*>(wrow + (size_t)(buf * WARPS + wid) * NMAX);
+                    if (bi == NONE) {
+                        if (lane == 0) { wval[buf][wid] = -1.0; wpos[buf][wid] = NONE; }
+                    } else if (idx == bi) {  // positions are unique: exactly one lane stages its row
+                        wval[buf][wid] = bv;
+                        wpos[buf][wid] = bi;
 #pragma unroll
-                for (int c = 0; c < NMAX; c++) wr[c] = a[c];
-            }
-            __syncthreads();
-            bv = wval[buf][0];
-            bi = wpos[buf][0];
-            int bw = 0;
+                        for (int c = 0; c < NMAX; c += 2) wr[c / 2] = make_double2(a[c], a[c + 1]);
+                    }
+                    __syncthreads();
+                    bv = wval[buf][0];
+                    bi = wpos[buf][0];
+                    int bw = 0;
 #pragma unroll
-            for (int w2 = 1; w2 < WARPS; w2++) {
-                const double ov = wval[buf][w2];
-                const int oi = wpos[buf][w2];
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bw = w2; }
-            }
-            const int p = bi < NONE ? bi : j;
-            record_pivot(bv, j, &sinfo);
-            if (t == 0) pb[j] = p;
-            if (pos == p) pos = j;
-            else if (pos == j) pos = p;
-            const double* pr = wrow + (size_t)(buf * WARPS + bw) * NMAX;
-            const double pv = bi < NONE ? pr[0] : 0.0;
-            const bool below = row && pos > j && pv != 0.0;
-            double l = 0.0;
-            if (below) {
-                l = a[0] / pv;
-                a[0] = l;
-            }
-            stage[j * T + t] = a[0];  // final: L entry below the pivot, U entry on and above it
+                    for (int w2 = 1; w2 < WARPS; w2++) {
+                        const double ov = wval[buf][w2];
+                        const int oi = wpos[buf][w2];
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bw = w2; }
+                    }
+                    const int p = bi < NONE ? bi : j;
+                    record_pivot(bv, j, &sinfo);
+                    if (t == 0) pb[j] = p;
+                    if (pos == p) pos = j;
+                    else if (pos == j) pos = p;
+                    const double2* pr = reinterpret_cast<const double2*>(wrow + (size_t)(buf * WARPS + bw) * NMAX);
+                    const double pv = bi < NONE ? reinterpret_cast<const double*>(pr)[jj] : 0.0;
+                    const bool below = row && pos > j && pv != 0.0;
+                    if (below) {
+                        const double l = a[jj] / pv;
+                        a[jj] = l;
+                        // the pivot row in 16-byte loads, eight entries at a time (entries <= jj are dropped)
 #pragma unroll
-            for (int c = 1; c < NMAX; c++) a[c - 1] = below ? fma(-l, pr[c], a[c]) : a[c];
-            a[NMAX - 1] = 0.0;
+                        for (int c8 = 0; c8 < NMAX; c8 += 8) {
+                            double q[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const double2 v2 = pr[(c8 + e) / 2];
+                                q[e] = v2.x;
+                                q[e + 1] = v2.y;
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; e++)
+                                if (c8 + e > jj) a[c8 + e] = fma(-l, q[e], a[c8 + e]);
+                        }
+                    }
+                    stage[j * T + t] = a[jj];  // final: L entry below the pivot, U entry on and above it
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NMAX - G; c++) a[c] = a[c + G];
+#pragma unroll
+            for (int c = NMAX - G; c < NMAX; c++) a[c] = 0.0;
         }
         if (N <= 32) pos32 = pos;
         if (row) {
@@ -488,14 +523,9 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
                     const bool ok = t + r * T < rows && pos[r] >= jj && vr >= 0.0;  // excluded rows, NaN entries
                     if (ok && (vr > v || (vr == v && pos[r] < idx))) { v = vr; idx = pos[r]; rs = r; }
                 }
-                double bv = v;
-                int bi = idx;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                }
+                double bv;
+                int bi;
+                warp_pivot_search(v, idx, NONE, bv, bi);
                 const int buf = jj & 1;
                 if (bi == NONE) {
                     if (lane == 0) { wval[buf][wid] = -1.0; wpos[buf][wid] = NONE; }
@@ -512,16 +542,10 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
                     }
                 }
                 __syncthreads();
-                bv = lane < nw ? wval[buf][lane] : -1.0;
-                bi = lane < nw ? wpos[buf][lane] : NONE;
-                int bw = lane;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bw = ow; }
-                }
+                const double cv = lane < nw ? wval[buf][lane] : -1.0;
+                const int ci = lane < nw ? wpos[buf][lane] : NONE;
+                warp_pivot_search(cv, ci, NONE, bv, bi);
+                const int bw = bi < NONE ? __ffs(__ballot_sync(0xffffffffu, ci == bi)) - 1 : 0;  // the warp that staged it
                 const int p = bi < NONE ? bi : jj;
                 record_pivot(bv, j0 + jj, &sinfo);
                 if (t == 0) spiv[jj] = p;
