@@ -171,12 +171,7 @@ __global__ void __launch_bounds__(256) lu_warp_kernel(int ld, const int32_t* __r
         double v = fabs(a[0]);
         int idx = pos;
         if (!(row && pos >= j && v >= 0.0)) { v = -1.0; idx = NONE; }  // excluded rows and NaN entries
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
+        warp_pivot_search(v, idx, NONE, v, idx);
         const int p = idx < NONE ? idx : j;
         record_pivot(v, j, &sinfo);
         const int lp = __ffs(__ballot_sync(0xffffffffu, pos == p)) - 1;  // lane that holds the pivot row
