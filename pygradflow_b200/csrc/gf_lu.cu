@@ -640,6 +640,77 @@ __device__ __forceinline__ double lu_col_dot(const double* __restrict__ col, int
     return acc;
 }
 
+// N <= 32: substitution with one WARP per system, eight systems per CTA, the factor resident in registers: lane r
+// holds storage row r (trans = 0: the dots of U' w = r and L' v = w become column sweeps, one broadcast per unknown)
+// or storage column r (trans = 1: L z = P r, U x = z), the right-hand side one entry per lane, the interchanges by
+// shuffles.  Same operations as lu_solve_kernel in a different summation order.
+__global__ void __launch_bounds__(256) lu_solve_warp_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                            const double* __restrict__ K,
+                                                            const int32_t* __restrict__ piv, double* __restrict__ rhs,
+                                                            int ldr, int trans, GfWork work, int nwork) {
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 8 + wid;
+    if (slot >= nwork) return;
+    const int b = gf_instance(work, slot);
+    if (b < 0) return;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    if (N <= 0) return;
+    const double* Kb = K + (size_t)b * ld * ld;
+    double* rb = rhs + (size_t)b * ldr;
+    const bool in = lane < N;
+    double k[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+        // trans = 0: k[c] = K[lane][c] (storage row);  trans = 1: k[c] = K[c][lane] (storage column)
+        const size_t o = trans ? (size_t)c * ld + lane : (size_t)lane * ld + c;
+        k[c] = (in && c < N) ? __ldg(Kb + o) : (c == lane ? 1.0 : 0.0);
+    }
+    double s = in ? rb[lane] : 0.0;
+    const int pj = in ? piv[(size_t)b * ld + lane] : lane;
+    if (trans) {  // z = P r
+        for (int j = 0; j < N; j++) {
+            const int p = __shfl_sync(0xffffffffu, pj, j);
+            const double sj = __shfl_sync(0xffffffffu, s, j), sp = __shfl_sync(0xffffffffu, s, p);
+            if (lane == j) s = sp;
+            else if (lane == p) s = sj;
+        }
+    }
+    // forward sweep: unknown i is final once the sweeps 0..i-1 are applied; lane r > i subtracts its (r, i) entry
+    // trans = 0: U' w = r, (r, i) = K[r][i], diagonal K[i][i];  trans = 1: L z = P r, (r, i) = L(r, i) = K[i][r], unit
+    double dg = 1.0;
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+        if (c == lane) dg = k[c];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        if (i < N) {
+            double w = trans ? s : s / dg;
+            w = __shfl_sync(0xffffffffu, w, i);
+            if (lane == i) s = w;
+            else if (lane > i) s -= k[i] * w;
+        }
+    }
+    // backward sweep: trans = 0: L' v = w (unit), (r, i) = K[r][i], i > r;  trans = 1: U x = z, (r, i) = K[i][r], diag
+#pragma unroll
+    for (int i = 31; i >= 0; i--) {
+        if (i < N) {
+            double w = trans ? s / dg : s;
+            w = __shfl_sync(0xffffffffu, w, i);
+            if (lane == i) s = w;
+            else if (lane < i) s -= k[i] * w;
+        }
+    }
+    if (!trans) {  // x = P' v: the interchanges in reverse
+        for (int j = N - 1; j >= 0; j--) {
+            const int p = __shfl_sync(0xffffffffu, pj, j);
+            const double sj = __shfl_sync(0xffffffffu, s, j), sp = __shfl_sync(0xffffffffu, s, p);
+            if (lane == j) s = sp;
+            else if (lane == p) s = sj;
+        }
+    }
+    if (in) rb[lane] = s;
+}
+
 // The interchanges of one 32-column block applied to the vector (warp 0; v in shared memory): forward order for
 // L z = P r, reverse order for x = P' v.
 __device__ __forceinline__ void lu_block_swaps(double* v, const int32_t* pb, int j0, int jb, int lane, bool reverse) {
@@ -979,6 +1050,11 @@ extern "C" int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const d
                            void* stream) {
     if (B <= 0 || ld <= 0 || Nmax < 0 || Nmax > ld || ldr < Nmax || !K || !piv || !rhs) return GF_ERR_ARG;
     if (nwork <= 0 || Nmax == 0) return GF_OK;
+    if (Nmax <= 32) {
+        lu_solve_warp_kernel<<<(nwork + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,
+                                                                               GfWork{work, nwork_dev}, nwork);
+        return gf_launch_status();
+    }
     const size_t smem = (size_t)(Nmax + 1) * sizeof(double) + (size_t)Nmax * sizeof(int32_t);
     if (smem > 200 * 1024) return GF_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
