@@ -711,6 +711,132 @@ __global__ void __launch_bounds__(256) lu_solve_warp_kernel(int ld, const int32_
     if (in) rb[lane] = s;
 }
 
+// 32 < N <= 64: the same idea with two warps per system (thread t holds storage row / column t, 64 doubles): each
+// 32-block is swept inside its warp by shuffles, the other block's 32 unknowns arrive through shared memory -- three
+// block barriers per substitution instead of one dependent round trip to HBM per block step.  Interchanges block by
+// block (factor layout, see the file header): inside warp 1 by shuffles, across the warps in shared memory.
+template <bool DIV>
+__device__ __forceinline__ void lu_sweep32(double& s, const double* kk, double dg, int lane, int nb, bool up) {
+    // kk[0..31]: this thread's coefficients against the 32 unknowns of its own block
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        const int i = up ? 31 - q : q;
+        if (i < nb) {
+            double w = DIV ? s / dg : s;
+            w = __shfl_sync(0xffffffffu, w, i);
+            if (lane == i) s = w;
+            else if (up ? lane < i : lane > i) s -= kk[i] * w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) lu_solve_rows_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                           const double* __restrict__ K,
+                                                           const int32_t* __restrict__ piv, double* __restrict__ rhs,
+                                                           int ldr, int trans, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+    if (N <= 0) return;
+    __shared__ double vs[64];
+    __shared__ int ps[64];
+    const int t = threadIdx.x, lane = t & 31, h = t >> 5;
+    const double* Kb = K + (size_t)b * ld * ld;
+    double* rb = rhs + (size_t)b * ldr;
+    const bool in = t < N;
+    double k[64];
+#pragma unroll
+    for (int c = 0; c < 64; c++) {
+        const size_t o = trans ? (size_t)c * ld + t : (size_t)t * ld + c;
+        k[c] = (in && c < N) ? __ldg(Kb + o) : (c == t ? 1.0 : 0.0);
+    }
+    double dg = 1.0;
+#pragma unroll
+    for (int c = 0; c < 64; c++)
+        if (c == t) dg = k[c];
+    vs[t] = in ? rb[t] : 0.0;
+    ps[t] = in ? piv[(size_t)b * ld + t] : t;
+    const int n0 = min(N, 32), n1 = max(N - 32, 0);  // unknowns in block 0 / block 1
+    __syncthreads();
+    double s;
+    if (!trans) {
+        // ---- U' w = r, forward
+        s = vs[t];
+        if (h == 0) {
+            lu_sweep32<true>(s, k, dg, lane, n0, false);
+            vs[t] = s;
+        }
+        __syncthreads();
+        if (h == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) s -= k[i] * vs[i];
+            lu_sweep32<true>(s, k + 32, dg, lane, n1, false);
+            // ---- L' v = w, backward: block 1, then its interchanges in reverse (all inside this warp)
+            lu_sweep32<false>(s, k + 32, 1.0, lane, n1, true);
+            for (int jj = n1 - 1; jj >= 0; jj--) {
+                const int p = ps[32 + jj] - 32;
+                const double sj = __shfl_sync(0xffffffffu, s, jj), sp = __shfl_sync(0xffffffffu, s, p);
+                if (lane == jj) s = sp;
+                else if (lane == p) s = sj;
+            }
+            vs[t] = s;
+        }
+        __syncthreads();
+        if (h == 0) {
+#pragma unroll
+            for (int i = 32; i < 64; i++) s -= k[i] * vs[i];
+            lu_sweep32<false>(s, k, 1.0, lane, n0, true);
+            vs[t] = s;
+            __syncwarp();
+            if (lane == 0) {  // block 0's interchanges in reverse: they reach into block 1
+                for (int jj = n0 - 1; jj >= 0; jj--) {
+                    const int p = ps[jj];
+                    if (p != jj) { const double tmp = vs[jj]; vs[jj] = vs[p]; vs[p] = tmp; }
+                }
+            }
+        }
+        __syncthreads();
+        s = vs[t];
+    } else {
+        // ---- z = P r block by block, L z = P r forward
+        if (t == 0) {
+            for (int jj = 0; jj < n0; jj++) {
+                const int p = ps[jj];
+                if (p != jj) { const double tmp = vs[jj]; vs[jj] = vs[p]; vs[p] = tmp; }
+            }
+        }
+        __syncthreads();
+        s = vs[t];
+        __syncthreads();
+        if (h == 0) {
+            lu_sweep32<false>(s, k, 1.0, lane, n0, false);
+            vs[t] = s;
+        }
+        __syncthreads();
+        if (h == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) s -= k[i] * vs[i];
+            for (int jj = 0; jj < n1; jj++) {  // block 1's interchanges (inside this warp)
+                const int p = ps[32 + jj] - 32;
+                const double sj = __shfl_sync(0xffffffffu, s, jj), sp = __shfl_sync(0xffffffffu, s, p);
+                if (lane == jj) s = sp;
+                else if (lane == p) s = sj;
+            }
+            lu_sweep32<false>(s, k + 32, 1.0, lane, n1, false);
+            // ---- U x = z, backward
+            lu_sweep32<true>(s, k + 32, dg, lane, n1, true);
+            vs[t] = s;
+        }
+        __syncthreads();
+        if (h == 0) {
+#pragma unroll
+            for (int i = 32; i < 64; i++) s -= k[i] * vs[i];
+            lu_sweep32<true>(s, k, dg, lane, n0, true);
+        }
+    }
+    if (in) rb[t] = s;
+}
+
 // The interchanges of one 32-column block applied to the vector (warp 0; v in shared memory): forward order for
 // L z = P r, reverse order for x = P' v.
 __device__ __forceinline__ void lu_block_swaps(double* v, const int32_t* pb, int j0, int jb, int lane, bool reverse) {
@@ -1053,6 +1179,11 @@ extern "C" int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const d
     if (Nmax <= 32) {
         lu_solve_warp_kernel<<<(nwork + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,
                                                                                GfWork{work, nwork_dev}, nwork);
+        return gf_launch_status();
+    }
+    if (Nmax <= 64) {
+        lu_solve_rows_kernel<<<nwork, 64, 0, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,
+                                                                    GfWork{work, nwork_dev});
         return gf_launch_status();
     }
     const size_t smem = (size_t)(Nmax + 1) * sizeof(double) + (size_t)Nmax * sizeof(int32_t);
