@@ -698,10 +698,11 @@ __global__ void __launch_bounds__(256) lu_solve_warp_kernel(int ld, const int32_
 #pragma unroll
     for (int c = 0; c < 32; c++)
         if (c == lane) dg = k[c];
+    dg = 1.0 / dg;  // the sweeps multiply by the reciprocal: no division on the serial chain
 #pragma unroll
     for (int i = 0; i < 32; i++) {
         if (i < N) {
-            double w = trans ? s : s / dg;
+            double w = trans ? s : s * dg;
             w = __shfl_sync(0xffffffffu, w, i);
             if (lane == i) s = w;
             else if (lane > i) s -= k[i] * w;
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(256) lu_solve_warp_kernel(int ld, const int32_
 #pragma unroll
     for (int i = 31; i >= 0; i--) {
         if (i < N) {
-            double w = trans ? s / dg : s;
+            double w = trans ? s * dg : s;
             w = __shfl_sync(0xffffffffu, w, i);
             if (lane == i) s = w;
             else if (lane < i) s -= k[i] * w;
@@ -739,7 +740,7 @@ __device__ __forceinline__ void lu_sweep32(double& s, const double* kk, double d
     for (int q = 0; q < 32; q++) {
         const int i = up ? 31 - q : q;
         if (i < nb) {
-            double w = DIV ? s / dg : s;
+            double w = DIV ? s * dg : s;  // dg = reciprocal of the diagonal entry, formed once outside the chain
             w = __shfl_sync(0xffffffffu, w, i);
             if (lane == i) s = w;
             else if (up ? lane < i : lane > i) s -= kk[i] * w;
@@ -771,6 +772,7 @@ __global__ void __launch_bounds__(64) lu_solve_rows_kernel(int ld, const int32_t
 #pragma unroll
     for (int c = 0; c < 64; c++)
         if (c == t) dg = k[c];
+    dg = 1.0 / dg;  // the sweeps multiply: a division per unknown would sit on the serial chain (~370 cycles each)
     vs[t] = in ? rb[t] : 0.0;
     ps[t] = in ? piv[(size_t)b * ld + t] : t;
     const int n0 = min(N, 32), n1 = max(N - 32, 0);  // unknowns in block 0 / block 1
