@@ -912,8 +912,9 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             __syncthreads();
             if (wid == 0) {
                 double s = (lane < jb) ? v[j0 + lane] - part[lane] : 0.0;
+                const double rd = lane < jb ? 1.0 / Tb[lane][lane] : 0.0;  // one division per lane, off the chain
                 for (int ii = 0; ii < jb; ii++) {
-                    double w = s / Tb[ii][ii];
+                    double w = s * rd;
                     w = __shfl_sync(0xffffffffu, w, ii);
                     if (lane == ii) s = w;
                     else if (lane > ii && lane < jb) s -= Tb[lane][ii] * w;
@@ -987,8 +988,9 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             __syncthreads();
             if (wid == 0) {
                 double s = (lane < jb) ? v[j0 + lane] : 0.0;
+                const double rd = lane < jb ? 1.0 / Tb[lane][lane] : 0.0;
                 for (int jj = jb - 1; jj >= 0; jj--) {
-                    double xj = s / Tb[jj][jj];
+                    double xj = s * rd;
                     xj = __shfl_sync(0xffffffffu, xj, jj);
                     if (lane == jj) s = xj;
                     else if (lane < jj) s -= Tb[jj][lane] * xj;
