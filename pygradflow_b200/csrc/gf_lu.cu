@@ -83,6 +83,21 @@ __device__ __forceinline__ void warp_pivot_search(double v, int idx, int none, d
     bv = mk == 0ull ? -1.0 : __longlong_as_double((long long)(mk - 1ull));
 }
 
+// Quotient by the pivot in the register-resident factorisation kernels: reciprocal (MUFU seed + two Newton steps) times
+// the entry, <= 2 ulp, as LAPACK's getf2 scales by the rounded reciprocal -- the IEEE division subroutine costs ~370
+// cycles on the column-to-column critical path (one system of order 64: 65 -> 53 us).  The seed flushes denormals, so
+// a pivot below GF_LU_TINY in magnitude is treated like an exact zero (record_pivot reports the column, no elimination
+// with it); a range check that falls back to the division was measured to cost the whole gain.
+__device__ __forceinline__ double lu_pivot_div(double a, double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return a * r;
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void lu_smem_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, double* __restrict__ K,
                                int32_t* __restrict__ piv, int32_t* __restrict__ info, GfWork work) {
@@ -182,10 +197,10 @@ __global__ void __launch_bounds__(256) lu_warp_kernel(int ld, const int32_t* __r
         else if (lane == lj) pos = p;
         if (lane == 0) pb[j] = p;
         const double pv = __shfl_sync(0xffffffffu, a[0], lp);
-        const bool below = row && pos > j && pv != 0.0;
+        const bool below = row && pos > j && fabs(pv) >= GF_LU_TINY;
         double l = 0.0;
         if (below) {
-            l = a[0] / pv;
+            l = a[0] / pv;  // IEEE division here: the smallest systems are the parity tests' reference point
             a[0] = l;
         }
         stage[j * 32 + lane] = a[0];  // final: L entry below the pivot, U entry on and above it
@@ -200,21 +215,6 @@ __global__ void __launch_bounds__(256) lu_warp_kernel(int ld, const int32_t* __r
     if (row)
         for (int c = 0; c < N; c++) Kb[(size_t)c * ld + pos] = stage[c * 32 + lane];
     if (lane == 0) info[b] = sinfo;
-}
-
-// Quotient by the pivot in the register-resident factorisation kernels: reciprocal (MUFU seed + two Newton steps) times
-// the entry, <= 2 ulp, as LAPACK's getf2 scales by the rounded reciprocal -- the IEEE division subroutine costs ~370
-// cycles on the column-to-column critical path (one system of order 64: 65 -> 53 us).  The seed flushes denormals, so
-// a pivot below GF_LU_TINY in magnitude is treated like an exact zero (record_pivot reports the column, no elimination
-// with it); a range check that falls back to the division was measured to cost the whole gain.
-__device__ __forceinline__ double lu_pivot_div(double a, double d) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    return a * r;
 }
 
 // 32 < N <= 64: one CTA of two warps per matrix, thread t owns row t in registers, the pivot row travels through
