@@ -875,6 +875,7 @@ __device__ __forceinline__ void lu_block_swaps(double* v, const int32_t* pb, int
 // ------------------------------------------------------------------------------------------------
 // Blocked substitution on the packed LU factors; rhs[b] (length >= N) is overwritten by the solution.
 // The interchanges are applied block by block (32 columns), matching the factor layout (see the file header).
+template <bool RCP>  // RCP: per-lane reciprocal of the diagonal outside the 32-step chains (faster up to N ~ 1000)
 __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                        const double* __restrict__ K, const int32_t* __restrict__ piv,
                                                        double* __restrict__ rhs, int ldr, int trans, GfWork work) {
@@ -912,9 +913,9 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             __syncthreads();
             if (wid == 0) {
                 double s = (lane < jb) ? v[j0 + lane] - part[lane] : 0.0;
-                const double rd = lane < jb ? 1.0 / Tb[lane][lane] : 0.0;  // one division per lane, off the chain
+                const double rd = (RCP && lane < jb) ? 1.0 / Tb[lane][lane] : 0.0;  // one division per lane, off the chain
                 for (int ii = 0; ii < jb; ii++) {
-                    double w = s * rd;
+                    double w = RCP ? s * rd : s / Tb[ii][ii];
                     w = __shfl_sync(0xffffffffu, w, ii);
                     if (lane == ii) s = w;
                     else if (lane > ii && lane < jb) s -= Tb[lane][ii] * w;
@@ -988,9 +989,9 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             __syncthreads();
             if (wid == 0) {
                 double s = (lane < jb) ? v[j0 + lane] : 0.0;
-                const double rd = lane < jb ? 1.0 / Tb[lane][lane] : 0.0;
+                const double rd = (RCP && lane < jb) ? 1.0 / Tb[lane][lane] : 0.0;
                 for (int jj = jb - 1; jj >= 0; jj--) {
-                    double xj = s * rd;
+                    double xj = RCP ? s * rd : s / Tb[jj][jj];
                     xj = __shfl_sync(0xffffffffu, xj, jj);
                     if (lane == jj) s = xj;
                     else if (lane < jj) s -= Tb[jj][lane] * xj;
@@ -1209,8 +1210,14 @@ extern "C" int gf_lu_solve(int B, int ld, int Nmax, const int32_t* Nvec, const d
     }
     const size_t smem = (size_t)(Nmax + 1) * sizeof(double) + (size_t)Nmax * sizeof(int32_t);
     if (smem > 200 * 1024) return GF_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lu_solve_kernel<<<nwork, 256, smem, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,
-                                                                GfWork{work, nwork_dev});
+    if (Nmax < 1000) {
+        lu_solve_kernel<true><<<nwork, 256, smem, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,
+                                                                          GfWork{work, nwork_dev});
+    } else {  // measured: from N ~ 1000 the kernel with the divisions in the chains is the faster one (HBM-bound)
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(lu_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        lu_solve_kernel<false><<<nwork, 256, smem, (cudaStream_t)stream>>>(ld, Nvec, Nmax, K, piv, rhs, ldr, trans,
+                                                                           GfWork{work, nwork_dev});
+    }
     return gf_launch_status();
 }
