@@ -142,6 +142,9 @@ int gf_kkt_rhs(int B, int n, int m, int ld, const double* H, const double* J, co
 #define GF_FORM_EXTENDED 2
 #define GF_FORM_STANDARD 3 /* unscaled implicit function (standard_step_solver.py:15-92, implicit_func.py:163-199): H must
                               be H_rho = lag_hess(x, y + rho c) + rho J'J, rhs = F unscaled, solution = (dx, dy) */
+#define GF_FORM_SCALED_DERIV 4 /* gf_kkt_assemble_full only: F' of the scaled implicit function itself,
+                                 [[lamb I + P_I H_rho, P_I J'], [-J, lamb I]] (ScaledImplicitFunc.deriv, implicit_func.py:254-294;
+                                 what GlobalizedNewtonMethod reads through StepFunc.deriv_at, newton.py:262) */
 int gf_kkt_assemble_full(int B, int n, int m, int ld, int form, const double* H, const double* J, const int32_t* perm,
                          const int32_t* nI, const uint8_t* active, const double* dt, const double* rho, double* K,
                          const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);

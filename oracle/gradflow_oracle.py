@@ -109,6 +109,10 @@ class OracleParams:
     scaling: Optional[Any] = None
     scaling_primal: Optional[np.ndarray] = None
     scaling_dual: Optional[np.ndarray] = None
+    # keep J / H / K as scipy.sparse matrices like the reference does (csr J, csc K; symmetric_step_solver.py:27-94)
+    # instead of dense arrays -- same arithmetic, needed for cfg4-sized banded problems (Symmetric formulation only)
+    sparse: bool = False
+    penalty_filter_capacity: Optional[int] = None  # unused by the oracle (its filter is an unbounded list)
     dtype = np.float64
 
 
@@ -502,7 +506,8 @@ class OCP(OracleProblem):
     All sums are accumulated sequentially in index order so that the CUDA evaluators reproduce them.
     """
 
-    def __init__(self, A, Bm, Q, R, xinit, umax, h):
+    def __init__(self, A, Bm, Q, R, xinit, umax, h, sparse=False):
+        self.sparse = bool(sparse)  # return scipy.sparse J / H like a reference Problem would (problem.py:160-192)
         self.A = np.asarray(A, dtype=np.float64)
         self.Bm = np.asarray(Bm, dtype=np.float64)
         self.Q = np.asarray(Q, dtype=np.float64)
@@ -554,7 +559,7 @@ class OCP(OracleProblem):
             if j >= 1:
                 e = self.h * (self.A[j] + eye * (0.1 * np.cos(Xprev[j]))[None, :])
                 J[rows, (j - 1) * w : (j - 1) * w + nx] = -(eye + e)
-        return J
+        return scipy.sparse.csr_matrix(J) if self.sparse else J
 
     def lag_hess(self, z, y):
         X1, U, _ = self._split(z)
@@ -563,7 +568,8 @@ class OCP(OracleProblem):
         c1 = 0.1 * self.h
         dx = self.Q.copy()
         dx[:-1] = self.Q[:-1] + (Y[1:] * c1) * np.sin(X1[:-1])
-        return np.diag(np.concatenate([dx, self.R], axis=1).reshape(-1))
+        d = np.concatenate([dx, self.R], axis=1).reshape(-1)
+        return scipy.sparse.diags([d], [0], format="csr") if self.sparse else np.diag(d)
 
 
 class Tame(OracleProblem):
@@ -672,10 +678,15 @@ class Iterate:
     def cons_jac(self):
         if self.problem.num_cons == 0:
             return np.zeros((0, self.problem.num_vars))
-        return self._get("J", lambda: _dense(self.problem.cons_jac(self.x)))
+        return self._get("J", lambda: self._mat(self.problem.cons_jac(self.x)))
+
+    def _mat(self, a):
+        if getattr(self.params, "sparse", False):
+            return scipy.sparse.csr_matrix(a)
+        return _dense(a)
 
     def lag_hess(self, y):
-        return _dense(self.problem.lag_hess(self.x, y))
+        return self._mat(self.problem.lag_hess(self.x, y))
 
     # iterate.py:91-110
     def aug_lag_deriv_x(self, rho):
@@ -1047,6 +1058,24 @@ def kkt_system(H0, J, active, lamb, rho, b0, b1, b2t):
     return K, rhs
 
 
+def kkt_system_sparse(H0, J, active, lamb, rho, b0, b1, b2t):
+    """kkt_system with scipy.sparse operands, statement by statement as the reference builds it
+    (symmetric_step_solver.py:27-39 compute_hess_jac, :49-77 _compute_deriv, :79-94 compute_rhs)."""
+    inactive_indices = np.where(np.logical_not(active))[0]
+    active_indices = np.where(active)[0]
+    n = H0.shape[0]
+    m = J.shape[0]
+    hess = H0 + scipy.sparse.diags([lamb], shape=(n, n), dtype=np.float64)
+    hess_rows = hess.tocsr()[inactive_indices, :].tocsc()
+    jac = J.tocsc()
+    inactive_jac = jac[:, inactive_indices]
+    inactive_hess = hess_rows[:, inactive_indices]
+    lower = scipy.sparse.diags([-lamb / (1.0 + lamb * rho)], shape=(m, m), dtype=np.float64)
+    K = scipy.sparse.bmat([[inactive_hess, inactive_jac.T], [inactive_jac, lower]], format="csc")
+    rhs = np.concatenate((b1 - (hess_rows[:, active_indices] @ b0), b2t - (jac[:, active_indices] @ b0)))
+    return K, rhs
+
+
 class SymmetricStepSolver:
     """scaled_step_solver.py:15-107 + symmetric_step_solver.py:13-164 on dense arrays."""
 
@@ -1072,8 +1101,9 @@ class SymmetricStepSolver:
         return self._func
 
     def update_derivs(self, iterate):
-        self.jac = np.array(iterate.aug_lag_deriv_xy(), copy=True)
-        self.hess = np.array(iterate.aug_lag_deriv_xx(0.0), copy=True)  # multiplier y only
+        J, H = iterate.aug_lag_deriv_xy(), iterate.aug_lag_deriv_xx(0.0)  # multiplier y only
+        self.jac = J.copy() if scipy.sparse.issparse(J) else np.array(J, copy=True)
+        self.hess = H.copy() if scipy.sparse.issparse(H) else np.array(H, copy=True)
         self.solver = None
         self.K = None
 
@@ -1100,7 +1130,8 @@ class SymmetricStepSolver:
         fact = 1.0 / (1.0 + lamb * rho)
         b2t = fact * b2
         A = self.active_set
-        K, rhs = kkt_system(self.hess, self.jac, A, lamb, rho, b0, b1, b2t)
+        build = kkt_system_sparse if scipy.sparse.issparse(self.hess) else kkt_system
+        K, rhs = build(self.hess, self.jac, A, lamb, rho, b0, b1, b2t)
         if self.K is None:
             self.K = K
         try:

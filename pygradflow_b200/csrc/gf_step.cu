@@ -256,6 +256,9 @@ __global__ void kkt_full_kernel(int n, int m, int ld, int form, const double* __
             if (form == GF_FORM_STANDARD) {  // [-dt J, I]  (implicit_func.py:185-186)
                 for (int c = lane; c < n; c += 32) out[c] = -__dmul_rn(dtb, __ldg(src + c));
                 for (int c = n + lane; c < N; c += 32) out[c] = (c == r) ? 1.0 : 0.0;
+            } else if (form == GF_FORM_SCALED_DERIV) {  // [-J, lamb I]  (implicit_func.py:274-276)
+                for (int c = lane; c < n; c += 32) out[c] = -__ldg(src + c);
+                for (int c = n + lane; c < N; c += 32) out[c] = (c == r) ? lamb : 0.0;
             } else {
                 for (int c = lane; c < n; c += 32) out[c] = __ldg(src + c);
                 for (int c = n + lane; c < N; c += 32) out[c] = (c == r) ? corner : 0.0;
@@ -270,8 +273,9 @@ __global__ void kkt_full_kernel(int n, int m, int ld, int form, const double* __
             if (ab[r]) unit = r;
             else hrow = r;
         }
-        if (unit >= 0) {
-            for (int c = lane; c < N; c += 32) out[c] = (c == unit) ? 1.0 : 0.0;
+        if (unit >= 0) {  // SCALED_DERIV: keep_rows zeroes the row of H_rho and J', lamb I stays (implicit_func.py:266-270)
+            const double one = form == GF_FORM_SCALED_DERIV ? lamb : 1.0;
+            for (int c = lane; c < N; c += 32) out[c] = (c == unit) ? one : 0.0;
         } else if (form == GF_FORM_STANDARD) {  // [I + dt H_rho, dt J'] on the inactive rows (implicit_func.py:176-183)
             const double* src = Hb + (size_t)hrow * n;
             for (int c = lane; c < n; c += 32) {
@@ -630,6 +634,7 @@ extern "C" int gf_kkt_assemble(int B, int n, int m, int ld, int pad, int lower_o
         return GF_ERR_ARG;
     if (m > 0 && !J) return GF_ERR_ARG;
     if (nwork <= 0) return GF_OK;
+    if (nwork > 65535) return GF_ERR_UNSUPPORTED;  // the instance index rides in grid.y
     constexpr int ROWS = 32;
     dim3 grid((ld + ROWS - 1) / ROWS, nwork);
     const size_t smem = (size_t)n * sizeof(int32_t);
@@ -660,8 +665,11 @@ extern "C" int gf_kkt_assemble_full(int B, int n, int m, int ld, int form, const
                                     int nwork, void* stream) {
     if (B <= 0 || n <= 0 || m < 0 || ld < n + m || !H || !perm || !nI || !active || !dt || !rho || !K) return GF_ERR_ARG;
     if (m > 0 && !J) return GF_ERR_ARG;
-    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED && form != GF_FORM_STANDARD) return GF_ERR_UNSUPPORTED;
+    if (form != GF_FORM_ASYMMETRIC && form != GF_FORM_EXTENDED && form != GF_FORM_STANDARD &&
+        form != GF_FORM_SCALED_DERIV)
+        return GF_ERR_UNSUPPORTED;
     if (nwork <= 0) return GF_OK;
+    if (nwork > 65535) return GF_ERR_UNSUPPORTED;  // the instance index rides in grid.y
     constexpr int ROWS = 16;
     dim3 grid((n + m + ROWS - 1) / ROWS, nwork);
     kkt_full_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, ld, form, H, J, perm, nI, active, dt, rho, K,

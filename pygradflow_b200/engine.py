@@ -32,13 +32,17 @@ BAND_MIN_N = 256  # order from which Auto prefers the family's banded ordering o
 
 class KKTEngine:
     def __init__(self, B: int, n: int, m: int, device, linear: LinearSolverType = LinearSolverType.Auto, band=None,
-                 formulation: StepSolverType = StepSolverType.Symmetric):
+                 formulation: StepSolverType = StepSolverType.Symmetric, inertia_correction: bool = False):
         """band: optional (order, half_bandwidth) of the family's KKT ordering (BatchedProblem.kkt_band).
         formulation: Symmetric = the reduced KKT system; Asymmetric / Extended = the full-order unsymmetric systems
         of asymmetric_step_solver.py / extended_step_solver.py, Standard = the derivative of the unscaled implicit
         function (standard_step_solver.py; the caller hands in H_rho and the unscaled residual) -- always pivoted LU,
-        order n + m for every instance."""
+        order n + m for every instance.
+        inertia_correction: Params.inertia_correction (symmetric_step_solver.py:146-153) -- a factorisation whose number
+        of negative pivots differs from m fails like a LinearSolverError (the step is rejected, lambda doubled); needs a
+        factorisation that reports the inertia (LDL' / Banded), there is no pivoted-LU fallback in this mode."""
         self.B, self.n, self.m = B, n, m
+        self.inertia_correction = bool(inertia_correction)
         self.device = device
         N = n + m
         self.form = {StepSolverType.Symmetric: K.FORM_SYMMETRIC, StepSolverType.Asymmetric: K.FORM_ASYMMETRIC,
@@ -50,8 +54,13 @@ class KKTEngine:
         if linear == LinearSolverType.Auto:
             if band is not None and N >= BAND_MIN_N:
                 linear = LinearSolverType.Banded
+            elif self.inertia_correction:
+                linear = LinearSolverType.LDLT
             else:
                 linear = LinearSolverType.LU if N <= SMALL_N else LinearSolverType.LDLT
+        if self.inertia_correction and linear == LinearSolverType.LU:
+            # LUSolver.num_neg_eigvals() is None: symmetric_step_solver.py:149-150 raises the same way
+            raise Exception("Inertia correction requested but not available")
         self.linear = linear
         if linear == LinearSolverType.Banded:
             self._init_banded(band)
@@ -149,6 +158,14 @@ class KKTEngine:
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
+        if self.inertia_correction:
+            # Sylvester: the signs of D are the inertia whatever their positions; nneg != m => "Invalid matrix inertia"
+            # (symmetric_step_solver.py:152-153), reported as info = -2 and never refactorised with LU
+            K.ldlt_factor(self.K, Nmax, self.Nvec, self.dvec, self.info, self.nneg, None, work)
+            torch.where((self.info == 0) & (self.nneg != self.m), torch.full_like(self.info, -2), self.info,
+                        out=self.info)
+            self.fbkey.zero_()
+            return
         if self.fuse_assembly:
             K.kkt_ldlt_factor(H, J, self.perm, self.nI, dt, rho, self.Nvec, self.K, self.dvec, self.info, self.nneg, work)
         else:

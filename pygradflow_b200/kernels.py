@@ -114,7 +114,7 @@ def kkt_rhs(H, J, perm, nI, F, dt, rho, rhs, work: WorkList):
           *_w(work))
 
 
-FORM_SYMMETRIC, FORM_ASYMMETRIC, FORM_EXTENDED, FORM_STANDARD = 0, 1, 2, 3  # GF_FORM_* of include/gradflow_b200.h
+FORM_SYMMETRIC, FORM_ASYMMETRIC, FORM_EXTENDED, FORM_STANDARD, FORM_SCALED_DERIV = 0, 1, 2, 3, 4  # GF_FORM_* of the header
 
 
 def kkt_assemble_full(H, J, perm, nI, active, dt, rho, K, form: int, work: WorkList):

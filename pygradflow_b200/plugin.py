@@ -191,15 +191,73 @@ class B200StepFunc:
         return self._dL
 
     def compute_active_set(self, iterate, rho: float, tau=None) -> np.ndarray:
-        if tau is not None:
-            raise NotImplementedError("tau-based active sets (ActiveSetType != Standard) are outside the B200 path")
+        """implicit_func.py:72-74; tau (ActiveSetType Explicit / Smallest / Largest, newton_control.py:60-88) selects
+        the tau-variant of the projected point (:237-244) inside gf_residual_tau."""
         it = _cache(iterate, self.device)
         o = _cache(self.orig_iterate, self.device)
         dL = self._grad_lag(it, rho)
         m = self.m
+        tau_d = None
+        if tau is not None:
+            tau_d = torch.full((1,), float(tau), dtype=torch.float64, device=self.device)
         K.residual(it.x, it.y if m > 0 else None, o.x, o.y if m > 0 else None, dL, it.cons if m > 0 else None,
-                   self.lb_d, self.ub_d, self.dt_d, True, 0, self._act, None, None, _one())
+                   self.lb_d, self.ub_d, self.dt_d, True, 0, self._act, None, None, _one(), tau=tau_d)
         return self._act[0].cpu().numpy().astype(bool)
+
+    def projection_initial(self, iterate, rho: float, tau=None) -> np.ndarray:
+        """implicit_func.py:233-246: the point whose box position decides the active set."""
+        it = _cache(iterate, self.device)
+        o = _cache(self.orig_iterate, self.device)
+        dL = self._grad_lag(it, rho)
+        lamb = self.lamb
+        if tau is not None:
+            p = (lamb * (1 - tau * lamb)) * it.x + (tau * lamb * lamb) * o.x - (tau * lamb) * dL
+        else:
+            p = lamb * o.x - dL
+        return p[0].cpu().numpy()
+
+    # host-side helpers of the StepFunc base class (implicit_func.py:21-60,80-99), kept for interface completeness
+    def compute_active_set_box(self, x, lb, ub) -> np.ndarray:
+        return np.logical_or(x < lb - 1e-8, x > ub + 1e-8)
+
+    def project_box(self, x, lb, ub, active_set) -> np.ndarray:
+        p = np.copy(x)
+        p[active_set] = np.clip(x[active_set], lb[active_set], ub[active_set])
+        return p
+
+    def project(self, x, active_set) -> np.ndarray:
+        return self.project_box(x, self.lb, self.ub, active_set)
+
+    def apply_project_deriv(self, mat, active_set):
+        """keep_rows(mat, inactive) (util.py:27-55): the rows of the active variables become zero."""
+        import scipy.sparse as sps
+
+        keep = sps.diags([np.logical_not(active_set).astype(np.float64)], [0])
+        return (keep @ sps.csr_matrix(mat)).tocsr()
+
+    def deriv(self, jac, hess, active_set):
+        """ScaledImplicitFunc.deriv (implicit_func.py:254-286): F' = [[lamb I + P_I H, P_I J'], [-J, lamb I]] assembled
+        by gf_kkt_assemble_full(GF_FORM_SCALED_DERIV); returned as a scipy csc matrix like the reference."""
+        import scipy.sparse as sps
+
+        n, m, dev = self.n, self.m, self.device
+        N = n + m
+        i32 = dict(dtype=torch.int32, device=dev)
+        act = torch.from_numpy(np.asarray(active_set, dtype=np.uint8)).to(dev).reshape(1, n).contiguous()
+        perm = torch.zeros((1, n), **i32)
+        nI = torch.zeros((1,), **i32)
+        K.index_sets(act, m, perm, nI, None, _one())
+        Hd = _dev(_dense(hess), dev).reshape(1, n, n)
+        Jd = _dev(_dense(jac), dev).reshape(1, m, n) if m > 0 else None
+        out = torch.zeros((1, N, N), dtype=torch.float64, device=dev)
+        K.kkt_assemble_full(Hd, Jd, perm, nI, act, self.dt_d, self._rho, out, K.FORM_SCALED_DERIV, _one())
+        return sps.csc_matrix(out[0].cpu().numpy())
+
+    def deriv_at(self, iterate, rho: float, active_set: Optional[np.ndarray] = None):
+        """implicit_func.py:288-294 (what GlobalizedNewtonMethod.step reads, newton.py:262)."""
+        if active_set is None:
+            active_set = self.compute_active_set(iterate, rho)
+        return self.deriv(iterate.aug_lag_deriv_xy(), iterate.aug_lag_deriv_xx(rho), active_set)
 
     def value_at(self, iterate, rho: float, active_set: Optional[np.ndarray] = None) -> np.ndarray:
         it = _cache(iterate, self.device)
@@ -276,7 +334,8 @@ class B200StepSolver:
         self._func = B200StepFunc(problem, orig_iterate, dt, device)
         if linear is None:
             linear = getattr(params, "b200_linear_solver", LinearSolverType.Auto)
-        self.engine = KKTEngine(1, self.n, self.m, device, linear)
+        self.engine = KKTEngine(1, self.n, self.m, device, linear,
+                                inertia_correction=bool(getattr(params, "inertia_correction", False)))
         f64 = dict(dtype=torch.float64, device=device)
         self.rho_d = torch.full((1,), rho, **f64)
         self.H = None
@@ -300,8 +359,29 @@ class B200StepSolver:
         assert self._active_host is not None
         return self._active_host
 
+    @property
+    def jac(self):
+        assert self.J is not None
+        return self.J[0].cpu().numpy()
+
+    @property
+    def hess(self):
+        assert self.H is not None
+        return self.H[0].cpu().numpy()
+
     def reset_deriv(self) -> None:
         self._factored = False
+
+    def estimate_rcond(self, mat=None, solver=None) -> Optional[float]:
+        """StepSolver.estimate_rcond (step_solver.py:100-113) for the current factorisation (Dixon's estimator on the
+        device, KKTEngine.estimate_rcond); `mat` / `solver` are implied by the engine's state."""
+        if not self._factored:
+            return None
+        try:
+            rc = self.engine.estimate_rcond(self.H, self.J, self._func.dt_d, self.rho_d, _one())
+        except NotImplementedError:
+            return None
+        return float(rc[0].item())
 
     def update_derivs(self, iterate) -> None:
         """scaled_step_solver.py:76-79: J = aug_lag_deriv_xy, H = aug_lag_deriv_xx(rho=0) (multiplier y)."""
@@ -332,13 +412,11 @@ class B200StepSolver:
         if not self._factored:
             eng.factor(self.H, self.J, f.dt_d, self.rho_d, _one())
             self.num_factorizations += 1
-            if int(eng.info.item()) != 0:
+            info = int(eng.info.item())
+            if info == -2 and eng.inertia_correction:  # symmetric_step_solver.py:146-153
+                raise SSE() from LSE("Invalid matrix inertia")
+            if info != 0:
                 raise SSE() from LSE("KKT factorisation failed")
-            if getattr(self.params, "inertia_correction", False):
-                if eng.linear != LinearSolverType.LDLT or int(eng.fbkey.item()) != 0:
-                    raise Exception("Inertia correction requested but not available")
-                if int(eng.nneg.item()) != self.m:
-                    raise SSE() from LSE("Invalid matrix inertia")
             self._factored = True
         F = f.value_device(iterate, self.rho, eng.active)
         it = _cache(iterate, self.device)
@@ -348,4 +426,5 @@ class B200StepSolver:
         out = torch.cat([self._xn[0], self._dx[0], self._dy[0], self._diff]).cpu().numpy()
         n = self.n
         xn, dx, dy, diff = out[:n], out[n : 2 * n], out[2 * n : 2 * n + m], float(out[-1])
-        return StepResult(iterate, dx, dy, self._active_host, None, xn=xn.copy(), diff=diff)
+        rcond = self.estimate_rcond() if getattr(self.params, "report_rcond", False) else None
+        return StepResult(iterate, dx, dy, self._active_host, rcond, xn=xn.copy(), diff=diff)

@@ -60,7 +60,8 @@ class BatchedSolver:
         p = problem
         B, n, m, dev = p.B, p.n, p.m, p.device
         self.engine = KKTEngine(B, n, m, dev, self.params.linear_solver_type, band=problem.kkt_band(),
-                                formulation=self.params.step_solver_type)
+                                formulation=self.params.step_solver_type,
+                                inertia_correction=self.params.inertia_correction)
         # StandardStepSolver works on the unscaled implicit function (its own active-set test, F and F')
         self._standard = self.params.step_solver_type == StepSolverType.Standard
         self._scaled = not self._standard

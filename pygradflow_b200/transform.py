@@ -15,6 +15,7 @@ from typing import Optional
 
 import torch
 
+from . import kernels as K
 from .kernels import WorkList
 from .problem import BatchedProblem
 
@@ -42,8 +43,15 @@ class BatchedConstrained(BatchedProblem):
         B, n, m = self.B, self.no, self.m
         self._xo = torch.zeros((B, n), **f64)
         self._go = torch.zeros((B, n), **f64)
+        # Scratch of the augmented outputs: every callback fills its scratch for the whole batch and then copies only
+        # the rows of the instances in `work` into the caller's tensor (gf_ldexp with no weights is a work-list copy),
+        # so that instances outside the list -- e.g. the ones ExactController already stopped -- keep their values.
+        self._ga = torch.zeros((B, self.n), **f64)
+        self._ci = torch.zeros((B, m), **f64)
         self._Ji = torch.zeros((B, m, n), **f64) if (m > 0 and not problem.jac_constant) else None
         self._Hi = torch.zeros((B, n, n), **f64) if not problem.hess_constant else None
+        self._Ja = torch.zeros((B, m, self.n), **f64) if (m > 0 and not problem.jac_constant) else None
+        self._Ha = torch.zeros((B, self.n, self.n), **f64) if not problem.hess_constant else None
         self._Jc: Optional[torch.Tensor] = None   # persistent augmented J / H of constant-derivative families
         self._Hc: Optional[torch.Tensor] = None
         self._prepared = set()
@@ -67,13 +75,16 @@ class BatchedConstrained(BatchedProblem):
 
     # -- Problem callbacks -----------------------------------------------------------------------
     def eval(self, x, grad, cons, obj, work):
-        self.inner.eval(self._orig(x), self._go, cons, obj, work)       # :62-94
-        grad[:, : self.no].copy_(self._go)
-        grad[:, self.no:].zero_()
-        if self.cons_offsets is not None:
-            cons.add_(self.cons_offsets)
-        if self.ns > 0:
-            cons[:, self.slack_positions] -= x[:, self.no:]
+        ci = self._ci if self.m > 0 else cons
+        self.inner.eval(self._orig(x), self._go, ci, obj, work)         # :62-94
+        self._ga[:, : self.no].copy_(self._go)                           # slack part of the scratch stays zero
+        K.ldexp(self._ga, grad, work)
+        if self.m > 0:
+            if self.cons_offsets is not None:
+                ci.add_(self.cons_offsets)
+            if self.ns > 0:
+                ci[:, self.slack_positions] -= x[:, self.no:]
+            K.ldexp(ci, cons, work)
 
     def jac(self, x, out, work):                                         # :96-113
         if self.jac_constant:
@@ -83,9 +94,10 @@ class BatchedConstrained(BatchedProblem):
                 self._prepare_jac(self._Jc)
                 self._Jc[:, :, : self.no].copy_(Ji)
             return self._Jc
-        self._prepare_jac(out)
+        self._prepare_jac(self._Ja)
         Ji = self.inner.jac(self._orig(x), self._Ji, work)
-        out[:, :, : self.no].copy_(Ji)
+        self._Ja[:, :, : self.no].copy_(Ji)
+        K.ldexp(self._Ja, out, work)
         return out
 
     def lag_hess(self, x, y, out, work):                                 # :115-128
@@ -95,9 +107,10 @@ class BatchedConstrained(BatchedProblem):
                 self._Hc = torch.zeros((self.B, self.n, self.n), dtype=torch.float64, device=self.device)
                 self._Hc[:, : self.no, : self.no].copy_(Hi)
             return self._Hc
-        self._prepare_hess(out)
+        self._prepare_hess(self._Ha)
         Hi = self.inner.lag_hess(self._orig(x), y, self._Hi, work)
-        out[:, : self.no, : self.no].copy_(Hi)
+        self._Ha[:, : self.no, : self.no].copy_(Hi)
+        K.ldexp(self._Ha, out, work)
         return out
 
     # -- solution transforms ---------------------------------------------------------------------

@@ -523,7 +523,23 @@ def golden_ocp():
     np.savez_compressed(os.path.join(HERE, "ocp.npz"), **out)
 
 
+def golden_ocp_full():
+    """cfg4 at FULL size (S=128, nx=nu=8: n=2048, m=1024) through the real reference with scipy.sparse J / H:
+    status, iteration counts, accept sequence, final iterate and every 25th candidate iterate."""
+    out = {}
+    for k in (0, 1, 2, 3):
+        d = synth.ocp_instance(k)
+        res = trace_solve(RefOCP(d), params_for("Simplified"), d["x0"], d["y0"], keep_every=25)
+        out.update(flat(f"ocp_full_k{k}", res))
+        print("ocp_full", k, int(res["status"]), int(res["iterations"]), flush=True)
+    np.savez_compressed(os.path.join(HERE, "ocp_full.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["golden_" + name]()
+        sys.exit(0)
     golden_linear_solver()
     golden_newton()
     golden_globalized()
