@@ -158,14 +158,6 @@ class KKTEngine:
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        if self.inertia_correction:
-            # Sylvester: the signs of D are the inertia whatever their positions; nneg != m => "Invalid matrix inertia"
-            # (symmetric_step_solver.py:152-153), reported as info = -2 and never refactorised with LU
-            K.ldlt_factor(self.K, Nmax, self.Nvec, self.dvec, self.info, self.nneg, None, work)
-            torch.where((self.info == 0) & (self.nneg != self.m), torch.full_like(self.info, -2), self.info,
-                        out=self.info)
-            self.fbkey.zero_()
-            return
         if self.fuse_assembly:
             K.kkt_ldlt_factor(H, J, self.perm, self.nI, dt, rho, self.Nvec, self.K, self.dvec, self.info, self.nneg, work)
         else:
@@ -183,6 +175,13 @@ class KKTEngine:
         K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, self._fb)
         K.lu_factor(self.K, Nmax, self.Nvec, self.piv, self.info_lu, self._fb)
         torch.where(self.fbkey != 0, self.info_lu, self.info, out=self.info)
+        if self.inertia_correction:
+            # symmetric_step_solver.py:146-153: num_neg_eigvals != m => LinearSolverError("Invalid matrix inertia").  By
+            # Sylvester's law the signs of D are the inertia whatever their positions, so the unpivoted LDL' counts it even
+            # when the pivot pattern is not the quasi-definite one; the SOLUTION of such an instance still comes from the
+            # pivoted LU above (stable), only the count from D.  A broken-down LDL' (zero pivot) has no inertia: rejected.
+            bad = (self.nneg != self.m) | (self.fbkey > 0) | (self.fbkey == -1)
+            torch.where((self.info == 0) & bad, torch.full_like(self.info, -2), self.info, out=self.info)
 
     def solve(self, rhs, work: WorkList, trans: bool = False):
         """rhs[B, ld] <- K^{-1} rhs for the instances in ``work``."""

@@ -33,9 +33,22 @@ class StepSolverError(Exception):
     """Same role as pygradflow/step/step_solver_error.py:1-7."""
 
 
+_ERROR_TYPES = None
+
+
+def set_error_types(linear_solver_error, step_solver_error) -> None:
+    """Exception classes the plug-in raises.  Under the reference's Solver they are found automatically
+    (``_reference_errors``); a host loop with its own classes (the test oracle's restatement of
+    StepController.compute_step) registers them here.  ``None, None`` restores the default."""
+    global _ERROR_TYPES
+    _ERROR_TYPES = None if linear_solver_error is None else (linear_solver_error, step_solver_error)
+
+
 def _reference_errors():
     """When the reference package is importable, raise ITS exception types so that
     StepController.compute_step (step_control.py:102-104) catches them."""
+    if _ERROR_TYPES is not None:
+        return _ERROR_TYPES
     try:  # pragma: no cover - depends on the host environment
         from pygradflow.linear_solver import LinearSolverError as RefLSE
         from pygradflow.step.step_solver_error import StepSolverError as RefSSE

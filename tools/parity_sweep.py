@@ -4,8 +4,8 @@ on identical inputs, instance by instance and outer iteration by outer iteration
     python tools/parity_sweep.py [--cfg 2,3,4] [--count 128,128,8] [--out profiles/r02_parity_sweep.json]
 
 For every instance the two sides are compared on: termination status, iteration count, accepted-step count, the
-accept / reject / failure sequence, the active set of every outer iteration (64-bit signature), the lambda
-trajectory (relative 1e-9) and the final iterate.  The first outer iteration where anything differs is reported with
+accept / reject / failure sequence, the active set of every outer iteration (64-bit signature), and the final
+iterate; the lambda trajectory is reported (maximal relative deviation while the decisions agree), not gated.  The first outer iteration where anything differs is reported with
 the contraction ratio theta there, the active-set margin |p - (bound -/+ 1e-8)| of the oracle at that iteration
 ("active-set bit-consistency") and whether the instance had already passed its rounding-noise horizon
 (first iteration with theta < 1e-8: from there on the reference feeds log(theta) of pure rounding noise into its PI
@@ -25,7 +25,12 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 THETA_NOISE = 1e-8
-LAMB_RTOL = 1e-9
+# lambda_next = lambda / exp(K_P e + K_I sum e), e = log(theta_ref) - log(theta), theta = |d2| / |d1|: the relative error of
+# lambda is 0.2 x that of theta, and |d2| -- the length of the second Newton step, 1e-6 .. 1e-12 of |d1| near convergence
+# -- carries the absolute rounding error of the linear solve (~1e-16 |x|), i.e. up to 1e-4 relative.  The lambda
+# trajectories of two correct implementations therefore agree to 1e-6 .. 1e-5 at best; decisions (accept / reject,
+# active sets, termination, iteration counts) are what must be identical, lambda is reported only.
+LAMB_RTOL = 1e-6
 HASH_MUL = 2654435761
 
 
@@ -174,19 +179,21 @@ def compare_instance(g, c):
             first, why = i, "accept"
         elif g["ahash"][i] != c["ahash"][i]:
             first, why = i, "active_set"
-        elif abs(g["lamb"][i] - c["lamb"][i]) > LAMB_RTOL * abs(c["lamb"][i]):
-            first, why = i, "lambda"
         if first is not None:
             break
     if first is None and len(g["code"]) != len(c["code"]):
         first, why = n, "length"
-    lam_rel = 0.0
+    lam_rel, lam_sep = 0.0, None
     upto = n if first is None else first
     if upto > 0:
-        lam_rel = float(np.max(np.abs(g["lamb"][:upto] - c["lamb"][:upto]) / np.abs(c["lamb"][:upto])))
+        lr = np.abs(g["lamb"][:upto] - c["lamb"][:upto]) / np.abs(c["lamb"][:upto])
+        lam_rel = float(np.max(lr))
+        sep = np.where(lr > LAMB_RTOL)[0]
+        lam_sep = int(sep[0]) if sep.size else None   # informational: first iteration with |dlambda| / lambda > LAMB_RTOL
     out = dict(k=c["k"], status_gpu=g["status"], status_cpu=c["status"], iters_gpu=g["iterations"],
                iters_cpu=c["iterations"], accepted_gpu=g["accepted"], accepted_cpu=c["accepted"], horizon=horizon,
                hit_horizon=bool(noisy.size), first_div=first, div_kind=why, lamb_rel_before_div=lam_rel,
+               lamb_separation_iter=lam_sep,
                x_rel=_rel(g["x"], c["x"]), y_rel=_rel(g["y"], c["y"]), cpu_s=c["cpu_s"])
     if first is not None and first < len(c["theta"]):
         out["theta_at_div"] = float(c["theta"][first]) if c["theta"][first] == c["theta"][first] else None
@@ -224,6 +231,7 @@ def sweep(cfg, count, stages=128, limit=None, workers=None):
         max_x_rel_identical=max([r["x_rel"] for r in rows if r["identical"] and "x_rel" in r] or [0.0]),
         max_x_rel_all=max([r["x_rel"] for r in rows if "x_rel" in r] or [0.0]),
         max_lamb_rel_before_div=max([r.get("lamb_rel_before_div", 0.0) for r in rows] or [0.0]),
+        median_lamb_rel_before_div=float(np.median([r.get("lamb_rel_before_div", 0.0) for r in rows])),
         iterations_cpu=dict(min=int(min(r["iters_cpu"] for r in rows if "iters_cpu" in r)),
                             max=int(max(r["iters_cpu"] for r in rows if "iters_cpu" in r))),
     )
