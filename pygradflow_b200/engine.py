@@ -32,7 +32,7 @@ BAND_MIN_N = 256  # order from which Auto prefers the family's banded ordering o
 
 class KKTEngine:
     def __init__(self, B: int, n: int, m: int, device, linear: LinearSolverType = LinearSolverType.Auto, band=None,
-                 formulation: StepSolverType = StepSolverType.Symmetric, inertia_correction: bool = False):
+                 formulation: StepSolverType = StepSolverType.Symmetric, inertia_correction: bool = False, stage=None):
         """band: optional (order, half_bandwidth) of the family's KKT ordering (BatchedProblem.kkt_band).
         formulation: Symmetric = the reduced KKT system; Asymmetric / Extended = the full-order unsymmetric systems
         of asymmetric_step_solver.py / extended_step_solver.py, Standard = the derivative of the unscaled implicit
@@ -51,6 +51,10 @@ class KKTEngine:
             if linear not in (LinearSolverType.Auto, LinearSolverType.LU):
                 raise ValueError(f"step_solver_type={formulation.name} has an unsymmetric matrix: LU only")
             linear = LinearSolverType.LU
+        if linear == LinearSolverType.BlockTri:
+            self.linear = linear
+            self._init_blocktri(stage)
+            return
         if linear == LinearSolverType.Auto:
             if band is not None and N >= BAND_MIN_N:
                 linear = LinearSolverType.Banded
@@ -120,6 +124,30 @@ class KKTEngine:
         self.active = torch.zeros((B, n), dtype=torch.uint8, device=device)
         self.n_factor_calls = 0
 
+    def _init_blocktri(self, stage):
+        """Stage-structured engine (gf_stage_kkt_factor / gf_stage_kkt_solve): H and J arrive in the family's compact
+        layout (BatchedProblem.kkt_stage_structure); no KKT matrix is ever assembled."""
+        assert stage is not None, "LinearSolverType.BlockTri needs a family with kkt_stage_structure()"
+        B, n, m, device = self.B, self.n, self.m, self.device
+        S, nx, nu = stage
+        assert n == S * (nx + nu) and m == S * nx
+        self.stage = (int(S), int(nx), int(nu))
+        f64 = dict(dtype=torch.float64, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.ld = n + m
+        self.K = None
+        self.Tinv, self.Lc, self.Uc = (torch.zeros((B, S, nx * nx), **f64) for _ in range(3))
+        self.rhs = torch.zeros((B, n + m), **f64)
+        self.perm = torch.zeros((B, n), **i32)
+        self.nI = torch.zeros((B,), **i32)
+        self.Nvec = torch.zeros((B,), **i32)
+        self.info = torch.zeros((B,), **i32)
+        self.nneg = torch.zeros((B,), **i32)
+        self.active = torch.zeros((B, n), dtype=torch.uint8, device=device)
+        self.perm_id = torch.arange(n, **i32).repeat(B, 1).contiguous()
+        self.n_full = torch.full((B,), n, **i32)
+        self.n_factor_calls = 0
+
     # ---------------------------------------------------------------------------------------
     def update_active_set(self, work: WorkList, active: Optional[torch.Tensor] = None):
         """np.where(~A) / np.where(A) for the stored active set (self.active unless given)."""
@@ -127,6 +155,8 @@ class KKTEngine:
 
     def assemble(self, H, J, dt, rho, work: WorkList):
         """The reduced symmetric KKT matrix of symmetric_step_solver.py:49-77 in the layout of the factorisation."""
+        if self.linear == LinearSolverType.BlockTri:
+            return  # the factorisation forms the Schur complement straight from the compact H, J
         if self.form != K.FORM_SYMMETRIC:
             K.kkt_assemble_full(H, J, self.perm, self.nI, self.active, dt, rho, self.K, self.form, work)
         elif self.linear == LinearSolverType.Banded:
@@ -144,6 +174,13 @@ class KKTEngine:
     def factor_assembled(self, H, J, dt, rho, work: WorkList):
         self.n_factor_calls += 1
         Nmax = self.n + self.m
+        if self.linear == LinearSolverType.BlockTri:
+            S, nx, nu = self.stage
+            # info = -2: some H_ii + lamb <= 0, K is not quasi-definite -- reported like a failed factorisation (the step
+            # is rejected and lambda doubled, step_control.py:102-104), as in Banded mode
+            K.stage_kkt_factor(S, nx, nu, J, H, self.active, dt, rho, self.Tinv, self.Lc, self.Uc, self.info, self.nneg,
+                               work)
+            return
         if self.linear == LinearSolverType.Banded:
             K.band_factor(self.Kband, self.bw, self.info, self.nneg, work)
             # inertia of a quasi-definite K: exactly m negative pivots (the active rows are +1); anything else is
@@ -186,6 +223,8 @@ class KKTEngine:
     def solve(self, rhs, work: WorkList, trans: bool = False):
         """rhs[B, ld] <- K^{-1} rhs for the instances in ``work``."""
         Nmax = self.n + self.m
+        if self.linear == LinearSolverType.BlockTri:
+            raise NotImplementedError("the stage-structured engine solves from the residual (KKTEngine.step)")
         if self.linear == LinearSolverType.Banded:
             K.band_permute(self.perm, self.nI, self.pos, rhs, self.bandv, True, self.m, work)
             K.band_solve(self.Kband, self.bw, self.bandv, work)  # symmetric: trans is irrelevant
@@ -208,8 +247,8 @@ class KKTEngine:
         products with a re-assembled copy of the matrix) and on its inverse (``solve(trans=True)`` then ``solve``),
         start vectors from ``default_rng(42)`` exactly as the reference draws them.  A diagnostic (``report_rcond``):
         it keeps a second matrix buffer and reads the orders back to the host."""
-        if self.linear == LinearSolverType.Banded:
-            raise NotImplementedError("report_rcond is not available with the banded factorisation")
+        if self.linear in (LinearSolverType.Banded, LinearSolverType.BlockTri):
+            raise NotImplementedError("report_rcond is not available with the banded / stage-structured factorisations")
         import numpy as np
 
         B, ld, dev = self.B, self.ld, self.device
@@ -267,6 +306,12 @@ class KKTEngine:
 
     def step(self, H, J, xbase, ybase, F, dt, rho, lb, ub, xn, yn, diff, work: WorkList, dx=None, dy=None):
         """ScaledStepSolver.solve + StepResult for the current factor: rhs, substitution, step finish."""
+        if self.linear == LinearSolverType.BlockTri:
+            S, nx, nu = self.stage
+            K.stage_kkt_solve(S, nx, nu, J, H, self.active, F, dt, rho, self.Tinv, self.Lc, self.Uc, self.rhs, work)
+            K.step_finish(xbase, ybase, self.rhs, self.perm_id, self.n_full, F, dt, rho, lb, ub, xn, yn, dx, dy, diff,
+                          work)
+            return
         if self.form != K.FORM_SYMMETRIC:
             # asymmetric_step_solver.py:140-173 / extended_step_solver.py:85-112: the solution is (dx, sy) itself
             K.kkt_rhs_full(self.n, self.m, self.perm, self.nI, self.active, F, dt, rho, self.rhs, self.form, work)

@@ -286,3 +286,27 @@ def band_permute(perm, nI, pos, stdv, bandv, to_band: bool, m: int, work: WorkLi
     B, n = perm.shape
     _call("gf_band_permute", B, n, m, stdv.shape[1], ptr(perm), ptr(nI), ptr(pos), ptr(stdv), ptr(bandv),
           1 if to_band else 0, *_w(work))
+
+
+# ---- stage-structured KKT systems (cfg4): compact Jacobian Jc [B, S*nx, nx + w], diagonal Hessian Hd [B, n] ----------
+def ocp_jac_banded(S, nx, nu, h, A, Bm, z, Jc, work: WorkList):
+    _call("gf_ocp_jac_banded", z.shape[0], S, nx, nu, h, ptr(A), ptr(Bm), ptr(z), ptr(Jc), *_w(work))
+
+
+def ocp_hess_diag(S, nx, nu, c1, Q, R, z, y, Hd, work: WorkList):
+    _call("gf_ocp_hess_diag", z.shape[0], S, nx, nu, c1, ptr(Q), ptr(R), ptr(z), ptr(y), ptr(Hd), *_w(work))
+
+
+def stage_aug_lag_grad(S, nx, nu, Jc, grad, cons, y, rho, dL, jty, jtc, work: WorkList):
+    _call("gf_stage_aug_lag_grad", grad.shape[0], S, nx, nu, ptr(Jc), ptr(grad), ptr(cons), ptr(y), ptr(rho), ptr(dL),
+          ptr(jty), ptr(jtc), *_w(work))
+
+
+def stage_kkt_factor(S, nx, nu, Jc, Hd, active, dt, rho, Tinv, Lc, Uc, info, nneg, work: WorkList):
+    _call("gf_stage_kkt_factor", Hd.shape[0], S, nx, nu, ptr(Jc), ptr(Hd), ptr(active), ptr(dt), ptr(rho), ptr(Tinv),
+          ptr(Lc), ptr(Uc), ptr(info), ptr(nneg), *_w(work))
+
+
+def stage_kkt_solve(S, nx, nu, Jc, Hd, active, F, dt, rho, Tinv, Lc, Uc, sol, work: WorkList):
+    _call("gf_stage_kkt_solve", Hd.shape[0], S, nx, nu, ptr(Jc), ptr(Hd), ptr(active), ptr(F), ptr(dt), ptr(rho),
+          ptr(Tinv), ptr(Lc), ptr(Uc), ptr(sol), sol.shape[1], *_w(work))

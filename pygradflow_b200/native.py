@@ -51,6 +51,11 @@ SIGNATURES = {
     "gf_band_factor": [_I, _I, _I, _P, _P, _P] + _WORK,
     "gf_band_solve": [_I, _I, _I, _P, _P] + _WORK,
     "gf_band_permute": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I] + _WORK,
+    "gf_ocp_jac_banded": [_I, _I, _I, _I, _D, _P, _P, _P, _P] + _WORK,
+    "gf_ocp_hess_diag": [_I, _I, _I, _I, _D, _P, _P, _P, _P, _P] + _WORK,
+    "gf_stage_aug_lag_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_stage_kkt_factor": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_stage_kkt_solve": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I] + _WORK,
     "gf_ldexp": [_I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _P] + _WORK,
     "gf_h2d_sym_lower": [_P, _P, _I, _I, _I, _P],
     "gf_symmetrize_lower": [_P, _I, _I, _I, _P],

@@ -28,7 +28,10 @@ class NewtonKKTStepper:
         self.problem = problem
         p = problem
         B, n, m, dev = p.B, p.n, p.m, p.device
-        self.engine = KKTEngine(B, n, m, dev, linear, band=problem.kkt_band())
+        from .params import StepSolverType
+
+        linear = problem.configure(linear, StepSolverType.Symmetric, False)
+        self.engine = KKTEngine(B, n, m, dev, linear, band=problem.kkt_band(), stage=problem.kkt_stage_structure())
         f64 = dict(dtype=torch.float64, device=dev)
         self.grad = torch.zeros((B, n), **f64)
         self.cons = torch.zeros((B, m), **f64)
@@ -43,8 +46,8 @@ class NewtonKKTStepper:
         self.diff = torch.zeros((B,), **f64)
         self.fnorm = torch.zeros((B,), **f64)
         self.dt = torch.zeros((B,), **f64)
-        self.Jbuf = [torch.zeros((B, m, n), **f64) for _ in range(2)] if (m > 0 and not p.jac_constant) else [None, None]
-        self.Hbuf = torch.zeros((B, n, n), **f64) if not p.hess_constant else None
+        self.Jbuf = [p.alloc_jac() for _ in range(2)] if (m > 0 and not p.jac_constant) else [None, None]
+        self.Hbuf = p.alloc_hess() if not p.hess_constant else None
         self.work = WorkList.all(B)
         self.events: Optional[Dict[str, list]] = None
 
@@ -81,7 +84,7 @@ class NewtonKKTStepper:
         K.dt_from_lamb(lamb, self.dt)
         prob.eval(x, self.grad, self.cons, self.obj, w)
         J = prob.jac(x, self.Jbuf[0], w) if m > 0 else None
-        K.aug_lag_grad(J, self.grad, cons, ym, rho, self.dL, None, None, w)
+        prob.aug_lag_grad(J, self.grad, cons, ym, rho, self.dL, None, None, w)
         if timing:
             t.append(self._mark())
         K.residual(x, ym, x, ym, self.dL, cons, prob.var_lb, prob.var_ub, self.dt, True, 0, eng.active, self.F, None, w)
@@ -95,17 +98,23 @@ class NewtonKKTStepper:
         self._factor_only(H, J, rho)
         if timing:
             t.append(self._mark())
-        K.kkt_rhs(H, J, eng.perm, eng.nI, self.F, self.dt, rho, eng.rhs, w)
-        eng.solve(eng.rhs, w)
-        if timing:
-            t.append(self._mark())
-        K.step_finish(x, ym, eng.rhs, eng.perm, eng.nI, self.F, self.dt, rho, prob.var_lb, prob.var_ub, self.xn,
-                      self.yn if m > 0 else None, None, None, self.diff, w)
+        if eng.linear == LinearSolverType.BlockTri:  # right-hand side, substitution and step finish in one engine call
+            eng.step(H, J, x, ym, self.F, self.dt, rho, prob.var_lb, prob.var_ub, self.xn, self.yn if m > 0 else None,
+                     self.diff, w)
+            if timing:
+                t.append(self._mark())
+        else:
+            K.kkt_rhs(H, J, eng.perm, eng.nI, self.F, self.dt, rho, eng.rhs, w)
+            eng.solve(eng.rhs, w)
+            if timing:
+                t.append(self._mark())
+            K.step_finish(x, ym, eng.rhs, eng.perm, eng.nI, self.F, self.dt, rho, prob.var_lb, prob.var_ub, self.xn,
+                          self.yn if m > 0 else None, None, None, self.diff, w)
         if timing:
             t.append(self._mark())
         prob.eval(self.xn, self.gn, self.cn, self.on, w)
         Jn = prob.jac(self.xn, self.Jbuf[1], w) if m > 0 else None
-        K.aug_lag_grad(Jn, self.gn, self.cn if m > 0 else None, self.yn if m > 0 else None, rho, self.dL, None, None, w)
+        prob.aug_lag_grad(Jn, self.gn, self.cn if m > 0 else None, self.yn if m > 0 else None, rho, self.dL, None, None, w)
         K.residual(self.xn, self.yn if m > 0 else None, x, ym, self.dL, self.cn if m > 0 else None, prob.var_lb,
                    prob.var_ub, self.dt, False, 0, None, None, self.fnorm, w)
         if timing:

@@ -32,6 +32,7 @@ class LinearSolverType(enum.Enum):
     LDLT = enum.auto()
     Auto = enum.auto()
     Banded = enum.auto()
+    BlockTri = enum.auto()  # stage-structured families (cfg4): Schur complement on the multipliers + block cyclic reduction
 
 
 class StepSolverType(enum.Enum):

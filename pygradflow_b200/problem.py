@@ -58,6 +58,31 @@ class BatchedProblem:
         n..n+m-1) under which the KKT matrix of every instance is banded; None for dense families."""
         return None
 
+    def kkt_stage_structure(self):
+        """Optional: (S, nx, nu) when the family currently hands out the compact stage layout of its derivatives
+        (block-bidiagonal Jacobian Jc [B, S*nx, nx + w], diagonal Hessian Hd [B, n]; include/gradflow_b200.h)."""
+        return None
+
+    def configure(self, linear, formulation, globalized: bool):
+        """Called once by the drivers before buffers are allocated: lets a family pick the layout of its derivatives
+        for the requested linear solver; returns the LinearSolverType the engine should use."""
+        return linear
+
+    def alloc_jac(self) -> Optional[torch.Tensor]:
+        """A buffer for ``jac`` (None for families with a constant Jacobian or without constraints)."""
+        if self.m == 0 or self.jac_constant:
+            return None
+        return torch.zeros((self.B, self.m, self.n), dtype=torch.float64, device=self.device)
+
+    def alloc_hess(self) -> Optional[torch.Tensor]:
+        if self.hess_constant:
+            return None
+        return torch.zeros((self.B, self.n, self.n), dtype=torch.float64, device=self.device)
+
+    def aug_lag_grad(self, J, grad, cons, y, rho, dL, jty, jtc, work: WorkList) -> None:
+        """Iterate.aug_lag_deriv_x (iterate.py:91-94): dL = grad + J'(rho c + y), optionally J'y and J'c."""
+        K.aug_lag_grad(J, grad, cons, y, rho, dL, jty, jtc, work)
+
 
 class BatchedQP(BatchedProblem):
     """f = x'Hx/2 + g'x, c = Ax + b (the reference's generic QP, tests/pygradflow/qp.py:4-30)."""
@@ -127,8 +152,10 @@ class BatchedOCP(BatchedProblem):
     """Discretised nonlinear optimal-control problems (cfg4): stage-interleaved variables
     z = (x_1, u_0, ..., x_S, u_{S-1}), equality dynamics, bounds on the controls only.
 
-    Device twin of the oracle's ``OCP`` class; J and H are kept dense (block-banded J, diagonal H), only their
-    non-zero entries are rewritten per evaluation."""
+    Device twin of the oracle's ``OCP`` class.  Two layouts of the derivatives: dense J [B, m, n] / H [B, n, n] (only
+    the non-zero entries are rewritten per evaluation; what the generic dense / banded engines read), and -- chosen by
+    ``configure`` for LinearSolverType.Auto / BlockTri with the Symmetric formulation -- the compact stage layout
+    Jc [B, S*nx, nx + w] / Hd [B, n] of the stage-structured engine (gf_stage_*), which never streams the zeros."""
 
     def __init__(self, A, Bm, Q, R, xinit, umax, h, device="cuda"):
         A, Bm, Q, R, xinit = (_dev(t, device) for t in (A, Bm, Q, R, xinit))
@@ -141,6 +168,35 @@ class BatchedOCP(BatchedProblem):
         self.A, self.Bm, self.Q, self.R, self.xinit = A, Bm, Q, R, xinit
         self.S, self.nx, self.nu, self.h, self.umax = S, nx, nu, float(h), float(umax)
         self._zeroed = set()
+        self.compact = False
+
+    def configure(self, linear, formulation, globalized):
+        from .params import LinearSolverType, StepSolverType
+
+        ok = self.nx == 8 and formulation == StepSolverType.Symmetric and not globalized
+        if linear == LinearSolverType.BlockTri and not ok:
+            raise ValueError("LinearSolverType.BlockTri needs nx == 8, the Symmetric formulation and a non-globalized Newton method")
+        self.compact = ok and linear in (LinearSolverType.Auto, LinearSolverType.BlockTri)
+        return LinearSolverType.BlockTri if self.compact else linear
+
+    def kkt_stage_structure(self):
+        return (self.S, self.nx, self.nu) if self.compact else None
+
+    def alloc_jac(self):
+        if self.compact:
+            return torch.zeros((self.B, self.m, 2 * self.nx + self.nu), dtype=torch.float64, device=self.device)
+        return super().alloc_jac()
+
+    def alloc_hess(self):
+        if self.compact:
+            return torch.zeros((self.B, self.n), dtype=torch.float64, device=self.device)
+        return super().alloc_hess()
+
+    def aug_lag_grad(self, J, grad, cons, y, rho, dL, jty, jtc, work):
+        if self.compact:
+            K.stage_aug_lag_grad(self.S, self.nx, self.nu, J, grad, cons, y, rho, dL, jty, jtc, work)
+        else:
+            super().aug_lag_grad(J, grad, cons, y, rho, dL, jty, jtc, work)
 
     def _zero_once(self, out):
         if out.data_ptr() not in self._zeroed:  # the kernels write the non-zero pattern only
@@ -152,11 +208,17 @@ class BatchedOCP(BatchedProblem):
                    work)
 
     def jac(self, x, out, work):
+        if self.compact:
+            K.ocp_jac_banded(self.S, self.nx, self.nu, self.h, self.A, self.Bm, x, out, work)
+            return out
         self._zero_once(out)
         K.ocp_jac(self.S, self.nx, self.nu, self.h, self.A, self.Bm, x, out, work)
         return out
 
     def lag_hess(self, x, y, out, work):
+        if self.compact:
+            K.ocp_hess_diag(self.S, self.nx, self.nu, 0.1 * self.h, self.Q, self.R, x, y, out, work)
+            return out
         self._zero_once(out)
         K.ocp_hess(self.S, self.nx, self.nu, 0.1 * self.h, self.Q, self.R, x, y, out, work)
         return out
@@ -179,6 +241,7 @@ class BatchedOCP(BatchedProblem):
             setattr(q, name, getattr(self, name)[idx].contiguous())
         q.S, q.nx, q.nu, q.h, q.umax = self.S, self.nx, self.nu, self.h, self.umax
         q._zeroed = set()
+        q.compact = self.compact
         return q
 
 

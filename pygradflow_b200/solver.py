@@ -59,9 +59,12 @@ class BatchedSolver:
         self.graph_steps = max(1, int(graph_steps))  # captured units replayed between two reads of the running count
         p = problem
         B, n, m, dev = p.B, p.n, p.m, p.device
-        self.engine = KKTEngine(B, n, m, dev, self.params.linear_solver_type, band=problem.kkt_band(),
+        linear = problem.configure(self.params.linear_solver_type, self.params.step_solver_type,
+                                   self.params.newton_type == NewtonType.Globalized)
+        self.engine = KKTEngine(B, n, m, dev, linear, band=problem.kkt_band(),
                                 formulation=self.params.step_solver_type,
-                                inertia_correction=self.params.inertia_correction)
+                                inertia_correction=self.params.inertia_correction,
+                                stage=problem.kkt_stage_structure())
         # StandardStepSolver works on the unscaled implicit function (its own active-set test, F and F')
         self._standard = self.params.step_solver_type == StepSolverType.Standard
         self._scaled = not self._standard
@@ -101,9 +104,9 @@ class BatchedSolver:
         self.Hbuf = [None, None]
         exact = self.params.step_control_type == StepControlType.Exact
         if m > 0 and not p.jac_constant:
-            self.Jbuf = [torch.zeros((B, m, n), **f64) for _ in range(3 if exact else 2)]
+            self.Jbuf = [p.alloc_jac() for _ in range(3 if exact else 2)]
         if not p.hess_constant:
-            self.Hbuf = [torch.zeros((B, n, n), **f64) for _ in range(2)]
+            self.Hbuf = [p.alloc_hess() for _ in range(2)]
         if self._standard and m > 0:
             self._Hrho = [torch.empty((B, n, n), **f64) for _ in range(2)]
         self.newton_step_count = torch.zeros((1,), dtype=torch.int64, device=dev)
@@ -129,7 +132,7 @@ class BatchedSolver:
         return pt[3] if self.problem.m > 0 else None
 
     def _aug_grad(self, J, pt, dL, jty, jtc, work):
-        K.aug_lag_grad(J, pt[2], self._cons(pt), self._y(pt), self.rho, dL, jty, jtc, work)
+        self.problem.aug_lag_grad(J, pt[2], self._cons(pt), self._y(pt), self.rho, dL, jty, jtc, work)
 
     def solve(self, x0=None, y0=None, on_iteration: Optional[Callable] = None,
               max_outer: Optional[int] = None) -> BatchedResult:
