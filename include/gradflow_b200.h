@@ -264,31 +264,34 @@ int gf_band_permute(int B, int n, int m, int ld, const int32_t* perm, const int3
                     void* stream);
 
 /* ---- stage-structured KKT systems (cfg4: discretised optimal control, n = S (nx + nu), m = S nx; nx == 8) ------------
- * Compact layouts: Jc [B, S*nx, nx + w], w = nx + nu -- row j nx + r of c_j holds d c_j / d x_j (variables (j-1) w + c, zero
- * block for j = 0) in columns 0..nx-1 and d c_j / d z_j (variables j w + c) in columns nx..nx+w-1; Hd [B, n] the DIAGONAL
- * Hessian of the Lagrangian.  gf_ocp_jac_banded / gf_ocp_hess_diag are the compact twins of gf_ocp_jac / gf_ocp_hess;
- * gf_stage_aug_lag_grad is gf_aug_lag_grad (iterate.py:91-94,125,138,171) on the compact Jacobian.
+ * Compact layouts: Jc [B, S, nx + w, nx], w = nx + nu, column-major inside a stage -- Jc[b][j][c][r] = d c_{j,r} / d (column
+ * c), columns 0..nx-1 = x_j (variables (j-1) w + c, zero block for j = 0), columns nx..nx+w-1 = z_j (variables j w + c - nx);
+ * Hd [B, n] the DIAGONAL Hessian of the Lagrangian.  gf_ocp_jac_banded / gf_ocp_hess_diag are the compact twins of
+ * gf_ocp_jac / gf_ocp_hess (diag_only != 0: Jc already holds the Jacobian of an earlier point, only the entries that
+ * depend on z are rewritten); gf_stage_aug_lag_grad is gf_aug_lag_grad (iterate.py:91-94,125,138,171) on the compact
+ * Jacobian.
  * gf_stage_kkt_factor replaces symmetric_step_solver.py:27-77 + lu_solver.py:9-17 for such families: it forms the Schur
  * complement on the multipliers M = delta I + J_I (H_II + lamb I)^-1 J_I' (SPD, block tridiagonal with S blocks of
  * nx x nx; the same "primal variables first" elimination order as the dense LDL') and factorises it by block cyclic
- * reduction -- Tinv / Lc / Uc [B, S, nx*nx] receive the inverse pivot block and the two couplings of every block at the
- * level where it is eliminated; info = 0, -2 (some H_ii + lamb <= 0: K not quasi-definite) or k > 0 (pivot breakdown).
+ * reduction -- Tinv / P / Q [B, S, nx*nx] receive, for every block i, the inverse pivot block and Tinv K[i, i -/+ s] at the
+ * level s where it is eliminated; nu must be a multiple of 4, <= 16; info = 0, -2 (some H_ii + lamb <= 0: K not
+ * quasi-definite) or k > 0 (pivot breakdown).
  * gf_stage_kkt_solve does scaled_step_solver.py:38-60,91-97 + symmetric_step_solver.py:79-121 + lu_solver.py:19-21 for
  * the scaled residual F: sol [B, ldsol] = (dx in the natural order with dx_A = dt F_x[A], sy); gf_step_finish with the
  * identity permutation and nI = n finishes the step. */
 int gf_ocp_jac_banded(int B, int S, int nx, int nu, double h, const double* A, const double* Bm, const double* z,
-                      double* Jc, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+                      double* Jc, int diag_only, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 int gf_ocp_hess_diag(int B, int S, int nx, int nu, double c1, const double* Q, const double* R, const double* z,
                      const double* y, double* Hd, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 int gf_stage_aug_lag_grad(int B, int S, int nx, int nu, const double* Jc, const double* grad, const double* cons,
                           const double* y, const double* rho, double* dL, double* jty, double* jtc, const int32_t* work,
                           const int32_t* nwork_dev, int nwork, void* stream);
 int gf_stage_kkt_factor(int B, int S, int nx, int nu, const double* Jc, const double* Hd, const uint8_t* active,
-                        const double* dt, const double* rho, double* Tinv, double* Lc, double* Uc, int32_t* info,
+                        const double* dt, const double* rho, double* Tinv, double* P, double* Q, int32_t* info,
                         int32_t* nneg, const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 int gf_stage_kkt_solve(int B, int S, int nx, int nu, const double* Jc, const double* Hd, const uint8_t* active,
-                       const double* F, const double* dt, const double* rho, const double* Tinv, const double* Lc,
-                       const double* Uc, double* sol, int ldsol, const int32_t* work, const int32_t* nwork_dev, int nwork,
+                       const double* F, const double* dt, const double* rho, const double* Tinv, const double* P,
+                       const double* Q, double* sol, int ldsol, const int32_t* work, const int32_t* nwork_dev, int nwork,
                        void* stream);
 
 /* ---- host-buffer entry (the reference hands its step solver host arrays: scaled_step_solver.py:76-79) ---- */

@@ -8,12 +8,22 @@
 // cyclic reduction (log2 S levels instead of S NX sequential pivots): one CTA per matrix, NX x NX blocks inverted by
 // in-warp Gauss-Jordan (four blocks per warp, width-8 shuffles), block products on the FP64 tensor pipe (DMMA 8x8x4).
 //
-// Compact layouts (per instance): Jc [S*NX, NX + w], w = NX + nu: row i = j NX + r of c_j holds d c_j / d x_j in columns
-// 0..NX-1 (variables (j-1) w + c; zero block for j = 0) and d c_j / d z_j in columns NX..NX+w-1 (variables j w + c);
-// Hd [n] the diagonal of the Hessian.  Factors: Tinv / Lc / Uc [S, NX*NX] (inverse pivot block, coupling to the left /
-// from the right neighbour at the level where block i is eliminated).
+// Compact layouts (per instance): Jc [S, NX + w, NX], w = NX + nu, column-major inside a stage: Jc[j][c][r] =
+// d c_{j,r} / d (column c), columns 0..NX-1 = x_j (variables (j-1) w + c; zero block for j = 0), columns NX..NX+w-1 = z_j
+// (variables j w + c - NX) -- row sums (J v), column sums (J' v) and DMMA fragments all read it coalesced; Hd [n] the
+// diagonal of the Hessian.  Factors per block i, eliminated at level s = lowbit(i) with neighbours i - s and i + s:
+// Tinv = inv(T_i), P = Tinv K[i, i-s], Q = Tinv K[i, i+s]   ([S, NX*NX] each; block 0 is the last one, P = Q = 0).
 #include "gf_common.cuh"
 #include "../../include/gradflow_b200.h"
+
+#ifdef GF_STAGE_TRACE
+__device__ unsigned long long g_stage_trace[32];
+#define ST_DECL long long st_t_ = clock64()
+#define ST_MARK(i) do { if (threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_stage_trace[i], (unsigned long long)(n_ - st_t_)); st_t_ = n_; } } while (0)
+#else
+#define ST_DECL
+#define ST_MARK(i)
+#endif
 
 namespace {
 
@@ -21,9 +31,11 @@ constexpr int NX = 8;          // states per stage = block size of M
 constexpr int BS = NX * NX;    // doubles per block
 
 // ---- compact evaluators of the OCP family (same arithmetic as ocp_jac_kernel / ocp_hess_kernel of gf_eval.cu) ----
+// diag_only != 0: the buffer already holds the Jacobian of an earlier point; only the entries that depend on z -- the
+// diagonal of d c_j / d x_j, through cos x_j -- are rewritten.
 __global__ void ocp_jac_banded_kernel(int S, int nx, int nu, double h, const double* __restrict__ A,
                                       const double* __restrict__ Bm, const double* __restrict__ z,
-                                      double* __restrict__ Jc, GfWork work) {
+                                      double* __restrict__ Jc, int diag_only, GfWork work) {
     const int b = gf_instance(work, blockIdx.x);
     if (b < 0) return;
     const int w = nx + nu, n = S * w, jw = nx + w;
@@ -31,15 +43,25 @@ __global__ void ocp_jac_banded_kernel(int S, int nx, int nu, double h, const dou
     const double* Ab = A + (size_t)b * S * nx * nx;
     const double* Bb = Bm + (size_t)b * S * nx * nu;
     double* Jb = Jc + (size_t)b * S * nx * jw;
+    if (diag_only) {
+        for (int e = threadIdx.x; e < S * nx; e += blockDim.x) {
+            const int j = e / nx, r = e - j * nx;
+            if (j == 0) continue;
+            const double xe = zb[(size_t)(j - 1) * w + r];
+            const double ee = __dmul_rn(h, __dadd_rn(Ab[((size_t)j * nx + r) * nx + r], __dmul_rn(1.0, __dmul_rn(0.1, cos(xe)))));
+            Jb[((size_t)j * jw + r) * nx + r] = -__dadd_rn(1.0, ee);
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < S * nx * jw; e += blockDim.x) {
-        const int i = e / jw, c = e - i * jw, j = i / nx, r = i - j * nx;
+        const int j = e / (nx * jw), t = e - j * nx * jw, c = t / nx, r = t - c * nx;
         double v;
         if (c < nx) {  // d c_j / d x_j
             if (j >= 1) {
                 const double d = (r == c) ? 1.0 : 0.0;
-                const double xe = zb[(size_t)(j - 1) * w + c];
-                const double ee = __dmul_rn(h, __dadd_rn(Ab[((size_t)j * nx + r) * nx + c],
-                                                        __dmul_rn(d, __dmul_rn(0.1, cos(xe)))));
+                double cs = 0.0;
+                if (r == c) cs = __dmul_rn(0.1, cos(zb[(size_t)(j - 1) * w + c]));
+                const double ee = __dmul_rn(h, __dadd_rn(Ab[((size_t)j * nx + r) * nx + c], __dmul_rn(d, cs)));
                 v = -__dadd_rn(d, ee);
             } else {
                 v = 0.0;
@@ -74,28 +96,29 @@ __global__ void ocp_hess_diag_kernel(int S, int nx, int nu, double c1, const dou
     }
 }
 
-// (J' v)_i for variable i = j w + k: rows of c_j (own block, column NX + k) and, for a state, rows of c_{j+1} (column k).
+// (J' v)_i for variable i = j w + k: column NX + k of stage j and, for a state, column k of stage j + 1; the NX entries of
+// a column are contiguous (two 32-byte sectors).
 __device__ __forceinline__ void jt_gather3(const double* __restrict__ Jb, int S, int w, int jw, int i,
                                            const double* v0, const double* v1, const double* v2, double& o0, double& o1,
                                            double& o2) {
     const int j = i / w, k = i - j * w;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    const double* col = Jb + (size_t)j * NX * jw + NX + k;
+    const double* col = Jb + ((size_t)j * jw + NX + k) * NX;
 #pragma unroll
-    for (int r = 0; r < NX; r++) {
-        const double e = col[(size_t)r * jw];
-        a0 += e * v0[j * NX + r];
-        if (v1) a1 += e * v1[j * NX + r];
-        if (v2) a2 += e * v2[j * NX + r];
+    for (int r = 0; r < NX; r += 2) {
+        const double2 e = *reinterpret_cast<const double2*>(col + r);
+        a0 += e.x * v0[j * NX + r] + e.y * v0[j * NX + r + 1];
+        if (v1) a1 += e.x * v1[j * NX + r] + e.y * v1[j * NX + r + 1];
+        if (v2) a2 += e.x * v2[j * NX + r] + e.y * v2[j * NX + r + 1];
     }
     if (k < NX && j + 1 < S) {
-        const double* colp = Jb + (size_t)(j + 1) * NX * jw + k;
+        const double* colp = Jb + ((size_t)(j + 1) * jw + k) * NX;
 #pragma unroll
-        for (int r = 0; r < NX; r++) {
-            const double e = colp[(size_t)r * jw];
-            a0 += e * v0[(j + 1) * NX + r];
-            if (v1) a1 += e * v1[(j + 1) * NX + r];
-            if (v2) a2 += e * v2[(j + 1) * NX + r];
+        for (int r = 0; r < NX; r += 2) {
+            const double2 e = *reinterpret_cast<const double2*>(colp + r);
+            a0 += e.x * v0[(j + 1) * NX + r] + e.y * v0[(j + 1) * NX + r + 1];
+            if (v1) a1 += e.x * v1[(j + 1) * NX + r] + e.y * v1[(j + 1) * NX + r + 1];
+            if (v2) a2 += e.x * v2[(j + 1) * NX + r] + e.y * v2[(j + 1) * NX + r + 1];
         }
     }
     o0 = a0; o1 = a1; o2 = a2;
@@ -131,7 +154,7 @@ __global__ void stage_aug_lag_grad_kernel(int S, int nu, const double* __restric
     }
 }
 
-// ---- 8x8 block primitives (row-major blocks of 64 doubles in shared memory) --------------------------------------
+// ---- 8x8 block primitives (row-major blocks of 64 doubles) ---------------------------------------------------------
 // D (C-fragment registers) += sign * op(A) op(B); TA / TB: use the transpose of the stored block.
 template <bool TA, bool TB, bool NEG>
 __device__ __forceinline__ void blk_mma(double& c0, double& c1, const double* A, const double* B) {
@@ -139,21 +162,30 @@ __device__ __forceinline__ void blk_mma(double& c0, double& c1, const double* A,
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int kk = q + 4 * h;
-        double a = TA ? A[kk * NX + g] : A[g * NX + kk];   // a = opA[g][kk]
+        double a = TA ? A[kk * NX + g] : A[g * NX + kk];        // a = opA[g][kk]
         const double bv = TB ? B[g * NX + kk] : B[kk * NX + g];  // b = opB[kk][g]
         if (NEG) a = -a;
         dmma884(c0, c1, a, bv);
     }
 }
+// C-fragment <-> memory: lane t owns elements 2t, 2t + 1 of the row-major block (a coalesced 512-byte access)
 __device__ __forceinline__ void blk_load_c(double& c0, double& c1, const double* C) {
-    const int t = threadIdx.x & 31, g = t >> 2, q = t & 3;
-    c0 = C[g * NX + 2 * q];
-    c1 = C[g * NX + 2 * q + 1];
+    const double2 v = *reinterpret_cast<const double2*>(C + 2 * (threadIdx.x & 31));
+    c0 = v.x; c1 = v.y;
 }
 __device__ __forceinline__ void blk_store_c(double c0, double c1, double* C) {
-    const int t = threadIdx.x & 31, g = t >> 2, q = t & 3;
-    C[g * NX + 2 * q] = c0;
-    C[g * NX + 2 * q + 1] = c1;
+    *reinterpret_cast<double2*>(C + 2 * (threadIdx.x & 31)) = make_double2(c0, c1);
+}
+
+// 1 / d to ~1 ulp: MUFU seed + two Newton steps (the reciprocal sits on the pivot-to-pivot chain)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
 }
 
 // In-place inverse of an SPD 8x8 block by Gauss-Jordan without pivoting; the 8 lanes of a width-8 group hold one row
@@ -167,14 +199,12 @@ __device__ __forceinline__ bool gj_inverse8(double (&a)[NX], int r) {
         for (int c = 0; c < NX; c++) rk[c] = __shfl_sync(0xffffffffu, a[c], k, NX);
         const double p = rk[k];
         if (!(p > 0.0) || !(p < 1.0e300)) ok = false;
-        const double pinv = __drcp_rn(p);
-        if (r == k) {
+        const double pinv = fast_rcp(p);
+        const double f = (r == k) ? 0.0 : a[k] * pinv;    // row k itself: scaled below
 #pragma unroll
-            for (int c = 0; c < NX; c++) a[c] = (c == k) ? pinv : a[c] * pinv;
-        } else {
-            const double f = a[k] * pinv;
-#pragma unroll
-            for (int c = 0; c < NX; c++) a[c] = (c == k) ? -f : a[c] - f * rk[c];
+        for (int c = 0; c < NX; c++) {
+            if (c == k) a[c] = (r == k) ? pinv : -f;
+            else a[c] = (r == k) ? a[c] * pinv : fma(-f, rk[c], a[c]);
         }
     }
     return ok;
@@ -185,22 +215,23 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
                                                            const double* __restrict__ Hd,
                                                            const uint8_t* __restrict__ active,
                                                            const double* __restrict__ dt, const double* __restrict__ rho,
-                                                           double* __restrict__ Tinv, double* __restrict__ Lc,
-                                                           double* __restrict__ Uc, int32_t* __restrict__ info,
+                                                           double* __restrict__ Tinv, double* __restrict__ Pf,
+                                                           double* __restrict__ Qf, int32_t* __restrict__ info,
                                                            int32_t* __restrict__ nneg, GfWork work) {
     const int b = gf_instance(work, blockIdx.x);
     if (b < 0) return;
     const int w = NX + nu, n = S * w, m = S * NX, jw = NX + w;
     extern __shared__ double sm[];
-    double* T = sm;                    // [S][64]
-    double* C = T + (size_t)S * BS;    // [S][64]
+    double* T = sm;                    // [S][64]  diagonal blocks; the inverse once a block is eliminated
+    double* C = T + (size_t)S * BS;    // [S][64]  coupling of block i to its current left neighbour, K[i, i - s]
     double* invD = C + (size_t)S * BS; // [n]
     const int nwarp = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* stg = invD + n + (size_t)wid * (2 * NX * jw + BS);  // per warp: rows of stage j-1 and j (2 x NX x jw), X (64)
+    double* X = invD + n + (size_t)wid * BS;  // per-warp 8x8 scratch
     __shared__ int s_bad;
     if (threadIdx.x == 0) s_bad = 0;
     const double lamb = 1.0 / dt[b];
     const double delta = lamb / (1.0 + lamb * rho[b]);
+    ST_DECL;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const bool act = active[(size_t)b * n + i] != 0;
@@ -209,38 +240,45 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
         invD[i] = act ? 0.0 : 1.0 / d;
     }
     __syncthreads();
-    // ---- M blocks, one stage per warp at a time: rows of c_{j-1} (slot 0) and c_j (slot 1) staged in shared memory
+    ST_MARK(0);
+    // ---- M blocks by DMMA straight from the compact Jacobian: with A = J D^-1 (8 x K) and B = J' (K x 8) the a- and
+    // b-fragments of a k-step are the SAME element J[g][kk] (scaled for a), one coalesced load each.
     const double* Jb = Jc + (size_t)b * m * jw;
-    for (int j = wid; j < S; j += nwarp) {
-        double* R0 = stg;             // c_{j-1}
-        double* R1 = stg + NX * jw;   // c_j
-        for (int e = lane; e < NX * jw; e += 32) {
-            R1[e] = Jb[(size_t)j * NX * jw + e];
-            R0[e] = j >= 1 ? Jb[(size_t)(j - 1) * NX * jw + e] : 0.0;
-        }
-        __syncwarp();
-        for (int e = lane; e < BS; e += 32) {
-            const int r = e >> 3, c = e & 7;
-            double acc = (r == c) ? delta : 0.0, accs = 0.0;
-            for (int k = 0; k < w; k++) acc += R1[r * jw + NX + k] * R1[c * jw + NX + k] * invD[j * w + k];
+    {
+        const int g = lane >> 2, q = lane & 3;
+        for (int j = wid; j < S; j += nwarp) {
+            const double* Js = Jb + (size_t)j * jw * NX;         // stage j: [jw][NX]
+            double t0 = (g == 2 * q) ? delta : 0.0, t1 = (g == 2 * q + 1) ? delta : 0.0, c0 = 0.0, c1 = 0.0;
+            double v[8], vp[2];
+            const int nk = jw / 4;  // k-steps of four columns (jw = 2 NX + nu; nu a multiple of 4 is required)
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++)
+                if (ks < nk) v[ks] = Js[(size_t)(4 * ks + q) * NX + g];
             if (j >= 1) {
 #pragma unroll
-                for (int k = 0; k < NX; k++) {
-                    const double sr = R1[r * jw + k] * invD[(j - 1) * w + k];
-                    acc += sr * R1[c * jw + k];
-                    accs += sr * R0[c * jw + NX + k];   // M_{j,j-1}[r][c]
+                for (int ks = 0; ks < 2; ks++) vp[ks] = Jb[((size_t)(j - 1) * jw + NX + 4 * ks + q) * NX + g];
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                if (ks < nk) {
+                    const int col = 4 * ks + q;
+                    double sc;
+                    if (col < NX) sc = j >= 1 ? invD[(j - 1) * w + col] : 0.0;
+                    else sc = invD[j * w + col - NX];
+                    const double a = v[ks] * sc;
+                    dmma884(t0, t1, a, v[ks]);
+                    if (ks < 2 && j >= 1) dmma884(c0, c1, a, vp[ks]);   // M_{j,j-1} = (Jp_j D^-1) Jz_{j-1}[:, x part]'
                 }
             }
-            T[(size_t)j * BS + e] = acc;
-            C[(size_t)j * BS + e] = accs;
+            blk_store_c(t0, t1, T + (size_t)j * BS);
+            blk_store_c(c0, c1, C + (size_t)j * BS);
         }
-        __syncwarp();
     }
     __syncthreads();
+    ST_MARK(1);
     double* Tg = Tinv + (size_t)b * S * BS;
-    double* Lg = Lc + (size_t)b * S * BS;
-    double* Ug = Uc + (size_t)b * S * BS;
-    double* X = stg + 2 * NX * jw;  // per-warp 8x8 scratch
+    double* Pg = Pf + (size_t)b * S * BS;
+    double* Qg = Qf + (size_t)b * S * BS;
     const int grp = lane >> 3, row = lane & 7;
     // ---- block cyclic reduction
     for (int s = 1; s < S; s <<= 1) {
@@ -257,16 +295,13 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
             if (have) {
                 if (!ok) atomicExch(&s_bad, i * NX + 1);
 #pragma unroll
-                for (int c = 0; c < NX; c++) {
-                    T[(size_t)i * BS + row * NX + c] = a[c];
-                    Tg[(size_t)i * BS + row * NX + c] = a[c];
-                    Lg[(size_t)i * BS + row * NX + c] = C[(size_t)i * BS + row * NX + c];
-                    Ug[(size_t)i * BS + row * NX + c] = (i + s < S) ? C[(size_t)(i + s) * BS + row * NX + c] : 0.0;
-                }
+                for (int c = 0; c < NX; c++) T[(size_t)i * BS + row * NX + c] = a[c];
             }
         }
         __syncthreads();
-        // (b) remaining blocks k = 0, 2s, 4s, ...: Schur updates from the eliminated neighbours k - s and k + s
+        ST_MARK(2);
+        // (b) remaining blocks k = 0, 2s, 4s, ...: Schur updates from the eliminated neighbours k - s and k + s; the
+        // products Tinv K[i, .] they need are the factors P / Q of those blocks and go to global memory from here
         const int nrem = (S + 2 * s - 1) / (2 * s);
         for (int q = wid; q < nrem; q += nwarp) {
             const int k = 2 * s * q;
@@ -276,14 +311,15 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
             if (k >= s) {
                 const double* Ti = T + (size_t)(k - s) * BS;  // inverse
                 double x0 = 0.0, x1 = 0.0;
-                blk_mma<false, true, false>(x0, x1, Ti, Ck);   // X = Tinv C_k'
+                blk_mma<false, true, false>(x0, x1, Ti, Ck);   // X = Tinv C_k' = Q_{k-s}
                 blk_store_c(x0, x1, X);
+                blk_store_c(x0, x1, Qg + (size_t)(k - s) * BS);
                 __syncwarp();
                 blk_mma<false, false, true>(t0, t1, Ck, X);    // T_k -= C_k X
                 __syncwarp();
                 if (k >= 2 * s) {
                     x0 = 0.0; x1 = 0.0;
-                    blk_mma<false, false, false>(x0, x1, Ti, C + (size_t)(k - s) * BS);  // X = Tinv C_{k-s}
+                    blk_mma<false, false, false>(x0, x1, Ti, C + (size_t)(k - s) * BS);  // X = Tinv C_{k-s} = P_{k-s}
                     blk_store_c(x0, x1, X);
                     __syncwarp();
                     blk_mma<false, false, true>(n0, n1, Ck, X);  // C_k(new) = -C_k X
@@ -294,8 +330,10 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
                 const double* Ti = T + (size_t)(k + s) * BS;
                 const double* Ci = C + (size_t)(k + s) * BS;
                 double x0 = 0.0, x1 = 0.0;
-                blk_mma<false, false, false>(x0, x1, Ti, Ci);  // X = Tinv C_{k+s}
+                blk_mma<false, false, false>(x0, x1, Ti, Ci);  // X = Tinv C_{k+s} = P_{k+s}
                 blk_store_c(x0, x1, X);
+                blk_store_c(x0, x1, Pg + (size_t)(k + s) * BS);
+                if (k + 2 * s >= S) blk_store_c(0.0, 0.0, Qg + (size_t)(k + s) * BS);  // no right neighbour
                 __syncwarp();
                 blk_mma<true, false, true>(t0, t1, Ci, X);      // T_k -= C_{k+s}' X
                 __syncwarp();
@@ -304,6 +342,7 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
             blk_store_c(n0, n1, C + (size_t)k * BS);
         }
         __syncthreads();
+        ST_MARK(3);
     }
     // ---- the last block
     if (wid == 0) {
@@ -315,14 +354,14 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
         if (have) {
             if (!ok) atomicExch(&s_bad, 1);
 #pragma unroll
-            for (int c = 0; c < NX; c++) {
-                Tg[row * NX + c] = a[c];
-                Lg[row * NX + c] = 0.0;
-                Ug[row * NX + c] = 0.0;
-            }
+            for (int c = 0; c < NX; c++) T[row * NX + c] = a[c];
         }
     }
     __syncthreads();
+    // all inverses, coalesced; block 0 has no neighbours
+    for (int e = threadIdx.x; e < S * BS; e += blockDim.x) Tg[e] = T[e];
+    for (int e = threadIdx.x; e < BS; e += blockDim.x) { Pg[e] = 0.0; Qg[e] = 0.0; }
+    ST_MARK(4);
     if (threadIdx.x == 0) {
         info[b] = s_bad;
         nneg[b] = m;  // M positive definite <=> K has exactly m negative eigenvalues
@@ -330,12 +369,23 @@ __global__ void __launch_bounds__(256) stage_factor_kernel(int S, int nu, const 
 }
 
 // ---- solve: sol = (dx in the natural order with dx_A = b0, sy) for the scaled residual F --------------------------
+__device__ __forceinline__ double row_dot8(const double* __restrict__ Mrow, const double* v) {
+    const double4 a = *reinterpret_cast<const double4*>(Mrow), c = *reinterpret_cast<const double4*>(Mrow + 4);
+    return a.x * v[0] + a.y * v[1] + a.z * v[2] + a.w * v[3] + c.x * v[4] + c.y * v[5] + c.z * v[6] + c.w * v[7];
+}
+__device__ __forceinline__ double col_dot8(const double* __restrict__ M, int r, const double* v) {
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; c++) acc += M[c * NX + r] * v[c];
+    return acc;
+}
+
 __global__ void __launch_bounds__(256) stage_solve_kernel(int S, int nu, const double* __restrict__ Jc,
                                                           const double* __restrict__ Hd,
                                                           const uint8_t* __restrict__ active,
                                                           const double* __restrict__ F, const double* __restrict__ dt,
                                                           const double* __restrict__ rho, const double* __restrict__ Tinv,
-                                                          const double* __restrict__ Lc, const double* __restrict__ Uc,
+                                                          const double* __restrict__ Pf, const double* __restrict__ Qf,
                                                           double* __restrict__ sol, int ldsol, GfWork work) {
     const int b = gf_instance(work, blockIdx.x);
     if (b < 0) return;
@@ -343,99 +393,74 @@ __global__ void __launch_bounds__(256) stage_solve_kernel(int S, int nu, const d
     extern __shared__ double sm[];
     double* wv = sm;        // [n]  w_i = b0 (active) or D^-1 b1 (inactive); later dx
     double* rr = wv + n;    // [m]  right-hand side of M / solution sy
-    double* gg = rr + m;    // [m]  Tinv r of the eliminated blocks
     const double dtb = dt[b];
     const double lamb = 1.0 / dtb;
     const double fact = 1.0 / (1.0 + lamb * rho[b]);
     const double* Fb = F + (size_t)b * (n + m);
     const double* Jb = Jc + (size_t)b * m * jw;
+    ST_DECL;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const bool act = active[(size_t)b * n + i] != 0;
         const double fx = Fb[i];
         wv[i] = act ? __dmul_rn(dtb, fx) : fx / (Hd[(size_t)b * n + i] + lamb);   // scaled_step_solver.py:56-57
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {   // J w - fact F_y
-        const int j = i / NX;
-        const double* row = Jb + (size_t)i * jw;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {   // J w - fact F_y; the 8 rows of a stage read each column coalesced
+        const int j = i / NX, r = i - j * NX;
+        const double* Js = Jb + (size_t)j * jw * NX + r;
         double acc = 0.0;
-        for (int k = 0; k < w; k++) acc += row[NX + k] * wv[j * w + k];
+        for (int k = 0; k < w; k++) acc += Js[(size_t)(NX + k) * NX] * wv[j * w + k];
         if (j >= 1) {
 #pragma unroll
-            for (int k = 0; k < NX; k++) acc += row[k] * wv[(j - 1) * w + k];
+            for (int k = 0; k < NX; k++) acc += Js[(size_t)k * NX] * wv[(j - 1) * w + k];
         }
         rr[i] = acc - fact * Fb[n + i];
     }
     __syncthreads();
+    ST_MARK(8);
     const double* Tg = Tinv + (size_t)b * S * BS;
-    const double* Lg = Lc + (size_t)b * S * BS;
-    const double* Ug = Uc + (size_t)b * S * BS;
+    const double* Pg = Pf + (size_t)b * S * BS;
+    const double* Qg = Qf + (size_t)b * S * BS;
     const int r = threadIdx.x & 7, slot = threadIdx.x >> 3, nslot = blockDim.x >> 3;
-    const unsigned gmask = 0xffu << (threadIdx.x & 24);  // the 8 lanes of this slot (they branch together)
     int top = 1;
     while (top * 2 < S) top *= 2;
-    // forward elimination
+    // forward elimination: r_k -= K[k, k-s] Tinv_{k-s} r_{k-s} + K[k, k+s] Tinv_{k+s} r_{k+s} = Q_{k-s}' r_{k-s} + P_{k+s}' r_{k+s}
     for (int s = 1; s < S; s <<= 1) {
-        const int nel = (S - s + 2 * s - 1) / (2 * s);
-        for (int q = slot; q < nel; q += nslot) {
-            const int i = s + 2 * s * q;
-            const double* Ti = Tg + (size_t)i * BS + r * NX;
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < NX; c++) acc += Ti[c] * rr[i * NX + c];
-            gg[i * NX + r] = acc;
-        }
-        __syncthreads();
         const int nrem = (S + 2 * s - 1) / (2 * s);
         for (int q = slot; q < nrem; q += nslot) {
             const int k = 2 * s * q;
             double acc = 0.0;
-            if (k >= s) {
-                const double* Ui = Ug + (size_t)(k - s) * BS + r * NX;   // K[k, k-s]
-#pragma unroll
-                for (int c = 0; c < NX; c++) acc += Ui[c] * gg[(k - s) * NX + c];
-            }
-            if (k + s < S) {
-                const double* Li = Lg + (size_t)(k + s) * BS;             // K[k+s, k]: transpose applies
-#pragma unroll
-                for (int c = 0; c < NX; c++) acc += Li[c * NX + r] * gg[(k + s) * NX + c];
-            }
+            if (k >= s) acc += col_dot8(Qg + (size_t)(k - s) * BS, r, rr + (k - s) * NX);
+            if (k + s < S) acc += col_dot8(Pg + (size_t)(k + s) * BS, r, rr + (k + s) * NX);
             rr[k * NX + r] -= acc;
         }
         __syncthreads();
     }
-    if (slot == 0) {
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c < NX; c++) acc += Tg[r * NX + c] * rr[c];
-        gg[r] = acc;
-    }
-    __syncthreads();
-    if (slot == 0) rr[r] = gg[r];
-    __syncthreads();
-    // back substitution: v_i = g_i - Tinv_i (Lc_i v_{i-s} + Uc_i' v_{i+s})
-    for (int s = top; s >= 1; s >>= 1) {
-        const int nel = (S - s + 2 * s - 1) / (2 * s);
-        for (int q = slot; q < nel; q += nslot) {
-            const int i = s + 2 * s * q;
-            const double* Li = Lg + (size_t)i * BS + r * NX;
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < NX; c++) acc += Li[c] * rr[(i - s) * NX + c];
-            if (i + s < S) {
-                const double* Ui = Ug + (size_t)i * BS;
-#pragma unroll
-                for (int c = 0; c < NX; c++) acc += Ui[c * NX + r] * rr[(i + s) * NX + c];
-            }
-            // Tinv_i times the 8-vector held by the 8 threads of this slot
-            const double* Ti = Tg + (size_t)i * BS + r * NX;
-            double t = 0.0;
-#pragma unroll
-            for (int c = 0; c < NX; c++) t += Ti[c] * __shfl_sync(gmask, acc, c, NX);
-            rr[i * NX + r] = gg[i * NX + r] - t;
-        }
+    ST_MARK(9);
+    // back substitution: v_0 = Tinv_0 r_0;  v_i = Tinv_i r_i - P_i v_{i-s} - Q_i v_{i+s}
+    {
+        double v0 = 0.0;
+        if (slot == 0) v0 = row_dot8(Tg + r * NX, rr);
+        __syncthreads();
+        if (slot == 0) rr[r] = v0;
         __syncthreads();
     }
+    for (int s = top; s >= 1; s >>= 1) {
+        const int nel = (S - s + 2 * s - 1) / (2 * s);
+        double vals[4];
+        int cnt = 0;
+        for (int q = slot; q < nel; q += nslot) {
+            const int i = s + 2 * s * q;
+            double acc = row_dot8(Tg + (size_t)i * BS + r * NX, rr + i * NX) - row_dot8(Pg + (size_t)i * BS + r * NX, rr + (i - s) * NX);
+            if (i + s < S) acc -= row_dot8(Qg + (size_t)i * BS + r * NX, rr + (i + s) * NX);
+            vals[cnt++ & 3] = acc;
+        }
+        __syncthreads();   // every row of r_i has been read before it is overwritten by v_i
+        cnt = 0;
+        for (int q = slot; q < nel; q += nslot) rr[(s + 2 * s * q) * NX + r] = vals[cnt++ & 3];
+        __syncthreads();
+    }
+    ST_MARK(10);
     // dx_I = D^-1 (b1 - J' sy) = w - D^-1 J' sy; dx_A = b0
     double* out = sol + (size_t)b * ldsol;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -449,16 +474,18 @@ __global__ void __launch_bounds__(256) stage_solve_kernel(int S, int nu, const d
     }
     for (int i = threadIdx.x; i < m; i += blockDim.x) out[n + i] = rr[i];
     for (int i = n + m + threadIdx.x; i < ldsol; i += blockDim.x) out[i] = 0.0;
+    ST_MARK(11);
 }
 
 }  // namespace
 
 extern "C" int gf_ocp_jac_banded(int B, int S, int nx, int nu, double h, const double* A, const double* Bm,
-                                 const double* z, double* Jc, const int32_t* work, const int32_t* nwork_dev, int nwork,
-                                 void* stream) {
+                                 const double* z, double* Jc, int diag_only, const int32_t* work,
+                                 const int32_t* nwork_dev, int nwork, void* stream) {
     if (B <= 0 || S <= 0 || nx <= 0 || nu <= 0 || !A || !Bm || !z || !Jc) return GF_ERR_ARG;
     if (nwork <= 0) return GF_OK;
-    ocp_jac_banded_kernel<<<nwork, 512, 0, (cudaStream_t)stream>>>(S, nx, nu, h, A, Bm, z, Jc, GfWork{work, nwork_dev});
+    ocp_jac_banded_kernel<<<nwork, diag_only ? 256 : 512, 0, (cudaStream_t)stream>>>(S, nx, nu, h, A, Bm, z, Jc, diag_only,
+                                                                                      GfWork{work, nwork_dev});
     return gf_launch_status();
 }
 
@@ -493,10 +520,10 @@ extern "C" int gf_stage_kkt_factor(int B, int S, int nx, int nu, const double* J
                                    const int32_t* nwork_dev, int nwork, void* stream) {
     if (B <= 0 || S <= 0 || nu <= 0 || !Jc || !Hd || !active || !dt || !rho || !Tinv || !Lc || !Uc || !info || !nneg)
         return GF_ERR_ARG;
-    if (nx != NX) return GF_ERR_UNSUPPORTED;
+    if (nx != NX || (nu % 4) != 0 || nu > 16) return GF_ERR_UNSUPPORTED;
     if (nwork <= 0) return GF_OK;
-    const int w = NX + nu, jw = NX + w, threads = 256;
-    const size_t smem = ((size_t)2 * S * BS + (size_t)S * w + (size_t)(threads / 32) * (2 * NX * jw + BS)) * sizeof(double);
+    const int w = NX + nu, threads = 256;
+    const size_t smem = ((size_t)2 * S * BS + (size_t)S * w + (size_t)(threads / 32) * BS) * sizeof(double);
     if (smem > 220 * 1024) return GF_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(stage_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     stage_factor_kernel<<<nwork, threads, smem, (cudaStream_t)stream>>>(S, nu, Jc, Hd, active, dt, rho, Tinv, Lc, Uc, info,
@@ -514,7 +541,7 @@ extern "C" int gf_stage_kkt_solve(int B, int S, int nx, int nu, const double* Jc
     const int w = NX + nu, n = S * w, m = S * NX;
     if (ldsol < n + m) return GF_ERR_ARG;
     if (nwork <= 0) return GF_OK;
-    const size_t smem = (size_t)(n + 2 * m) * sizeof(double);
+    const size_t smem = (size_t)(n + m) * sizeof(double);
     if (smem > 200 * 1024) return GF_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) cudaFuncSetAttribute(stage_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     stage_solve_kernel<<<nwork, 256, smem, (cudaStream_t)stream>>>(S, nu, Jc, Hd, active, F, dt, rho, Tinv, Lc, Uc, sol,

@@ -136,7 +136,7 @@ class KKTEngine:
         i32 = dict(dtype=torch.int32, device=device)
         self.ld = n + m
         self.K = None
-        self.Tinv, self.Lc, self.Uc = (torch.zeros((B, S, nx * nx), **f64) for _ in range(3))
+        self.Tinv, self.Pf, self.Qf = (torch.zeros((B, S, nx * nx), **f64) for _ in range(3))
         self.rhs = torch.zeros((B, n + m), **f64)
         self.perm = torch.zeros((B, n), **i32)
         self.nI = torch.zeros((B,), **i32)
@@ -178,7 +178,7 @@ class KKTEngine:
             S, nx, nu = self.stage
             # info = -2: some H_ii + lamb <= 0, K is not quasi-definite -- reported like a failed factorisation (the step
             # is rejected and lambda doubled, step_control.py:102-104), as in Banded mode
-            K.stage_kkt_factor(S, nx, nu, J, H, self.active, dt, rho, self.Tinv, self.Lc, self.Uc, self.info, self.nneg,
+            K.stage_kkt_factor(S, nx, nu, J, H, self.active, dt, rho, self.Tinv, self.Pf, self.Qf, self.info, self.nneg,
                                work)
             return
         if self.linear == LinearSolverType.Banded:
@@ -308,7 +308,7 @@ class KKTEngine:
         """ScaledStepSolver.solve + StepResult for the current factor: rhs, substitution, step finish."""
         if self.linear == LinearSolverType.BlockTri:
             S, nx, nu = self.stage
-            K.stage_kkt_solve(S, nx, nu, J, H, self.active, F, dt, rho, self.Tinv, self.Lc, self.Uc, self.rhs, work)
+            K.stage_kkt_solve(S, nx, nu, J, H, self.active, F, dt, rho, self.Tinv, self.Pf, self.Qf, self.rhs, work)
             K.step_finish(xbase, ybase, self.rhs, self.perm_id, self.n_full, F, dt, rho, lb, ub, xn, yn, dx, dy, diff,
                           work)
             return

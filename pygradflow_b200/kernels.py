@@ -289,8 +289,9 @@ def band_permute(perm, nI, pos, stdv, bandv, to_band: bool, m: int, work: WorkLi
 
 
 # ---- stage-structured KKT systems (cfg4): compact Jacobian Jc [B, S*nx, nx + w], diagonal Hessian Hd [B, n] ----------
-def ocp_jac_banded(S, nx, nu, h, A, Bm, z, Jc, work: WorkList):
-    _call("gf_ocp_jac_banded", z.shape[0], S, nx, nu, h, ptr(A), ptr(Bm), ptr(z), ptr(Jc), *_w(work))
+def ocp_jac_banded(S, nx, nu, h, A, Bm, z, Jc, diag_only: bool, work: WorkList):
+    _call("gf_ocp_jac_banded", z.shape[0], S, nx, nu, h, ptr(A), ptr(Bm), ptr(z), ptr(Jc), 1 if diag_only else 0,
+          *_w(work))
 
 
 def ocp_hess_diag(S, nx, nu, c1, Q, R, z, y, Hd, work: WorkList):
@@ -302,11 +303,11 @@ def stage_aug_lag_grad(S, nx, nu, Jc, grad, cons, y, rho, dL, jty, jtc, work: Wo
           ptr(jty), ptr(jtc), *_w(work))
 
 
-def stage_kkt_factor(S, nx, nu, Jc, Hd, active, dt, rho, Tinv, Lc, Uc, info, nneg, work: WorkList):
+def stage_kkt_factor(S, nx, nu, Jc, Hd, active, dt, rho, Tinv, Pf, Qf, info, nneg, work: WorkList):
     _call("gf_stage_kkt_factor", Hd.shape[0], S, nx, nu, ptr(Jc), ptr(Hd), ptr(active), ptr(dt), ptr(rho), ptr(Tinv),
-          ptr(Lc), ptr(Uc), ptr(info), ptr(nneg), *_w(work))
+          ptr(Pf), ptr(Qf), ptr(info), ptr(nneg), *_w(work))
 
 
-def stage_kkt_solve(S, nx, nu, Jc, Hd, active, F, dt, rho, Tinv, Lc, Uc, sol, work: WorkList):
+def stage_kkt_solve(S, nx, nu, Jc, Hd, active, F, dt, rho, Tinv, Pf, Qf, sol, work: WorkList):
     _call("gf_stage_kkt_solve", Hd.shape[0], S, nx, nu, ptr(Jc), ptr(Hd), ptr(active), ptr(F), ptr(dt), ptr(rho),
-          ptr(Tinv), ptr(Lc), ptr(Uc), ptr(sol), sol.shape[1], *_w(work))
+          ptr(Tinv), ptr(Pf), ptr(Qf), ptr(sol), sol.shape[1], *_w(work))

@@ -51,7 +51,7 @@ SIGNATURES = {
     "gf_band_factor": [_I, _I, _I, _P, _P, _P] + _WORK,
     "gf_band_solve": [_I, _I, _I, _P, _P] + _WORK,
     "gf_band_permute": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I] + _WORK,
-    "gf_ocp_jac_banded": [_I, _I, _I, _I, _D, _P, _P, _P, _P] + _WORK,
+    "gf_ocp_jac_banded": [_I, _I, _I, _I, _D, _P, _P, _P, _P, _I] + _WORK,
     "gf_ocp_hess_diag": [_I, _I, _I, _I, _D, _P, _P, _P, _P, _P] + _WORK,
     "gf_stage_aug_lag_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_stage_kkt_factor": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,

@@ -173,9 +173,11 @@ class BatchedOCP(BatchedProblem):
     def configure(self, linear, formulation, globalized):
         from .params import LinearSolverType, StepSolverType
 
-        ok = self.nx == 8 and formulation == StepSolverType.Symmetric and not globalized
+        ok = (self.nx == 8 and self.nu % 4 == 0 and self.nu <= 16 and formulation == StepSolverType.Symmetric
+              and not globalized)
         if linear == LinearSolverType.BlockTri and not ok:
-            raise ValueError("LinearSolverType.BlockTri needs nx == 8, the Symmetric formulation and a non-globalized Newton method")
+            raise ValueError("LinearSolverType.BlockTri needs nx == 8, nu in {4, 8, 12, 16}, the Symmetric formulation and a "
+                             "non-globalized Newton method")
         self.compact = ok and linear in (LinearSolverType.Auto, LinearSolverType.BlockTri)
         return LinearSolverType.BlockTri if self.compact else linear
 
@@ -184,7 +186,7 @@ class BatchedOCP(BatchedProblem):
 
     def alloc_jac(self):
         if self.compact:
-            return torch.zeros((self.B, self.m, 2 * self.nx + self.nu), dtype=torch.float64, device=self.device)
+            return torch.zeros((self.B, self.S, 2 * self.nx + self.nu, self.nx), dtype=torch.float64, device=self.device)
         return super().alloc_jac()
 
     def alloc_hess(self):
@@ -209,7 +211,11 @@ class BatchedOCP(BatchedProblem):
 
     def jac(self, x, out, work):
         if self.compact:
-            K.ocp_jac_banded(self.S, self.nx, self.nu, self.h, self.A, self.Bm, x, out, work)
+            if out.data_ptr() not in self._zeroed:  # first touch: the constant entries, for every instance of the batch
+                K.ocp_jac_banded(self.S, self.nx, self.nu, self.h, self.A, self.Bm, x, out, False, WorkList.all(self.B))
+                self._zeroed.add(out.data_ptr())
+            else:                                   # afterwards only the entries that depend on x
+                K.ocp_jac_banded(self.S, self.nx, self.nu, self.h, self.A, self.Bm, x, out, True, work)
             return out
         self._zero_once(out)
         K.ocp_jac(self.S, self.nx, self.nu, self.h, self.A, self.Bm, x, out, work)

@@ -129,7 +129,7 @@ def test_batched_ocp_golden_reference(golden, newton):
 
 
 # ------------------------------------------------------------------ stage-structured engine (gf_blocktri.cu)
-@pytest.mark.parametrize("S,nu", [(1, 8), (2, 3), (5, 8), (16, 4), (37, 8), (128, 8)])
+@pytest.mark.parametrize("S,nu", [(1, 8), (2, 4), (5, 8), (16, 4), (37, 16), (128, 8)])
 def test_stage_layout_and_step_vs_oracle(S, nu):
     """Compact Jacobian / diagonal Hessian equal the dense ones entry by entry; J'v through the compact layout; one
     Newton-KKT step of the stage-structured engine (Schur complement on the multipliers + block cyclic reduction)
@@ -156,11 +156,17 @@ def test_stage_layout_and_step_vs_oracle(S, nu):
     Jc = prob.jac(zt, prob.alloc_jac(), w)
     Hc = prob.lag_hess(zt, yt, prob.alloc_hess(), w)
     wv = nx + nu
-    for j in range(S):
+    assert Jc.shape == (B, S, nx + wv, nx)
+    for j in range(S):   # Jc[b][j][c][r] = d c_{j,r} / d (column c): transposed stage blocks of the dense Jacobian
         rows = slice(j * nx, (j + 1) * nx)
-        assert torch.equal(Jc[:, rows, nx:], Jd[:, rows, j * wv:(j + 1) * wv])
+        assert torch.equal(Jc[:, j, nx:, :].transpose(1, 2), Jd[:, rows, j * wv:(j + 1) * wv])
         if j >= 1:
-            assert torch.equal(Jc[:, rows, :nx], Jd[:, rows, (j - 1) * wv:(j - 1) * wv + nx])
+            assert torch.equal(Jc[:, j, :nx, :].transpose(1, 2), Jd[:, rows, (j - 1) * wv:(j - 1) * wv + nx])
+    z2 = zt + 0.1   # a second evaluation into the same buffer rewrites only the x-dependent entries
+    Jc2 = prob.jac(z2, Jc, w).clone()
+    prob._zeroed.clear()
+    assert torch.equal(Jc2, prob.jac(z2, prob.alloc_jac(), w))
+    prob.jac(zt, Jc, w)
     assert torch.equal(Hc, torch.diagonal(Hd, dim1=1, dim2=2))
     grad, cons = torch.as_tensor(rng.standard_normal((B, n)), **f64), torch.as_tensor(rng.standard_normal((B, m)), **f64)
     rho = torch.as_tensor(10.0 ** rng.uniform(-6, 0, B), **f64)
