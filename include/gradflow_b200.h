@@ -309,6 +309,47 @@ int gf_ldexp(int B, int rows, int cols, const double* in, const int32_t* rw, int
 int gf_h2d_sym_lower(double* dst, const double* src_host, int cnt, int n, int blk, void* stream);
 int gf_symmetrize_lower(double* H, int cnt, int n, int blk, void* stream);
 
+/* ---- iterative LinearSolvers (linear_solver/gmres_solver.py:7-35, linear_solver/minres_solver.py:6-24) ----
+ * One CTA per instance runs the whole iteration of scipy.sparse.linalg.gmres / minres on the dense K[b] (order Nvec[b] or
+ * Nmax, row-major, ld >= Nmax) and overwrites rhs[B,ldr] with the solution.  info[b] = 0 on convergence, otherwise the
+ * iteration limit (the value scipy returns and the wrappers turn into LinearSolverError: gmres_solver.py:32-33,
+ * minres_solver.py:21-22); iters[b] (may be NULL) = matrix-vector products scipy's routine performs.
+ * scratch: gf_krylov_scratch_rows(method, restart) * ld doubles per instance (indexed by instance, not by work slot).
+ * GMRES: restart = 20 and rtol = 1e-5 are scipy's defaults, atol = 1e-8 and maxiter = N the wrapper's arguments;
+ * trans != 0 solves K' x = rhs (LinearSolver.solve(trans=True)).  The start vector (LinearSolver.solve(initial_sol=...),
+ * a zero-argument callable in the reference) is x0[B,ldr], or -- x0 == NULL, x0_mask[B,nmask] != NULL -- the vector
+ * AsymmetricStepSolver.initial_sol builds (asymmetric_step_solver.py:125-138): rhs[i] where x0_mask[i] is set (i < nmask),
+ * zero elsewhere; both NULL = no start vector.  With a start vector the wrapper's early return applies (:22-25).
+ * MINRES: shift 0, rtol = 1e-5, maxiter = 5 N, the matrix must be symmetric (minres_solver.py:9). */
+#define GF_KRYLOV_GMRES 0
+#define GF_KRYLOV_MINRES 1
+int gf_krylov_scratch_rows(int method, int restart);
+int gf_gmres_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, double* rhs, int ldr, const double* x0,
+                   const uint8_t* x0_mask, int nmask, int trans, int restart, double rtol, double atol, double* scratch,
+                   int32_t* info, int32_t* iters, const int32_t* work, const int32_t* nwork_dev, int nwork,
+                   void* stream);
+int gf_minres_solve(int B, int ld, int Nmax, const int32_t* Nvec, const double* K, double* rhs, int ldr, const double* x0,
+                    double rtol, double* scratch, int32_t* info, int32_t* iters, const int32_t* work,
+                    const int32_t* nwork_dev, int nwork, void* stream);
+
+/* ---- penalty strategies that look at the candidate iterate (penalty.py:115-255; veto of solver.py:357-378) ----
+ * gf_pareto_update: ParetoDecrease.update (penalty.py:136-168) for every instance of the work list whose last step was
+ * accepted (phase 2 / 3, status running), on the committed iterate: grad = obj_grad, jty = J'y, jtc = J'c (the products
+ * gf_aug_lag_grad delivers); rho[b] <- max(min(10 rho, bound), rho).  Never rejects.
+ * gf_filter_update: kind 0 = ObjectivePenaltyFilter (entry = (obj, |c|_inf)), kind 1 = LagrangianPenaltyFilter (entry =
+ * (|dL|^2 + |c|^2, |c|_2), dL = aug_lag_deriv_x of the candidate at the strategy's rho_pen[b], evaluated by the caller).
+ * The candidate of instance b is the `m` set (om, cm, dm) when phase[b] = GF_PHASE_ACCEPT_MID, the `f` set when
+ * GF_PHASE_ACCEPT_FINAL.  filt[B,cap,2] / nfilt[B] hold each instance's filter (PenaltyFilter.entries, penalty.py:176);
+ * a dominated candidate sets phase[b] = GF_PHASE_REJECT and rho_pen[b] *= 10 (penalty.py:209-210), otherwise the entry is
+ * inserted (dominated entries dropped) and rho[b] = rho_pen[b] (solver.py:364-369); overflow[b] = 1 if cap is too small. */
+int gf_pareto_update(int B, int n, int m, const double* grad, const double* cons, const double* jty, const double* jtc,
+                     const int32_t* phase, const int32_t* status, double opt_tol, double local_infeas_tol, double* rho,
+                     const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+int gf_filter_update(int B, int n, int m, int kind, int32_t* phase, const int32_t* status, const double* om,
+                     const double* cm, const double* dm, const double* of, const double* cf, const double* df,
+                     double* rho, double* rho_pen, double* filt, int32_t* nfilt, int cap, int32_t* overflow,
+                     const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
 /* helpers of the batched driver: ordered compaction of { b in parent (or 0..B-1) : (lo <= key[b] <= hi) != invert } */
 int gf_build_worklist(int B, const int32_t* key, int lo, int hi, int invert, const int32_t* parent,
                       const int32_t* parent_count, int32_t* list, int32_t* count, void* stream);

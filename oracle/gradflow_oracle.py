@@ -97,7 +97,8 @@ class OracleParams:
     step_control_type: str = "distance_ratio"  # distance_ratio | residuum_ratio | exact | fixed
     active_set_type: str = "standard"  # standard | explicit | smallest | largest  (params.py:14-18,225-227)
     active_set_tau: Optional[float] = None
-    penalty_update: str = "dual_norm"  # dual_norm | constant | dual_equilibration
+    # dual_norm | constant | dual_equilibration | pareto_decrease | objective_filter | lagrangian_filter
+    penalty_update: str = "dual_norm"
     iteration_limit: Optional[int] = None
     obj_lower_limit: float = -1e10
     inertia_correction: bool = False
@@ -956,6 +957,68 @@ class OracleLUSolver:
         return None
 
 
+class OracleIterativeSolver:
+    """linear_solver/gmres_solver.py:7-35 and linear_solver/minres_solver.py:6-24: the wrappers restated line by line
+    around the SAME third-party routines (scipy.sparse.linalg.gmres / minres, SciPy 1.18.1 here; the reference leaves
+    scipy unpinned).  ``matvecs`` counts the products of the last solve (the reference does not expose it; the CUDA
+    kernels report the same count)."""
+
+    def __init__(self, K, kind: str, symmetric: bool = False):
+        assert kind in ("gmres", "minres")
+        if kind == "minres":
+            assert symmetric, "MINRES requires a symmetric matrix"     # minres_solver.py:9
+        self.kind = kind
+        self.mat = scipy.sparse.csc_matrix(K)
+        self.N = self.mat.shape[0]
+        self.symmetric = symmetric
+        self.matvecs = 0
+
+    def _counted(self, mat):
+        def mv(v):
+            self.matvecs += 1
+            return mat @ v
+
+        return scipy.sparse.linalg.LinearOperator(mat.shape, matvec=mv, dtype=np.float64)
+
+    def solve(self, rhs, trans=False, initial_sol=None):
+        self.matvecs = 0
+        if self.N == 0:
+            return np.zeros(0)
+        if self.kind == "minres":
+            if initial_sol is not None:
+                initial_sol = initial_sol()
+            sol, info = scipy.sparse.linalg.minres(self._counted(self.mat), rhs, x0=initial_sol)
+            if info != 0:
+                raise LinearSolverError("MINRES failed with error code {}".format(info))
+            return sol
+        mat = self.mat.T if trans else self.mat
+        if initial_sol is not None:
+            initial_sol = initial_sol()
+        n = mat.shape[0]
+        atol = 1e-8
+        if initial_sol is not None:                                      # gmres_solver.py:22-25
+            res = rhs - mat @ initial_sol
+            if np.linalg.norm(res, ord=np.inf) < atol:
+                return initial_sol
+        sol, info = scipy.sparse.linalg.gmres(self._counted(mat), rhs, maxiter=n, x0=initial_sol, atol=atol)
+        if info != 0:
+            raise LinearSolverError("GMRES failed with error code {}".format(info))
+        return sol
+
+    def num_neg_eigvals(self):
+        return None
+
+    def rcond(self):
+        return None
+
+
+def make_linear_solver(K, kind: str, symmetric: bool):
+    """linear_solver/__init__.py:8-39."""
+    if kind in ("gmres", "minres"):
+        return OracleIterativeSolver(K, kind, symmetric=symmetric)
+    return OracleLUSolver(K, kind, symmetric=symmetric)
+
+
 class ConditionEstimator:
     """step/cond_estimate.py:13-114 (Dixon): 1/cond_2 from power iterations on A'A and (A'A)^-1, the latter through
     solve(trans=True) / solve of the factorised matrix; random start vectors from default_rng(42)."""
@@ -1120,7 +1183,7 @@ class SymmetricStepSolver:
         return self.dt * rx[A], rx[~A], ry
 
     def linear_solver(self, K):
-        return OracleLUSolver(K, self.params.linear_solver, symmetric=True)
+        return make_linear_solver(K, self.params.linear_solver, symmetric=True)
 
     def solve(self, iterate):
         """scaled_step_solver.py:85-107 + symmetric_step_solver.py:96-164."""
@@ -1179,7 +1242,18 @@ class AsymmetricStepSolver(SymmetricStepSolver):
         return K, rhs
 
     def linear_solver(self, K):
-        return OracleLUSolver(K, self.params.linear_solver, symmetric=False)
+        return make_linear_solver(K, self.params.linear_solver, symmetric=False)
+
+    def initial_sol(self, b0):
+        """asymmetric_step_solver.py:125-138 (None for the Extended solver, which passes none)."""
+        n, m, A = self.n, self.m, self.active_set
+
+        def initial_sol():
+            sol = np.zeros(n + m)
+            sol[:n][A] = b0
+            return sol
+
+        return initial_sol
 
     def solve(self, iterate):
         b0, b1, b2 = self.initial_rhs(iterate)
@@ -1194,7 +1268,7 @@ class AsymmetricStepSolver(SymmetricStepSolver):
             if self.solver is None:
                 self.solver = self.linear_solver(self.K)
                 self.num_factorizations += 1
-            s = self.solver.solve(rhs)
+            s = self.solver.solve(rhs, initial_sol=self.initial_sol(b0))
         except LinearSolverError as err:
             raise StepSolverError() from err
         self.last_rhs = rhs
@@ -1220,6 +1294,9 @@ class ExtendedStepSolver(AsymmetricStepSolver):
         K[n:, :n] = self.jac
         K[n:, n:] = (-lamb / (1.0 + lamb * self.rho)) * np.eye(m)
         return K, np.concatenate([b0, b1, b2t])
+
+    def initial_sol(self, b0):
+        return None                                                      # extended_step_solver.py:98: solve(rhs) only
 
 
 class StandardStepSolver:
@@ -1275,7 +1352,7 @@ class StandardStepSolver:
         rhs = self._func.value_at(iterate, self.rho, self.active_set)
         try:
             if self.solver is None:
-                self.solver = OracleLUSolver(self.K, self.params.linear_solver, symmetric=False)
+                self.solver = make_linear_solver(self.K, self.params.linear_solver, symmetric=False)
                 self.num_factorizations += 1
             s = self.solver.solve(rhs)
         except LinearSolverError as err:
@@ -1587,30 +1664,85 @@ def step_controller(problem, params):
 # Penalty (pygradflow/penalty.py:36-74)
 # --------------------------------------------------------------------------
 class Penalty:
+    """penalty.py:12-275: ``update(next_iterate)`` returns (next_rho, accept).  ``self.rho`` is the strategy's own
+    state; the solver only takes it over when the step is accepted (solver.py:357-369), so after a filter rejection
+    (penalty.py:209-210: rho *= 10, reject) the two differ until the next accepted step."""
+
     def __init__(self, problem, params):
         self.problem = problem
         self.params = params
         self.rho = params.rho
+        self.entries = []                                               # PenaltyFilter.entries (penalty.py:176)
+
+    def filter_insert(self, first, second):                            # penalty.py:179-192
+        entry = (first, second)
+
+        def dominates(a, b):
+            return a[0] <= b[0] and a[1] <= b[1]
+
+        if any(dominates(e, entry) for e in self.entries):
+            return False
+        self.entries = [e for e in self.entries if not dominates(entry, e)]
+        self.entries.append(entry)
+        return True
 
     def update(self, next_iterate):
-        if self.params.penalty_update == "constant":
-            return self.params.rho
-        if self.params.penalty_update == "dual_equilibration":         # penalty.py:77-113
+        kind = self.params.penalty_update
+        if kind == "constant":
+            return self.params.rho, True
+        if kind == "dual_equilibration":                                # penalty.py:77-113
             cons = next_iterate.cons
             yprod = abs(np.dot(next_iterate.y, cons))
             viol = 1.0 / 2.0 * np.dot(cons, cons)
             if viol == 0.0:
-                return self.rho
+                return self.rho, True
             target_rho = 0.01 * yprod / viol
             if self.rho < target_rho:
                 self.rho = max(self.rho * 10.0, target_rho)
-            return self.rho
+            return self.rho, True
+        if kind == "pareto_decrease":                                   # penalty.py:115-168
+            it, prm = next_iterate, self.params
+            cons = it.cons
+            viol = 1.0 / 2.0 * np.dot(cons, cons)
+            if viol <= prm.opt_tol:
+                return self.rho, True
+            J = it.cons_jac
+            infeas_opt_res = J.T.dot(cons)
+            if np.linalg.norm(infeas_opt_res, ord=np.inf) <= prm.local_infeas_tol:
+                return self.rho, True
+            obj_bound = np.inf
+            g = it.obj_grad
+            obj_prod = np.dot(g, infeas_opt_res)
+            cons_dual_prod = J.T.dot(it.y)
+            if abs(obj_prod) > 1e-10:
+                lhs = -(np.linalg.norm(g) + cons_dual_prod.dot(g))
+                obj_bound = lhs / obj_prod
+            lhs = -np.dot(infeas_opt_res, g + cons_dual_prod)
+            cons_bound = lhs / np.linalg.norm(infeas_opt_res)
+            bound = min(obj_bound, cons_bound)
+            assert np.isfinite(bound)
+            next_rho = max(min(self.rho * 10.0, bound), self.rho)
+            self.rho = next_rho
+            return self.rho, True
+        if kind in ("objective_filter", "lagrangian_filter"):           # penalty.py:170-255
+            it = next_iterate
+            if kind == "objective_filter":
+                entry = (it.obj, it.cons_violation)
+            else:
+                lag_x = it.aug_lag_deriv_x(self.rho)
+                lag_y = it.aug_lag_deriv_y()
+                entry = (np.dot(lag_x, lag_x) + np.dot(lag_y, lag_y), float(np.linalg.norm(it.cons)))
+            if self.filter_insert(*entry):
+                return self.rho, True
+            self.rho *= 10.0
+            return self.rho, False
+        assert kind == "dual_norm", kind
         if self.problem.num_cons == 0:                                  # penalty.py:46-74
-            return self.rho
+            return self.rho, True
         ynorm = float(np.max(np.abs(next_iterate.y)))
         if ynorm >= 10.0 * self.rho:
             self.rho = min(ynorm, 10.0 * self.rho)
-        return self.rho
+        return self.rho, True
 
 
 # --------------------------------------------------------------------------
@@ -1711,8 +1843,12 @@ class Solver:
                         theta=res.theta,
                     )
                 )
+            if accept:                                                  # solver.py:357-378
+                next_rho, accept = penalty.update(res.iterate)
+                if record:
+                    trace[-1]["penalty_accept"] = bool(accept)
             if accept:
-                rho = penalty.update(res.iterate)
+                rho = next_rho
                 iterate = res.iterate
                 accepted_steps += 1
             iteration += 1

@@ -47,10 +47,13 @@ class KKTEngine:
         N = n + m
         self.form = {StepSolverType.Symmetric: K.FORM_SYMMETRIC, StepSolverType.Asymmetric: K.FORM_ASYMMETRIC,
                      StepSolverType.Extended: K.FORM_EXTENDED, StepSolverType.Standard: K.FORM_STANDARD}[formulation]
+        self.iterative = linear in (LinearSolverType.GMRES, LinearSolverType.MINRES)
         if self.form != K.FORM_SYMMETRIC:
-            if linear not in (LinearSolverType.Auto, LinearSolverType.LU):
-                raise ValueError(f"step_solver_type={formulation.name} has an unsymmetric matrix: LU only")
-            linear = LinearSolverType.LU
+            if linear not in (LinearSolverType.Auto, LinearSolverType.LU, LinearSolverType.GMRES):
+                # minres_solver.py:9 asserts a symmetric matrix; the symmetric factorisations do not apply either
+                raise ValueError(f"step_solver_type={formulation.name} has an unsymmetric matrix: LU or GMRES only")
+            if linear != LinearSolverType.GMRES:
+                linear = LinearSolverType.LU
         if linear == LinearSolverType.BlockTri:
             self.linear = linear
             self._init_blocktri(stage)
@@ -62,7 +65,7 @@ class KKTEngine:
                 linear = LinearSolverType.LDLT
             else:
                 linear = LinearSolverType.LU if N <= SMALL_N else LinearSolverType.LDLT
-        if self.inertia_correction and linear == LinearSolverType.LU:
+        if self.inertia_correction and (linear == LinearSolverType.LU or self.iterative):
             # LUSolver.num_neg_eigvals() is None: symmetric_step_solver.py:149-150 raises the same way
             raise Exception("Inertia correction requested but not available")
         self.linear = linear
@@ -96,7 +99,18 @@ class KKTEngine:
             self.fbkey = torch.zeros((B,), **i32)  # 0: LDL' factor valid, != 0: pivoted-LU fallback
             self._ok = WorkList(torch.zeros((B,), **i32), torch.zeros((1,), **i32), B)
             self._fb = WorkList(torch.zeros((B,), **i32), torch.zeros((1,), **i32), B)
+        if self.iterative:
+            # gmres_solver.py / minres_solver.py: the "factorisation" only keeps the matrix; every solve runs the whole
+            # iteration (one CTA per instance) and may fail (info != 0 -> LinearSolverError -> the step is rejected)
+            rows = K.krylov_scratch_rows(linear == LinearSolverType.MINRES)
+            self.kscratch = torch.zeros((B, rows, self.ld), **f64)
+            self.kiters = torch.zeros((B,), **i32)
         self.n_factor_calls = 0
+
+    @property
+    def solve_can_fail(self) -> bool:
+        """True when LinearSolver.solve itself can raise (the iterative solvers), not only the constructor."""
+        return self.iterative
 
     def _init_banded(self, band):
         assert band is not None, "LinearSolverType.Banded needs a problem family with kkt_band()"
@@ -161,7 +175,7 @@ class KKTEngine:
             K.kkt_assemble_full(H, J, self.perm, self.nI, self.active, dt, rho, self.K, self.form, work)
         elif self.linear == LinearSolverType.Banded:
             K.band_assemble(H, J, self.active, self.order, self.bw, dt, rho, self.Kband, work)
-        elif self.linear == LinearSolverType.LU:
+        elif self.linear == LinearSolverType.LU or self.iterative:
             K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 1, False, work)
         elif not self.fuse_assembly:
             K.kkt_assemble(H, J, self.perm, self.nI, dt, rho, self.K, 64, True, work)
@@ -187,6 +201,9 @@ class KKTEngine:
             # reported like a failed factorisation (the step is rejected and lambda doubled, step_control.py:102-104)
             torch.where((self.info == 0) & (self.nneg != self.m), torch.full_like(self.info, -2), self.info,
                         out=self.info)
+            return
+        if self.iterative:
+            self.info.zero_()  # GMRESSolver / MINRESSolver constructors cannot fail
             return
         if self.linear == LinearSolverType.LU:
             K.lu_factor(self.K, Nmax, self._order(), self.piv, self.info, work)
@@ -229,6 +246,15 @@ class KKTEngine:
             K.band_permute(self.perm, self.nI, self.pos, rhs, self.bandv, True, self.m, work)
             K.band_solve(self.Kband, self.bw, self.bandv, work)  # symmetric: trans is irrelevant
             K.band_permute(self.perm, self.nI, self.pos, rhs, self.bandv, False, self.m, work)
+            return
+        if self.linear == LinearSolverType.GMRES:
+            # AsymmetricStepSolver hands GMRES its start vector (asymmetric_step_solver.py:125-138,154): b0 in the rows
+            # of the active variables, which is where rhs already holds it (:106-123)
+            mask = self.active if (self.form == K.FORM_ASYMMETRIC and rhs is self.rhs) else None
+            K.gmres_solve(self.K, Nmax, self._order(), rhs, None, mask, trans, self.kscratch, self.info, self.kiters, work)
+            return
+        if self.linear == LinearSolverType.MINRES:
+            K.minres_solve(self.K, Nmax, self._order(), rhs, None, self.kscratch, self.info, self.kiters, work)
             return
         if self.linear == LinearSolverType.LU:
             K.lu_solve(self.K, Nmax, self._order(), self.piv, rhs, trans, work)

@@ -140,6 +140,42 @@ def lu_solve(K, Nmax: int, Nvec, piv, rhs, trans: bool, work: WorkList):
           *_w(work))
 
 
+def pareto_update(grad, cons, jty, jtc, phase, status, opt_tol, local_infeas_tol, rho, work: WorkList):
+    """ParetoDecrease.update (penalty.py:136-168) on the committed iterates of the instances that just accepted."""
+    B, n = grad.shape
+    m = 0 if cons is None else cons.shape[1]
+    _call("gf_pareto_update", B, n, m, ptr(grad), ptr(cons), ptr(jty), ptr(jtc), ptr(phase), ptr(status), opt_tol,
+          local_infeas_tol, ptr(rho), *_w(work))
+
+
+def filter_update(kind: int, n: int, m: int, phase, status, om, cm, dm, of, cf, df, rho, rho_pen, filt, nfilt, overflow,
+                  work: WorkList):
+    """ObjectivePenaltyFilter (kind 0) / LagrangianPenaltyFilter (kind 1).update + the veto of solver.py:357-378."""
+    B = phase.shape[0]
+    _call("gf_filter_update", B, n, m, kind, ptr(phase), ptr(status), ptr(om), ptr(cm), ptr(dm), ptr(of), ptr(cf), ptr(df),
+          ptr(rho), ptr(rho_pen), ptr(filt), ptr(nfilt), filt.shape[1], ptr(overflow), *_w(work))
+
+
+def krylov_scratch_rows(minres: bool, restart: int = 20) -> int:
+    return native.load().gf_krylov_scratch_rows(1 if minres else 0, restart)
+
+
+def gmres_solve(K, Nmax: int, Nvec, rhs, x0, x0_mask, trans: bool, scratch, info, iters, work: WorkList,
+                restart: int = 20, rtol: float = 1e-5, atol: float = 1e-8):
+    """GMRESSolver.solve (gmres_solver.py:12-35): rhs <- solution; x0 / x0_mask = the start vector (see the header)."""
+    B, ld, _ = K.shape
+    nmask = 0 if x0_mask is None else x0_mask.shape[1]
+    _call("gf_gmres_solve", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(rhs), rhs.shape[1], ptr(x0), ptr(x0_mask), nmask,
+          1 if trans else 0, restart, rtol, atol, ptr(scratch), ptr(info), ptr(iters), *_w(work))
+
+
+def minres_solve(K, Nmax: int, Nvec, rhs, x0, scratch, info, iters, work: WorkList, rtol: float = 1e-5):
+    """MINRESSolver.solve (minres_solver.py:12-24): rhs <- solution."""
+    B, ld, _ = K.shape
+    _call("gf_minres_solve", B, ld, Nmax, ptr(Nvec), ptr(K), ptr(rhs), rhs.shape[1], ptr(x0), rtol, ptr(scratch),
+          ptr(info), ptr(iters), *_w(work))
+
+
 def ldlt_factor(K, Nmax: int, Nvec, dvec, info, nneg, npos_expected, work: WorkList):
     B, ld, _ = K.shape
     nblk = (Nmax + 63) // 64

@@ -59,6 +59,11 @@ SIGNATURES = {
     "gf_ldexp": [_I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _P] + _WORK,
     "gf_h2d_sym_lower": [_P, _P, _I, _I, _I, _P],
     "gf_symmetrize_lower": [_P, _I, _I, _I, _P],
+    "gf_krylov_scratch_rows": [_I, _I],
+    "gf_gmres_solve": [_I, _I, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _P, _P] + _WORK,
+    "gf_minres_solve": [_I, _I, _I, _P, _P, _P, _I, _P, _D, _P, _P, _P] + _WORK,
+    "gf_pareto_update": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _P] + _WORK,
+    "gf_filter_update": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P] + _WORK,
     "gf_build_worklist": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "gf_dt_from_lamb": [_I, _P, _P, _P],
 }

@@ -33,6 +33,8 @@ class LinearSolverType(enum.Enum):
     Auto = enum.auto()
     Banded = enum.auto()
     BlockTri = enum.auto()  # stage-structured families (cfg4): Schur complement on the multipliers + block cyclic reduction
+    GMRES = enum.auto()   # linear_solver/gmres_solver.py: scipy's restarted GMRES(20), atol 1e-8, at most n restarts
+    MINRES = enum.auto()  # linear_solver/minres_solver.py: scipy's MINRES (symmetric formulation only)
 
 
 class StepSolverType(enum.Enum):
@@ -77,12 +79,14 @@ class StepControlType(enum.Enum):
 
 
 class PenaltyUpdate(enum.Enum):
-    """pygradflow/params.py:122-128: the strategies that always accept the step (penalty.py:36-113); ParetoDecrease
-    and the filters, which may reject it, are out of scope."""
+    """pygradflow/params.py:122-128, penalty.py:36-255.  The two filters can veto an accepted step (solver.py:357-378)."""
 
     Constant = enum.auto()
     DualNorm = enum.auto()
     DualEquilibration = enum.auto()
+    ParetoDecrease = enum.auto()
+    ObjectiveFilter = enum.auto()
+    LagrangianFilter = enum.auto()
 
 
 def _enum_name(value) -> str:
@@ -121,6 +125,9 @@ class Params:
     obj_lower_limit: float = -1e10
     inertia_correction: bool = False
     report_rcond: bool = False
+    # entries each instance's penalty filter can hold (the reference's list is unbounded, penalty.py:176; the entries
+    # are mutually non-dominated, so the list stays far shorter than the number of accepted steps); exceeding it raises
+    penalty_filter_capacity: int = 1024
 
     def __post_init__(self):
         for key, cls in (("newton_type", NewtonType), ("linear_solver_type", LinearSolverType),
@@ -149,10 +156,14 @@ class Params:
             if hasattr(ref, f):
                 v = getattr(ref, f)
                 if f == "penalty_update" and _enum_name(v) not in PenaltyUpdate.__members__:
-                    raise ValueError(f"penalty_update={_enum_name(v)} is outside the B200 path (Constant / DualNorm / DualEquilibration)")
+                    raise ValueError(f"penalty_update={_enum_name(v)} is not a PenaltyUpdate")
                 if f == "step_solver_type" and _enum_name(v) not in StepSolverType.__members__:
                     raise ValueError(f"step_solver_type={_enum_name(v)} is outside the B200 path")
                 if f == "step_control_type" and _enum_name(v) not in StepControlType.__members__:
                     raise ValueError(f"step_control_type={_enum_name(v)} is outside the B200 path (Newton-based only)")
                 kw[f] = v
+        # the reference's direct solvers (LU, MA57, ...) map to the engine's own choice; its iterative ones carry over
+        lin = _enum_name(getattr(ref, "linear_solver_type", "Auto"))
+        if lin in ("GMRES", "MINRES"):
+            kw["linear_solver_type"] = LinearSolverType[lin]
         return Params(**kw)

@@ -82,8 +82,10 @@ def _one():
 class B200LinearSolver:
     """LinearSolver(matrix, symmetric=False): the constructor factorises, ``solve`` substitutes.
 
-    method: "lu" (pivoted, default for unsymmetric), "ldlt" (symmetric, inertia available), or None =
-    LDL' for symmetric input with a pivoted-LU fallback when a pivot breaks down or the factor grows."""
+    method: "lu" (pivoted, default for unsymmetric), "ldlt" (symmetric, inertia available), None =
+    LDL' for symmetric input with a pivoted-LU fallback when a pivot breaks down or the factor grows, or the
+    reference's iterative solvers "gmres" (gmres_solver.py:7-35, honours ``initial_sol`` and ``trans``) and "minres"
+    (minres_solver.py:6-24, symmetric matrices only) -- scipy's iterations, one CTA per system."""
 
     GROWTH_LIMIT = 1e8
 
@@ -104,6 +106,15 @@ class B200LinearSolver:
         i32 = dict(dtype=torch.int32, device=device)
         self.Nvec = torch.full((1,), N, **i32)
         self.info = torch.zeros((1,), **i32)
+        if method in ("gmres", "minres"):
+            # GMRESSolver / MINRESSolver (gmres_solver.py:8-10, minres_solver.py:7-10): keep the matrix, iterate in solve
+            assert method == "gmres" or symmetric, "MINRES requires a symmetric matrix"
+            self.K = _dev(mat, device).reshape(1, N, N)
+            rows = K.krylov_scratch_rows(method == "minres")
+            self.scratch = torch.zeros((1, rows, N), dtype=torch.float64, device=device)
+            self.iters = torch.zeros((1,), **i32)
+            self.method = method
+            return
         if want_ldlt:
             ld = max(((N + 63) // 64) * 64, 64)
             Kp = np.eye(ld)
@@ -137,7 +148,20 @@ class B200LinearSolver:
         ld = self.K.shape[1]
         r = torch.zeros((1, ld), dtype=torch.float64, device=self.device)
         r[0, : self.N] = torch.from_numpy(rhs).to(self.device)
-        if self.method == "ldlt":
+        if self.method in ("gmres", "minres"):
+            x0 = None
+            if initial_sol is not None:  # a zero-argument callable (gmres_solver.py:15-16)
+                x0 = torch.zeros((1, ld), dtype=torch.float64, device=self.device)
+                x0[0, : self.N] = torch.from_numpy(np.asarray(initial_sol(), dtype=np.float64)).to(self.device)
+            if self.method == "gmres":
+                K.gmres_solve(self.K, self.N, self.Nvec, r, x0, None, trans, self.scratch, self.info, self.iters, _one())
+            else:
+                K.minres_solve(self.K, self.N, self.Nvec, r, x0, self.scratch, self.info, self.iters, _one())
+            code = int(self.info.item())
+            if code != 0:
+                LSE, _ = _reference_errors()
+                raise LSE(f"{self.method.upper()} failed with error code {code}")
+        elif self.method == "ldlt":
             K.ldlt_solve(self.K, self.N, self.Nvec, r, _one())
         else:
             K.lu_solve(self.K, self.N, self.Nvec, self.piv, r, trans, _one())
@@ -346,7 +370,12 @@ class B200StepSolver:
         self.device = device
         self._func = B200StepFunc(problem, orig_iterate, dt, device)
         if linear is None:
-            linear = getattr(params, "b200_linear_solver", LinearSolverType.Auto)
+            linear = getattr(params, "b200_linear_solver", None)
+        if linear is None:
+            # the reference's own Params.linear_solver_type selects the iterative solvers (linear_solver/__init__.py:15,
+            # 35-39); its direct solvers all map to the factorisation the engine picks
+            name = getattr(getattr(params, "linear_solver_type", None), "name", "")
+            linear = LinearSolverType[name] if name in ("GMRES", "MINRES") else LinearSolverType.Auto
         self.engine = KKTEngine(1, self.n, self.m, device, linear,
                                 inertia_correction=bool(getattr(params, "inertia_correction", False)))
         f64 = dict(dtype=torch.float64, device=device)
@@ -437,6 +466,8 @@ class B200StepSolver:
         eng.step(self.H, self.J, it.x, it.y if m > 0 else None, F, f.dt_d, self.rho_d, f.lb_d, f.ub_d, self._xn,
                  self._yn if m > 0 else None, self._diff, _one(), dx=self._dx, dy=self._dy if m > 0 else None)
         out = torch.cat([self._xn[0], self._dx[0], self._dy[0], self._diff]).cpu().numpy()
+        if eng.solve_can_fail and int(eng.info.item()) != 0:  # gmres_solver.py:32-33 / minres_solver.py:21-22
+            raise SSE() from LSE(f"{eng.linear.name} failed with error code {int(eng.info.item())}")
         n = self.n
         xn, dx, dy, diff = out[:n], out[n : 2 * n], out[2 * n : 2 * n + m], float(out[-1])
         rcond = self.estimate_rcond() if getattr(self.params, "report_rcond", False) else None

@@ -103,8 +103,19 @@ class BatchedSolver:
         self.Jbuf = [None, None, None]
         self.Hbuf = [None, None]
         exact = self.params.step_control_type == StepControlType.Exact
+        pu = self.params.penalty_update
+        self._filter_kind = {PenaltyUpdate.ObjectiveFilter: 0, PenaltyUpdate.LagrangianFilter: 1}.get(pu)
+        self._pareto = pu == PenaltyUpdate.ParetoDecrease
+        if self._filter_kind is not None:
+            cap = int(self.params.penalty_filter_capacity)
+            self.rho_pen = torch.zeros((B,), **f64)       # the strategy's own rho (penalty.py:177,209)
+            self.filt = torch.zeros((B, cap, 2), **f64)   # PenaltyFilter.entries per instance
+            self.nfilt = torch.zeros((B,), **i32)
+            self.filt_overflow = torch.zeros((B,), **i32)
+            self.dLpm, self.dLpf = (vec(n), vec(n)) if self._filter_kind == 1 else (None, None)
+        lag_filter = self._filter_kind == 1
         if m > 0 and not p.jac_constant:
-            self.Jbuf = [p.alloc_jac() for _ in range(3 if exact else 2)]
+            self.Jbuf = [p.alloc_jac() for _ in range(3 if (exact or lag_filter) else 2)]
         if not p.hess_constant:
             self.Hbuf = [p.alloc_hess() for _ in range(2)]
         if self._standard and m > 0:
@@ -157,6 +168,11 @@ class BatchedSolver:
         self.iters.zero_()
         self.accepted.zero_()
         self.newton_step_count.zero_()
+        self.phase.zero_()
+        if self._filter_kind is not None:
+            self.rho_pen.fill_(prm.rho)
+            self.nfilt.zero_()
+            self.filt_overflow.zero_()
         allw = WorkList.all(B)
         prob.eval(x, grad, cons, obj, allw)
 
@@ -195,6 +211,8 @@ class BatchedSolver:
                 self._top(run)
                 outer += 1
 
+        if self._filter_kind is not None and bool(self.filt_overflow.any().item()):
+            raise RuntimeError("penalty filter capacity exceeded: raise Params.penalty_filter_capacity")
         return BatchedResult(
             x=x.clone(), y=y.clone(), status=self.status.clone(), iterations=self.iters.clone(),
             accepted_steps=self.accepted.clone(), lamb=self.lamb.clone(), rho=self.rho.clone(),
@@ -209,6 +227,12 @@ class BatchedSolver:
         m = prob.m
         x, y, grad, cons, obj = self.cur
         self._J0 = prob.jac(x, self.Jbuf[0], wtop) if m > 0 else None
+        if self._pareto and m > 0:
+            # ParetoDecrease.update (penalty.py:136-168) of the instances that just accepted a step, on the iterate they
+            # moved to: it needs J'c and J'y (no rho involved), and dL below must see the new rho
+            self._aug_grad(self._J0, self.cur, None, self.jty, self.jtc, wtop)
+            K.pareto_update(grad, cons, self.jty, self.jtc, self.phase, self.status, prm.opt_tol, prm.local_infeas_tol,
+                            self.rho, wtop)
         self._aug_grad(self._J0, self.cur, self.dL0, self.jty if m > 0 else None, self.jtc if m > 0 else None, wtop)
         K.check_terminate(x, grad, self._cons(self.cur), self.jty if m > 0 else None,
                           self.jtc if m > 0 else None, obj, prob.var_lb, prob.var_ub, prm.opt_tol, prm.active_tol,
@@ -232,9 +256,37 @@ class BatchedSolver:
         if on_iteration is not None:
             on_iteration(outer, self)
         # ---- accept / reject, penalty, counters (solver.py:318-378)
-        dual_norm = {PenaltyUpdate.Constant: 0, PenaltyUpdate.DualNorm: 1, PenaltyUpdate.DualEquilibration: 2}[prm.penalty_update]
+        if self._filter_kind is not None:
+            self._penalty_filter()
+        # ParetoDecrease acts in _top (on the committed iterate), the filters above: gf_commit leaves rho alone for them
+        dual_norm = {PenaltyUpdate.Constant: 0, PenaltyUpdate.DualNorm: 1, PenaltyUpdate.DualEquilibration: 2}.get(
+            prm.penalty_update, 0)
         K.commit(self.phase, self.lamb_next, prm.lamb_max, dual_norm, self.mid, self.fin, self.cur, self.lamb,
                  self.rho, self.iters, self.accepted, self.status)
+
+    def _penalty_filter(self):
+        """PenaltyFilter.update (penalty.py:201-210) on every accepted candidate + the veto of solver.py:357-378."""
+        prob = self.problem
+        n, m = prob.n, prob.m
+        run = self.run
+        if self._filter_kind == 1:
+            # LagrangianPenaltyFilter.iterate_entry (penalty.py:228-238): aug_lag_deriv_x of the candidate at the
+            # STRATEGY's rho -- of both candidate buffers, the kernel picks per instance by phase
+            rho_keep, self.rho = self.rho, self.rho_pen
+            const_j = m == 0 or prob.jac_constant
+            Jm = self._J0 if const_j else self.Jbuf[1]
+            if const_j:
+                Jf = self._J0
+            elif self.params.step_control_type == StepControlType.Exact:
+                Jf = self.Jbuf[2]
+            else:
+                Jf = prob.jac(self.fin[0], self.Jbuf[2], run)
+            self._aug_grad(Jm, self.mid, self.dLpm, None, None, run)
+            self._aug_grad(Jf, self.fin, self.dLpf, None, None, run)
+            self.rho = rho_keep
+        K.filter_update(self._filter_kind, n, m, self.phase, self.status, self.mid[4], self._cons(self.mid), self.dLpm if self._filter_kind == 1 else None,
+                        self.fin[4], self._cons(self.fin), self.dLpf if self._filter_kind == 1 else None, self.rho,
+                        self.rho_pen, self.filt, self.nfilt, self.filt_overflow, run)
 
     # ---- Newton steps -------------------------------------------------------------------------
     def _first_newton_step(self):
@@ -372,7 +424,7 @@ class BatchedSolver:
         # ---- second Newton step from mid
         Jm = self.Jbuf[1] if (prob.m > 0 and not prob.jac_constant) else self._J0
         st = self._next_newton_step(self.mid, self.dLm, Jm, self.fin, self.diff2, second)
-        if self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet):
+        if self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet) or eng.solve_can_fail:
             self._mark_failed_second(eng)
         if st is not None:
             self._line_search_failed((st == 2) & (self.phase == PHASE_SECOND))
@@ -469,7 +521,8 @@ class BatchedSolver:
             Jsrc = self.Jbuf[1 + (i % 2)] if (prob.m > 0 and not prob.jac_constant) else self._J0
             st = self._next_newton_step(src, dLs[i % 2], Jsrc, dst, diffs[(i + 1) % 2], loop)
             # a failed refactorisation (Full / ActiveSet / Globalized) ends the loop like a StepSolverError
-            if self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet):
+            if (self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet)
+                    or eng.solve_can_fail):
                 bad = it & (eng.info != 0)
                 phase = torch.where(bad, torch.full_like(phase, 5), phase)
                 lamb_next = torch.where(bad, 2.0 * lamb, lamb_next)

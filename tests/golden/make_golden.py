@@ -535,6 +535,110 @@ def golden_ocp_full():
     np.savez_compressed(os.path.join(HERE, "ocp_full.npz"), **out)
 
 
+def golden_penalty_reject():
+    """The penalty strategies that look at the candidate iterate (penalty.py:115-255): ParetoDecrease and the two
+    filters (which can reject an accepted step, solver.py:357-378), whole Solver.solve traces incl. the rho sequence."""
+    from pygradflow.params import PenaltyUpdate
+
+    out = {}
+    for kind in ("ParetoDecrease", "ObjectiveFilter", "LagrangianFilter"):
+        for newton in ("Simplified", "Full"):
+            cases = [("qp", (16, 8, 0)), ("qp", (32, 16, 2)), ("hs71", None), ("tame", None)]
+            # random starts (x0 ~ U(-1,1), y0 ~ 2 N(0,1) from default_rng(500 + k)): the filters reject on these
+            cases += [("qpr", (12, 5, k)) for k in (0, 2, 3, 10, 18, 32, 35)]
+            for fam, spec in cases:
+                if fam in ("qp", "qpr"):
+                    n, m, k = spec
+                    d = synth.qp_instance(k, n, m)
+                    prob, x0, y0, name = RefQP(d), d["x0"], d["y0"], f"{fam}_n{n}_m{m}_k{k}"
+                    if fam == "qpr":
+                        rng = np.random.default_rng(500 + k)
+                        x0, y0 = rng.uniform(-1, 1, n), rng.normal(size=m) * 2
+                elif fam == "hs71":
+                    prob, x0, y0, name = ref_hs71(), np.array([1.0, 5.0, 5.0, 1.0, 0.0]), np.zeros(2), "hs71"
+                else:
+                    prob, x0, y0, name = ref_tame(), np.zeros(2), np.zeros(1), "tame"
+                rhos = []
+                solver = Solver(prob, params_for(newton, penalty_update=PenaltyUpdate[kind], iteration_limit=300))
+                xs, accepts = [], []
+
+                def cb(iterate, next_iterate, accept):
+                    xs.append(next_iterate.x.copy())
+                    accepts.append(bool(accept))
+                    rhos.append(float(solver.rho))
+
+                solver.callbacks.register(CallbackType.ComputedStep, cb)
+                try:
+                    res = solver.solve(x0, y0)
+                    r = dict(failed=np.bool_(False), x=np.asarray(res.x), y=np.asarray(res.y),
+                             status=np.int32(STATUS_CODE[res.status]), iterations=np.int32(res.iterations),
+                             accepted_steps=np.int32(res.num_accepted_steps), accepts=np.array(accepts, dtype=bool),
+                             rhos=np.array(rhos), rho_final=np.float64(solver.rho), trace_x=np.array(xs))
+                except Exception as err:
+                    r = dict(failed=np.bool_(True), error=np.str_(repr(err)[:80]), accepts=np.array(accepts, dtype=bool),
+                             rhos=np.array(rhos))
+                out.update(flat(f"{kind}/{newton}/{name}", r))
+                print(kind, newton, name, r.get("status"), r.get("iterations"), r.get("accepted_steps"),
+                      r.get("rho_final"), r.get("error"), flush=True)
+    np.savez_compressed(os.path.join(HERE, "penalty_reject.npz"), **out)
+
+
+def golden_iterative():
+    """The reference's iterative LinearSolvers (linear_solver/gmres_solver.py, minres_solver.py): solutions of its own
+    5x5 fixtures and of cfg5-style KKT matrices (GMRES also transposed and with the start vector of
+    AsymmetricStepSolver.initial_sol), and whole Solver.solve traces with Params.linear_solver_type = GMRES / MINRES."""
+    from pygradflow.linear_solver import LinearSolverError
+    from pygradflow.params import StepSolverType
+
+    g = np.load(os.path.join(HERE, "linear_solver.npz"))
+    rhs5 = g["rhs"]
+    out = {}
+    mats = {name: (g[f"{name}/mat"], rhs5) for name in ("indef", "posdef", "negdef")}
+    for N in (12, 48, 96):
+        K, r, _ = synth.kkt_instance(N)
+        mats[f"kkt{N}"] = (K, r)
+    rng = np.random.default_rng(77)
+    for N in (10, 40):  # unsymmetric, well conditioned (exercises trans and x0)
+        mats[f"unsym{N}"] = (np.eye(N) * 4.0 + rng.normal(size=(N, N)) / np.sqrt(N), rng.normal(size=N))
+    for name, (mat, rhs) in mats.items():
+        N = mat.shape[0]
+        out[f"{name}/mat"] = mat
+        out[f"{name}/rhs"] = rhs
+        x0 = np.zeros(N)
+        x0[::3] = rhs[::3]
+        out[f"{name}/x0"] = x0
+        sym = bool(np.array_equal(mat, mat.T))
+        for kind, typ in (("gmres", LinearSolverType.GMRES), ("minres", LinearSolverType.MINRES)):
+            if kind == "minres" and not sym:
+                continue
+            s = linear_solver(sps.csc_matrix(mat), typ, symmetric=sym)
+            cases = [("sol", dict())]
+            if kind == "gmres":
+                cases += [("sol_trans", dict(trans=True)), ("sol_x0", dict(initial_sol=lambda x0=x0: x0.copy()))]
+            else:
+                cases += [("sol_x0", dict(initial_sol=lambda x0=x0: x0.copy()))]
+            for key, kw in cases:
+                try:
+                    out[f"{name}/{kind}/{key}"] = s.solve(rhs, **kw)
+                    out[f"{name}/{kind}/{key}_failed"] = np.bool_(False)
+                except LinearSolverError:
+                    out[f"{name}/{kind}/{key}_failed"] = np.bool_(True)
+    for lin, forms in (("GMRES", ("Symmetric", "Asymmetric", "Extended")), ("MINRES", ("Symmetric",))):
+        for form in forms:
+            kw = dict(linear_solver_type=LinearSolverType[lin], step_solver_type=StepSolverType[form], iteration_limit=400)
+            for newton in ("Simplified", "Full"):
+                for (n, m, k) in [(16, 8, 0), (32, 16, 2), (24, 0, 5)]:
+                    d = synth.qp_instance(k, n, m)
+                    try:
+                        res = trace_solve(RefQP(d), params_for(newton, **kw), d["x0"], d["y0"], keep_every=2)
+                        res["failed"] = np.bool_(False)
+                    except Exception as err:
+                        res = dict(failed=np.bool_(True), error=np.str_(str(err)[:60]))
+                    out.update(flat(f"{lin}/{form}/{newton}/qp_n{n}_m{m}_k{k}", res))
+                    print(lin, form, newton, n, m, k, res.get("status"), res.get("iterations"), flush=True)
+    np.savez_compressed(os.path.join(HERE, "iterative.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -553,6 +657,8 @@ if __name__ == "__main__":
     golden_scaling()
     golden_penalty()
     golden_rcond()
+    golden_iterative()
+    golden_penalty_reject()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -436,3 +436,110 @@ def test_condition_estimator(golden, name):
     est = orc.ConditionEstimator(mat, orc.OracleLUSolver(mat))
     assert est.required_its() == int(g[f"{name}/its"])
     assert abs(est.estimate_rcond() - float(g[f"{name}/rcond"])) <= 1e-13 * float(g[f"{name}/rcond"])
+
+
+def check_iterative_trace(res, g, key, prefix=10):
+    """The iterative solvers stop at rtol = 1e-5, so a Newton step is only defined up to the iteration count of the
+    Krylov method: two implementations whose matrix-vector products round differently (sparse CSC here and in the
+    reference, but with different index orders; a block tree on the GPU) agree to rounding while every solve stops
+    after the same number of products and differ at the 1e-5 level afterwards.  Checked: the same status, the first
+    `prefix` outer iterations identical (accept sequence, iterates within 1e-8), the same optimum (to opt_tol)."""
+    assert res.status == int(g[f"{key}/status"])
+    acc = list(g[f"{key}/accepts"])
+    k = min(prefix, len(acc), len(res.trace))
+    assert [t["accept"] for t in res.trace][:k] == acc[:k]
+    for row, i in enumerate(g[f"{key}/trace_idx"]):
+        if i < k and res.trace[i]["accept"]:  # the candidate of a step that died with a LinearSolverError is never used
+            assert rel_err(res.trace[i]["x"], g[f"{key}/trace_x"][row]) <= 1e-8, (key, i)
+    assert abs(res.iterations - int(g[f"{key}/iterations"])) <= max(3, int(g[f"{key}/iterations"]) // 5)
+    assert rel_err(res.x, g[f"{key}/x"]) <= 1e-5
+
+
+ITER_MATS = ["indef", "posdef", "negdef", "kkt12", "kkt48", "kkt96", "unsym10", "unsym40"]
+
+
+@pytest.mark.parametrize("name", ITER_MATS)
+def test_iterative_linear_solvers(golden, name):
+    """gmres_solver.py / minres_solver.py: the oracle's wrappers against the reference's own (same scipy routine)."""
+    g = golden("iterative")
+    mat, rhs, x0 = g[f"{name}/mat"], g[f"{name}/rhs"], g[f"{name}/x0"]
+    sym = bool(np.array_equal(mat, mat.T))
+    for kind in ("gmres", "minres"):
+        if kind == "minres" and not sym:
+            continue
+        s = orc.make_linear_solver(mat, kind, symmetric=sym)
+        cases = [("sol", {}), ("sol_x0", dict(initial_sol=lambda: x0.copy()))]
+        if kind == "gmres":
+            cases.append(("sol_trans", dict(trans=True)))
+        for key, kw in cases:
+            if bool(g[f"{name}/{kind}/{key}_failed"]):
+                with pytest.raises(orc.LinearSolverError):
+                    s.solve(rhs, **kw)
+            else:
+                assert np.array_equal(s.solve(rhs, **kw), g[f"{name}/{kind}/{key}"]), (name, kind, key)
+
+
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("lin,form", [("GMRES", "Symmetric"), ("GMRES", "Asymmetric"), ("GMRES", "Extended"),
+                                      ("MINRES", "Symmetric")])
+def test_iterative_solves(golden, lin, form, newton):
+    """Solver.solve with Params.linear_solver_type = GMRES / MINRES against the reference's traces."""
+    g = golden("iterative")
+    for (n, m, k) in [(16, 8, 0), (32, 16, 2), (24, 0, 5)]:
+        key = f"{lin}/{form}/{newton}/qp_n{n}_m{m}_k{k}"
+        d = synth.qp_instance(k, n, m)
+        p = orc.DenseQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"])
+        params = orc.OracleParams(linear_solver=lin.lower(), step_solver_type=form.lower(), newton_type=NEWTON[newton],
+                                  iteration_limit=400)
+        if bool(g[f"{key}/failed"]):
+            with pytest.raises(orc.LambMaxError):
+                orc.Solver(p, params).solve(d["x0"], d["y0"])
+            continue
+        res = orc.Solver(p, params).solve(d["x0"], d["y0"], record=True)
+        check_iterative_trace(res, g, key)
+
+
+PENALTY_REJECT_CASES = ["qp_n16_m8_k0", "qp_n32_m16_k2", "hs71", "tame"] + [f"qpr_n12_m5_k{k}" for k in
+                                                                              (0, 2, 3, 10, 18, 32, 35)]
+PENALTY_KIND = {"ParetoDecrease": "pareto_decrease", "ObjectiveFilter": "objective_filter",
+                "LagrangianFilter": "lagrangian_filter"}
+
+
+def penalty_reject_problem(name):
+    """(oracle problem, data dict or None, x0, y0) of a case of tests/golden/penalty_reject.npz."""
+    if name == "hs71":
+        return orc.HS71(), None, np.array([1.0, 5.0, 5.0, 1.0, 0.0]), np.zeros(2)
+    if name == "tame":
+        return orc.Tame(), None, np.zeros(2), np.zeros(1)
+    fam, n, m, k = name.split("_")
+    n, m, k = int(n[1:]), int(m[1:]), int(k[1:])
+    d = synth.qp_instance(k, n, m)
+    x0, y0 = d["x0"], d["y0"]
+    if fam == "qpr":
+        rng = np.random.default_rng(500 + k)
+        x0, y0 = rng.uniform(-1, 1, n), rng.normal(size=m) * 2
+    return orc.DenseQP(d["H"], d["A"], d["g"], d["b"], d["lb"], d["ub"]), d, x0, y0
+
+
+@pytest.mark.parametrize("newton", ["Simplified", "Full"])
+@pytest.mark.parametrize("kind", list(PENALTY_KIND))
+def test_penalty_strategies_that_see_the_candidate(golden, kind, newton):
+    """penalty.py:115-255 (ParetoDecrease, ObjectiveFilter, LagrangianFilter) + solver.py:357-378 against the real
+    reference: status, iteration / accepted counts, the accept sequence (incl. filter rejections) and the rho the
+    solver used in every iteration."""
+    g = golden("penalty_reject")
+    for name in PENALTY_REJECT_CASES:
+        key = f"{kind}/{newton}/{name}"
+        assert not bool(g[f"{key}/failed"])
+        p, _, x0, y0 = penalty_reject_problem(name)
+        params = orc.OracleParams(penalty_update=PENALTY_KIND[kind], newton_type=NEWTON[newton], iteration_limit=300)
+        res = orc.Solver(p, params).solve(x0, y0, record=True)
+        assert res.status == int(g[f"{key}/status"]), key
+        assert res.iterations == int(g[f"{key}/iterations"]) and res.accepted_steps == int(g[f"{key}/accepted_steps"]), key
+        got = [t["accept"] and t.get("penalty_accept", True) for t in res.trace]
+        # the reference's callback sees the controller's verdict (before the penalty strategy may veto it)
+        assert [t["accept"] for t in res.trace] == list(g[f"{key}/accepts"]), key
+        assert sum(got) == res.accepted_steps
+        rhos = np.array([t["rho"] for t in res.trace])
+        assert np.allclose(rhos, g[f"{key}/rhos"], rtol=1e-9, atol=0.0), key
+        assert rel_err(res.x, g[f"{key}/x"]) <= 1e-8, key
