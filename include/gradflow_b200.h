@@ -350,6 +350,22 @@ int gf_filter_update(int B, int n, int m, int kind, int32_t* phase, const int32_
                      double* rho, double* rho_pen, double* filt, int32_t* nfilt, int cap, int32_t* overflow,
                      const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 
+/* ---- fused persistent solver for small bound-constrained instances (cfg2) ----
+ * Solver.solve (solver.py:233-431, default Params: DistanceRatio controller, simplified Newton, Symmetric step solver)
+ * of the chained-Rosenbrock family with n <= 64 variables, bounds only: ONE WARP per instance runs the whole outer loop
+ * -- termination test, residual + active set, Hessian, reduced system (tridiagonal for this family: LAPACK-style
+ * dgttrf / dgttrs per run of inactive variables), both Newton steps, controller, commit -- for up to max_outer outer
+ * iterations per launch; the state (x, grad, obj, lamb, err_sum, status, iters, accepted, newton_steps) lives in the
+ * caller's arrays, so the call is repeated until every status is non-zero.  fresh != 0: evaluate grad / obj at x first.
+ * params_host (HOST pointer, 12 doubles): opt_tol, active_tol, obj_lower_limit, newton_tol, lamb_red, lamb_min, lamb_max,
+ * lamb_inc, theta_max, log(theta_ref), K_P, K_I (params.py:197-265); iteration_limit < 0 = none.
+ * active[B,n] (may be NULL) receives the active set of each instance's last factorisation. */
+int gf_rosen_fused_solve(int B, int n, const double* a, const double* b, const double* lb, const double* ub, double* x,
+                         double* grad, double* obj, double* lamb, double* err_sum, int32_t* status, int32_t* iters,
+                         int32_t* accepted, int32_t* newton_steps, double* total_res, uint8_t* active,
+                         const double* params_host, int iteration_limit, int max_outer, int fresh, const int32_t* work,
+                         const int32_t* nwork_dev, int nwork, void* stream);
+
 /* helpers of the batched driver: ordered compaction of { b in parent (or 0..B-1) : (lo <= key[b] <= hi) != invert } */
 int gf_build_worklist(int B, const int32_t* key, int lo, int hi, int invert, const int32_t* parent,
                       const int32_t* parent_count, int32_t* list, int32_t* count, void* stream);

@@ -156,6 +156,19 @@ def filter_update(kind: int, n: int, m: int, phase, status, om, cm, dm, of, cf, 
           ptr(rho), ptr(rho_pen), ptr(filt), ptr(nfilt), filt.shape[1], ptr(overflow), *_w(work))
 
 
+def rosen_fused_solve(a, b, lb, ub, x, grad, obj, lamb, err_sum, status, iters, accepted, newton_steps, total_res, active,
+                      params12, iteration_limit, max_outer: int, fresh: bool, work: WorkList):
+    """Whole Solver.solve of small chained-Rosenbrock instances, one warp per instance (see the header)."""
+    import ctypes
+
+    B, n = x.shape
+    arr = (ctypes.c_double * 12)(*[float(v) for v in params12])
+    _call("gf_rosen_fused_solve", B, n, ptr(a), ptr(b), ptr(lb), ptr(ub), ptr(x), ptr(grad), ptr(obj), ptr(lamb),
+          ptr(err_sum), ptr(status), ptr(iters), ptr(accepted), ptr(newton_steps), ptr(total_res), ptr(active),
+          ctypes.cast(arr, ctypes.c_void_p), -1 if iteration_limit is None else int(iteration_limit), int(max_outer),
+          1 if fresh else 0, *_w(work))
+
+
 def krylov_scratch_rows(minres: bool, restart: int = 20) -> int:
     return native.load().gf_krylov_scratch_rows(1 if minres else 0, restart)
 

@@ -128,6 +128,9 @@ class Params:
     # entries each instance's penalty filter can hold (the reference's list is unbounded, penalty.py:176; the entries
     # are mutually non-dominated, so the list stays far shorter than the number of accepted steps); exceeding it raises
     penalty_filter_capacity: int = 1024
+    # families with a fused persistent solver (problem.fused_family(); cfg2: one warp runs a whole instance) use it when
+    # the other parameters are the defaults it implements; False forces the lock-step driver
+    fused: bool = True
 
     def __post_init__(self):
         for key, cls in (("newton_type", NewtonType), ("linear_solver_type", LinearSolverType),

@@ -68,6 +68,10 @@ class BatchedProblem:
         for the requested linear solver; returns the LinearSolverType the engine should use."""
         return linear
 
+    def fused_family(self) -> Optional[str]:
+        """Name of the family's fused persistent solver (one warp / CTA runs a whole instance), if it has one."""
+        return None
+
     def alloc_jac(self) -> Optional[torch.Tensor]:
         """A buffer for ``jac`` (None for families with a constant Jacobian or without constraints)."""
         if self.m == 0 or self.jac_constant:
@@ -126,6 +130,9 @@ class BatchedRosenbrock(BatchedProblem):
         super().__init__(lb, ub, 0)
         self.a, self.b = _dev(a, device), _dev(b, device)
         self._zeroed = set()
+
+    def fused_family(self):
+        return "rosen" if self.n <= 64 else None  # gf_rosen_fused_solve
 
     def eval(self, x, grad, cons, obj, work):
         K.rosen_eval(self.a, self.b, x, grad, obj, work)

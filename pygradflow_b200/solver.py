@@ -169,6 +169,8 @@ class BatchedSolver:
         self.accepted.zero_()
         self.newton_step_count.zero_()
         self.phase.zero_()
+        if self._fused_eligible() and on_iteration is None and max_outer is None:
+            return self._solve_fused()
         if self._filter_kind is not None:
             self.rho_pen.fill_(prm.rho)
             self.nfilt.zero_()
@@ -219,6 +221,53 @@ class BatchedSolver:
             total_res=self.total_res.clone(), rcond=None if self.rcond is None else self.rcond.clone(),
             outer_iterations=int(self.iters.max().item()),
             newton_steps=int(self.newton_step_count.item()),
+        )
+
+    # ---- fused persistent path (cfg2) ----------------------------------------------------------
+    FUSED_CHUNK = 4096  # outer iterations per instance and launch (bounds the kernel's run time: ~25 ms)
+
+    def _fused_eligible(self) -> bool:
+        """The fused kernel implements the default path only: simplified Newton, DistanceRatio, standard active set,
+        Symmetric formulation, a penalty strategy that is a no-op without constraints."""
+        prm, prob = self.params, self.problem
+        from .params import LinearSolverType
+
+        return (prm.fused and prob.fused_family() == "rosen" and prob.m == 0
+                and prm.newton_type == NewtonType.Simplified and prm.step_control_type == StepControlType.DistanceRatio
+                and prm.active_set_type == ActiveSetType.Standard and prm.active_set_tau is None
+                and prm.step_solver_type == StepSolverType.Symmetric
+                and prm.linear_solver_type == LinearSolverType.Auto
+                and prm.penalty_update in (PenaltyUpdate.Constant, PenaltyUpdate.DualNorm, PenaltyUpdate.DualEquilibration)
+                and not prm.inertia_correction and not prm.report_rcond)
+
+    def _solve_fused(self) -> BatchedResult:
+        """Solver.solve of every instance inside gf_rosen_fused_solve (one warp per instance, no lock-step); the host
+        only relaunches for the instances that have used up FUSED_CHUNK outer iterations."""
+        prm, prob = self.params, self.problem
+        B = prob.B
+        x, y, grad, cons, obj = self.cur
+        p12 = (prm.opt_tol, prm.active_tol, prm.obj_lower_limit, prm.newton_tol, prm.lamb_red, prm.lamb_min, prm.lamb_max,
+               prm.lamb_inc, prm.theta_max, prm.log_theta_ref, prm.K_P, prm.K_I)
+        nsteps = torch.zeros((B,), dtype=torch.int32, device=prob.device)
+        run = self.run
+        work, fresh, launches = WorkList.all(B), True, 0
+        while True:
+            K.rosen_fused_solve(prob.a, prob.b, prob.var_lb, prob.var_ub, x, grad, obj, self.lamb, self.err_sum,
+                                self.status, self.iters, self.accepted, nsteps, self.total_res, self.engine.active, p12,
+                                prm.iteration_limit, self.FUSED_CHUNK, fresh, work)
+            launches += 1
+            K.build_worklist(self.status, 0, 0, run)
+            nrun = int(run.count_dev.item())
+            if nrun == 0:
+                break
+            run.nwork = nrun
+            work, fresh = run, False
+        self.fused_launches = launches
+        return BatchedResult(
+            x=x.clone(), y=y.clone(), status=self.status.clone(), iterations=self.iters.clone(),
+            accepted_steps=self.accepted.clone(), lamb=self.lamb.clone(), rho=self.rho.clone(),
+            total_res=self.total_res.clone(), rcond=None, outer_iterations=int(self.iters.max().item()),
+            newton_steps=int(nsteps.sum().item()),
         )
 
     def _top(self, wtop: WorkList):

