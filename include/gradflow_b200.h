@@ -309,6 +309,12 @@ int gf_ldexp(int B, int rows, int cols, const double* in, const int32_t* rw, int
 int gf_h2d_sym_lower(double* dst, const double* src_host, int cnt, int n, int blk, void* stream);
 int gf_symmetrize_lower(double* H, int cnt, int n, int blk, void* stream);
 
+/* Hessian block of the Standard formulation: out[B,n,n] = H + rho[b] J'J (iterate.py:103-110 aug_lag_deriv_xx(rho), used by
+ * standard_step_solver.py:50-53); H = lag_hess(x, y + rho c) comes from the family.  Batched rank-m update on the FP64
+ * tensor pipe.  nwork <= 65535. */
+int gf_hess_rho(int B, int n, int m, const double* H, const double* J, const double* rho, double* out,
+                const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+
 /* ---- iterative LinearSolvers (linear_solver/gmres_solver.py:7-35, linear_solver/minres_solver.py:6-24) ----
  * One CTA per instance runs the whole iteration of scipy.sparse.linalg.gmres / minres on the dense K[b] (order Nvec[b] or
  * Nmax, row-major, ld >= Nmax) and overwrites rhs[B,ldr] with the solution.  info[b] = 0 on convergence, otherwise the

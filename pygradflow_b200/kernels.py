@@ -169,6 +169,12 @@ def rosen_fused_solve(a, b, lb, ub, x, grad, obj, lamb, err_sum, status, iters, 
           1 if fresh else 0, *_w(work))
 
 
+def hess_rho(H, J, rho, out, work: WorkList):
+    """out = H + rho J'J (aug_lag_deriv_xx(rho) of the Standard formulation, iterate.py:103-110)."""
+    B, m, n = J.shape
+    _call("gf_hess_rho", B, n, m, ptr(H), ptr(J), ptr(rho), ptr(out), *_w(work))
+
+
 def krylov_scratch_rows(minres: bool, restart: int = 20) -> int:
     return native.load().gf_krylov_scratch_rows(1 if minres else 0, restart)
 

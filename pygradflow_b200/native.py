@@ -65,6 +65,7 @@ SIGNATURES = {
     "gf_pareto_update": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _D, _D, _P] + _WORK,
     "gf_filter_update": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P] + _WORK,
     "gf_rosen_fused_solve": [_I, _I] + [_P] * 15 + [_P, _I, _I, _I] + _WORK,
+    "gf_hess_rho": [_I, _I, _I, _P, _P, _P, _P] + _WORK,
     "gf_build_worklist": [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "gf_dt_from_lamb": [_I, _P, _P, _P],
 }

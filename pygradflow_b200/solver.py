@@ -382,8 +382,7 @@ class BatchedSolver:
         ymod = torch.addcmul(pt[1], self.rho[:, None], pt[3])
         H = prob.lag_hess(pt[0], ymod, self.Hbuf[slot], work)
         out = self._Hrho[slot]
-        torch.bmm(J.transpose(1, 2), J, out=out)          # plain batched GEMM (cuBLAS): J'J
-        out.mul_(self.rho[:, None, None]).add_(H)
+        K.hess_rho(H, J, self.rho, out, work)             # rho J'J + H (own DMMA kernel, gf_syrk.cu)
         return out
 
     def _compute_tau(self):
