@@ -365,18 +365,51 @@ def run_gpu_arm(args):
     solve_bytes = float(((Nvec ** 2) * 8 + 16 * Nvec).sum().item())
     eng_linear = eng.linear
 
-    # ---- end to end, per step, through host buffers (pinned), chunked + double buffered
-    e2e = None
+    # ---- end to end, per step, through host buffers (pinned).  Two shapes of the same public call:
+    #   e2e           : the problem is registered once (its data stays in HBM, like the reference keeps its Problem object
+    #                   across the steps of a solve); every step copies this step's inputs -- x, y, lambda, rho -- from
+    #                   pinned host memory and reads xn, yn, diff, |F|, info back (ResidentNewtonKKT)
+    #   e2e_streaming : nothing is resident: H, A, g, b, bounds cross PCIe again every step, chunked and double
+    #                   buffered (HostNewtonKKT) -- for data that changes every step or exceeds HBM
+    e2e, e2e_streaming = None, None
     hostx = {k: HostNewtonKKT.pinned_like(v) for k, v in dict(x=x, y=y, lamb=lamb, rho=rho).items()}
+    outp = {"xn": torch.empty((B, n), dtype=torch.float64, pin_memory=True),
+            "yn": torch.empty((B, m), dtype=torch.float64, pin_memory=True),
+            "diff": torch.empty((B,), dtype=torch.float64, pin_memory=True),
+            "fnorm": torch.empty((B,), dtype=torch.float64, pin_memory=True),
+            "info": torch.empty((B,), dtype=torch.int32, pin_memory=True)}
+    try:
+        from pygradflow_b200.host_step import ResidentNewtonKKT
+
+        stepper.events = None
+        stepper.engine.ldlt_events = None
+        rk = ResidentNewtonKKT(prob, linear, stepper=stepper)
+        rk.step(hostx, outp)
+        barrier()
+        t0 = time.perf_counter()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            rk.step(hostx, outp)
+        a1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = max_over_ranks(a0.elapsed_time(a1))
+        h2d, d2h = rk.bytes_per_step()
+        e2e = {"value": B * world * args.steps / (ems * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": args.steps,
+               "wall_s": wall, "max_abs_diff_vs_device_path": float((outp["xn"].to(device) - xn_gpu).abs().max().item()),
+               "what": "problem registered once (H, A, g, b, bounds resident in HBM, uploaded outside the timed region, "
+                       "as the reference arm keeps its Problem objects in host memory); per step: x, y, lambda, rho "
+                       "pinned host -> device, the full Newton-KKT step, xn, yn, diff, |F(next)|, info device -> pinned "
+                       "host, all inside the timed region (CUDA events on the launching stream, max over ranks)"}
+        del rk
+    except Exception as exc:  # pragma: no cover
+        e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
     try:
         hk = HostNewtonKKT(n, m, chunk=256, device=device, linear=linear)
         hin = dict(host)
         hin.update(hostx)
-        outp = {"xn": torch.empty((B, n), dtype=torch.float64, pin_memory=True),
-                "yn": torch.empty((B, m), dtype=torch.float64, pin_memory=True),
-                "diff": torch.empty((B,), dtype=torch.float64, pin_memory=True),
-                "fnorm": torch.empty((B,), dtype=torch.float64, pin_memory=True),
-                "info": torch.empty((B,), dtype=torch.int32, pin_memory=True)}
         esteps = max(1, min(args.steps, 3))
         hk.step(hin, outp)
         barrier()
@@ -390,7 +423,7 @@ def run_gpu_arm(args):
         wall = time.perf_counter() - t0
         ems = max_over_ranks(a0.elapsed_time(a1))
         h2d, d2h = hk.bytes_per_step(B)
-        e2e = {"value": B * world * esteps / (ems * 1e-3), "unit": UNIT,
+        e2e_streaming = {"value": B * world * esteps / (ems * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "steps": esteps,
                "wall_s": wall, "chunk": 256, "host_gb_per_s": (h2d + d2h) * world * esteps / (ems * 1e-3) * 1e-9,
                "max_abs_diff_vs_device_path": float((outp["xn"].to(device) - xn_gpu).abs().max().item()),
@@ -398,7 +431,7 @@ def run_gpu_arm(args):
                         "node for all GPUs (nvidia-smi topo), so there is no NUMA-local staging to choose"}
         del hk, hin
     except Exception as exc:  # pragma: no cover
-        e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
+        e2e_streaming = {"value": None, "unit": UNIT, "error": repr(exc)}
 
     # ---- end to end, whole solves: upload the problem data once from pinned host memory, BatchedSolver.solve,
     # download (x, y, status, iterations) -- H and A are constant over the Newton steps of a solve
@@ -531,6 +564,7 @@ def run_gpu_arm(args):
             "phase_ms": phases,
             "clocks": clocks,
             "e2e": e2e,
+            "e2e_streaming": e2e_streaming,
             "e2e_solve": e2e_solve,
             "gather": gather,
             "gpu_launches": launches,

@@ -247,6 +247,7 @@ extern "C" int gf_band_assemble(int B, int n, int m, int bw, const double* H, co
         return GF_ERR_ARG;
     if (m > 0 && !J) return GF_ERR_ARG;
     if (nwork <= 0) return GF_OK;
+    if (nwork > 65535) return GF_ERR_UNSUPPORTED;  // the instance index rides in grid.y
     const int total = (n + m) * (bw + 1);
     int gx = (total + 255) / 256;
     if (gx > 64) gx = 64;

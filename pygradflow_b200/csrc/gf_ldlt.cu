@@ -954,6 +954,13 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
         return v < 2 ? 1 : (v > LDLT_MAX_LANES ? LDLT_MAX_LANES : v);
     }();
     LdltLanes* L = (lanes_req > 1 && nwork >= LDLT_SPLIT_MIN && nblk > 2) ? ldlt_lanes() : nullptr;
+    // The lane streams and their fork / join events are per device, shared by every caller: the whole fork -> launches ->
+    // join sequence is issued under one lock, so two host threads (or two caller streams) factorising on the same device
+    // cannot re-record each other's events between a record and the waits on it.  (A wait captures the event's state at
+    // the time of the call, so holding the lock while ISSUING is sufficient; the kernels themselves overlap freely.)
+    static std::mutex issue_mu;
+    std::unique_lock<std::mutex> issue_lock(issue_mu, std::defer_lock);
+    if (L != nullptr) issue_lock.lock();
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (L != nullptr && (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) L = nullptr;
     static const bool split_on = [] { const char* e = getenv("GF_LDLT_P64"); return e != nullptr && e[0] == '1'; }();

@@ -32,7 +32,7 @@ extern "C" int gf_ldexp(int B, int rows, int cols, const double* in, const int32
     if (B <= 0 || rows < 0 || cols < 0 || !in || !out) return GF_ERR_ARG;
     if (nwork <= 0 || rows == 0 || cols == 0) return GF_OK;
     const long total = (long)rows * cols;
-    if (total > (1L << 30)) return GF_ERR_UNSUPPORTED;
+    if (total > (1L << 30) || nwork > 65535) return GF_ERR_UNSUPPORTED;  // the instance index rides in grid.y
     int gx = (int)((total + 1023) / 1024);
     if (gx > 64) gx = 64;
     ldexp_kernel<<<dim3(gx, nwork), 256, 0, (cudaStream_t)stream>>>(rows, cols, in, rw, sr, cw, sc, ow, so, out,

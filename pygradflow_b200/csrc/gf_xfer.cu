@@ -59,6 +59,7 @@ extern "C" int gf_symmetrize_lower(double* H, int cnt, int n, int blk, void* str
     const int nt = (n + 31) / 32;
     const int pairs = nt * (nt - 1) / 2;
     if (pairs == 0) return GF_OK;
+    if (cnt > 65535) return GF_ERR_UNSUPPORTED;  // the instance index rides in grid.y
     symmetrize_kernel<<<dim3(pairs, cnt), 256, 0, (cudaStream_t)stream>>>(n, blk, H);
     return gf_launch_status();
 }

@@ -101,3 +101,51 @@ class HostNewtonKKT:
                 s.done.record(sk)
         cur.wait_stream(sk)
         cur.wait_stream(sc)
+
+
+class ResidentNewtonKKT:
+    """``newton_kkt_step`` on host iterates for a problem registered ONCE.
+
+    The reference builds its ``Problem`` once and hands the step solver a new ``Iterate`` every step
+    (pygradflow/solver.py:305-316, step/solver/__init__.py:18-19): the problem data (H, A, g, b, bounds of the QP
+    family) does not change between the Newton steps of a solve.  ``register`` therefore uploads it once; ``step`` copies
+    this step's inputs -- the iterates x, y and the per-instance lambda, rho -- from pinned host memory, runs the
+    batched step on the resident data and copies (xn, yn, diff, fnorm, info) back to pinned host memory.
+    ``HostNewtonKKT`` above is the variant for data that changes every step or does not fit into HBM."""
+
+    def __init__(self, problem: BatchedQP, linear: LinearSolverType = LinearSolverType.Auto, stepper=None):
+        self.problem = problem
+        B, n, m, dev = problem.B, problem.n, problem.m, problem.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.stepper = stepper if stepper is not None else NewtonKKTStepper(problem, linear)
+        self.x = torch.zeros((B, n), **f64)
+        self.y = torch.zeros((B, m), **f64)
+        self.lamb = torch.zeros((B,), **f64)
+        self.rho = torch.zeros((B,), **f64)
+
+    @classmethod
+    def register(cls, host: Dict[str, torch.Tensor], device="cuda", linear: LinearSolverType = LinearSolverType.Auto):
+        """host: (pinned) H [B,n,n], A [B,m,n] or None, g, b, lb, ub."""
+        prob = BatchedQP(host["H"], host.get("A"), host["g"], host.get("b"), host["lb"], host["ub"], device=device)
+        return cls(prob, linear)
+
+    def bytes_per_step(self):
+        B, n, m = self.problem.B, self.problem.n, self.problem.m
+        return 8 * B * (n + m + 2), 8 * B * (n + m + 2) + 4 * B
+
+    def step(self, host: Dict[str, torch.Tensor], out: Dict[str, torch.Tensor]) -> None:
+        """host: pinned x [B,n], y [B,m], lamb [B], rho [B]; out: pinned xn, yn, diff, fnorm, info.  Asynchronous on
+        the current stream (synchronise before reading `out`)."""
+        m = self.problem.m
+        self.x.copy_(host["x"], non_blocking=True)
+        if m > 0:
+            self.y.copy_(host["y"], non_blocking=True)
+        self.lamb.copy_(host["lamb"], non_blocking=True)
+        self.rho.copy_(host["rho"], non_blocking=True)
+        xn, yn, diff, fnorm, info = self.stepper.step(self.x, self.y, self.lamb, self.rho)
+        out["xn"].copy_(xn, non_blocking=True)
+        if m > 0:
+            out["yn"].copy_(yn, non_blocking=True)
+        out["diff"].copy_(diff, non_blocking=True)
+        out["fnorm"].copy_(fnorm, non_blocking=True)
+        out["info"].copy_(info, non_blocking=True)

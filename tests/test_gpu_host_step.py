@@ -58,6 +58,16 @@ def test_host_step_matches_device_stepper(n, m, B, chunk):
     out = dict(xn=torch.empty((B, n), dtype=torch.float64).pin_memory(), yn=torch.empty((B, m), dtype=torch.float64).pin_memory(),
                diff=torch.empty((B,), dtype=torch.float64).pin_memory(), fnorm=torch.empty((B,), dtype=torch.float64).pin_memory(),
                info=torch.empty((B,), dtype=torch.int32).pin_memory())
+    from pygradflow_b200.host_step import ResidentNewtonKKT
+
+    rk = ResidentNewtonKKT.register({k: host[k] for k in ("H", "A", "g", "b", "lb", "ub") if m or k not in ("A", "b")})
+    rk.step(host, out)  # problem registered once; only x, y, lamb, rho cross the bus
+    torch.cuda.synchronize()
+    assert np.array_equal(out["xn"].numpy(), xn.cpu().numpy()) and np.array_equal(out["diff"].numpy(), diff.cpu().numpy())
+    assert np.array_equal(out["fnorm"].numpy(), fn.cpu().numpy()) and np.array_equal(out["info"].numpy(), info.cpu().numpy())
+    assert rk.bytes_per_step()[0] == 8 * B * (n + m + 2)
+    for t in out.values():
+        t.zero_()
     for _ in range(2):  # the second pass reuses the slots
         hk.step(host, out)
         torch.cuda.synchronize()
