@@ -397,7 +397,7 @@ __device__ __forceinline__ double xt_fragment(const double* Xs, int kq, int n) {
 // LROWS: A rows the shared-memory layout is sized for (128 inside the column kernel, 64 in the 64-row-only kernel).
 template <int ROWS, int LROWS = TM>
 __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int ld, double* __restrict__ Kb,
-                                                const double* __restrict__ db, const KktView& kv) {
+                                                const double* db, const KktView& kv) {
     constexpr int WN = (ROWS == 128) ? 2 : 4;   // warps along the 64 columns
     constexpr int NI = 8 / WN;                  // 8-column DMMA tiles per warp
     constexpr int WC = NI * 8;                  // columns per warp
@@ -436,7 +436,7 @@ __device__ __forceinline__ void ldlt_panel_tile(double* sm, int i0, int j0, int 
     else load_diag_block(sm + EPI_XS, Kb, j0, ld);
     cp_async_commit();
     // reciprocal pivots of block column k for the epilogue: fetched and inverted now, behind the main loop
-    const double my_rinv = (tid < NB) ? 1.0 / __ldg(db + j0 + tid) : 0.0;
+    const double my_rinv = (tid < NB) ? 1.0 / db[j0 + tid] : 0.0;  // plain load: the whole-matrix kernel wrote it
     // accumulators start from the current A tile (these loads overlap the first pipeline stage)
     double acc[4][NI][2];
 #pragma unroll
@@ -582,7 +582,7 @@ __device__ __forceinline__ void ldlt_chain_body(double* sm, int b, int ld, const
     if (nchunks > 0) load_stage(0, 0);
     else load_diag_block(sm + EPI_XS, Kb, j0, ld);
     cp_async_commit();
-    const double my_rinv = (tid < NB) ? 1.0 / __ldg(db + j0 + tid) : 0.0;  // for the epilogue, behind the main loop
+    const double my_rinv = (tid < NB) ? 1.0 / db[j0 + tid] : 0.0;  // for the epilogue, behind the main loop
     double acc[4][4][2];
     {
         const int colbase = (diag_part ? i0 + (wn - 2) * 32 : j0 + wn * 32) + 2 * q;
@@ -792,6 +792,54 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
     else ldlt_panel_tile<64>(sm, i0, j0, ld, Kb, db, kv);   // odd remainder block: Np - i0 == 64
 }
 
+// Whole factorisation of one matrix by ONE CTA (opt-in experiment, GF_LDLT_WHOLE=1): diagonal block 0, then per block
+// column k the chain tile (rows of block k+1 + the factorisation of diagonal block k+1) and the panel tiles below it,
+// one after the other, with the device functions of the per-column kernels.  No launch boundaries, no per-column tails,
+// and the two CTAs of an SM drift apart, so the latency-bound pivot chain of one runs beside the DMMA main loops of
+// the other instead of beside another pivot chain.  Measured (B200, B = 4096): N = 768 27.5 ms vs 26.1 ms for the
+// per-column launches, N = 512 10.0 vs 9.5, N = 1024 58.6 vs 55.7, N = 2048 (B = 1024) 102 vs 97 -- identical results,
+// 5 % SLOWER: the pivot chain next to a DMMA stream is starved (tools/fp64_contention_bench.cu) for longer than the
+// lock-step chain phases of the per-column launches leave the pipe idle.  Not adopted; kept for the record.
+__global__ void __launch_bounds__(256, 2) ldlt_whole_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                            double* __restrict__ K, double* __restrict__ dvec,
+                                                            int32_t* __restrict__ info, int32_t* __restrict__ nneg,
+                                                            const int32_t* __restrict__ npos_expected, GfWork work,
+                                                            int woff, KktSrc src) {
+    const int b = gf_instance(work, woff + blockIdx.x);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    const KktView kv = kkt_view(src, b);
+    const int Np = padded_order(Nvec, Nfixed, b, ld);
+    if (Np <= 0) {
+        if (threadIdx.x == 0) { info[b] = 0; nneg[b] = 0; }
+        return;
+    }
+    double* Kb = K + (size_t)b * ld * ld;
+    {
+        double(*S)[DP] = reinterpret_cast<double(*)[DP]>(sm);
+        for (int e = threadIdx.x; e < NB * NB / 2; e += blockDim.x) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            const double2 v = kkt_load2(kv, Kb, ld, r, c);
+            S[r][c] = v.x;
+            S[r][c + 1] = v.y;
+        }
+        __syncthreads();
+        ldlt_diag_factor(sm, sm + DG_S, sm + DG_S + DG_OPS, b, ld, Nvec, Nfixed, 0, K, dvec, info, nneg, npos_expected);
+    }
+    const double* db = dvec + (size_t)b * ld;
+    const int nblk = Np / NB;
+    for (int k = 0; k + 1 < nblk; k++) {
+        const int j0 = k * NB;
+        __syncthreads();  // the previous phase's global writes (L, W', d) and shared-memory use are complete
+        ldlt_chain_body(sm, b, ld, Nvec, Nfixed, k, K, dvec, info, nneg, npos_expected, kv);
+        for (int i0 = j0 + 2 * NB; i0 < Np; i0 += TM) {
+            __syncthreads();
+            if (Np - i0 >= TM) ldlt_panel_tile<128>(sm, i0, j0, ld, Kb, db, kv);
+            else ldlt_panel_tile<64>(sm, i0, j0, ld, Kb, db, kv);
+        }
+    }
+}
+
 // Panel tiles only, 64 rows each, three CTAs per SM (<= 85 registers, 74 KB shared memory): the rows below block
 // k + 1 of block column k.  Launched beside the chain kernel of the same column.
 constexpr int P64_SMEM = STAGES * 2 * NB * PSP * (int)sizeof(double);
@@ -947,6 +995,14 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
 #endif
     cudaFuncSetAttribute(ldlt_diag0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
     cudaFuncSetAttribute(ldlt_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM);
+    // GF_LDLT_WHOLE=1: one CTA per matrix (experiment, 5 % slower than the per-column launches; see ldlt_whole_kernel)
+    static const bool whole_req = [] { const char* e = getenv("GF_LDLT_WHOLE"); return e != nullptr && e[0] == '1'; }();
+    static_assert(DG_SMEM <= PN_SMEM, "the first diagonal block must fit into the column kernel's shared memory");
+    if (whole_req && nblk > 1) {
+        cudaFuncSetAttribute(ldlt_whole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM);
+        ldlt_whole_kernel<<<nwork, 256, COL_SMEM, s>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, 0, src);
+        return gf_launch_status();
+    }
     // GF_LDLT_LANES: 0 = one stream, 2 (default) .. 4 = parts of the batch whose launches interleave
     static const int lanes_req = [] {
         const char* e = getenv("GF_LDLT_LANES");
