@@ -215,6 +215,20 @@ int gf_dr_first(int B, const int32_t* status, const int32_t* info, const double*
 int gf_dr_second(int B, const double* dt, const double* diff1, const double* diff2, double theta_max,
                  double log_theta_ref, double K_P, double K_I, double lamb_min, double lamb_inc, double* err_sum,
                  int32_t* phase, double* lamb_next, double* theta, void* stream);
+/* ResiduumRatioController.step (residuum_ratio_control.py:18-63; fixed != 0: FixedStepSizeController.step,
+ * fixed_control.py:12-19) after their single Newton step; nsteps (device int64) counts the Newton steps taken. */
+int gf_single_control(int B, int fixed, const int32_t* status, const int32_t* info, const double* dt,
+                      const double* mid_norm, const double* orig_norm, double newton_tol, double theta_max,
+                      double log_theta_ref, double K_P, double K_I, double lamb_red, double lamb_min, double lamb_inc,
+                      double lamb_init, double* err_sum, int32_t* phase, double* lamb_next, double* theta,
+                      int64_t* nsteps, void* stream);
+/* ExactController.step (exact_control.py:16-66), one call per stage of its Newton loop over the instances with
+ * live[b] != 0.  mode 0: set-up after the first step (info != 0 => failed); mode 1: verdict on Newton iterate `it`
+ * (residual norm val[B]; even iterates are committed from the mid buffers, odd from the fin buffers; last != 0: the
+ * tenth iterate); mode 2: a failed refactorisation ends an instance's loop. */
+int gf_exact_control(int B, int mode, int it, int last, const int32_t* status, const int32_t* info, const double* dt,
+                     const double* val, const double* orig_norm, double newton_tol, double rate_bound, double* curr,
+                     int32_t* live, int32_t* phase, double* lamb_next, int64_t* nsteps, void* stream);
 /* End of the outer iteration (solver.py:318-378): lamb_max guard, penalty update (dual_norm_update = 0: constant,
  * 1: DualNormUpdate penalty.py:46-74, 2: DualEquilibration penalty.py:77-113), iterate <- accepted Newton iterate,
  * counters. */

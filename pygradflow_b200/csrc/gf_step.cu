@@ -477,6 +477,99 @@ __global__ void dr_second_kernel(int B, const double* __restrict__ dt, const dou
     }
 }
 
+
+// ResiduumRatioController.step (residuum_ratio_control.py:18-63) / FixedStepSizeController.step (fixed_control.py:12-19)
+// after their single Newton step, with the solver-failure path of StepController.compute_step (step_control.py:102-104).
+__global__ void single_control_kernel(int B, int fixed, const int32_t* __restrict__ status,
+                                      const int32_t* __restrict__ info, const double* __restrict__ dt,
+                                      const double* __restrict__ mid_norm, const double* __restrict__ orig_norm,
+                                      double newton_tol, double theta_max, double log_theta_ref, double K_P, double K_I,
+                                      double lamb_red, double lamb_min, double lamb_inc, double lamb_init,
+                                      double* __restrict__ err_sum, int32_t* __restrict__ phase,
+                                      double* __restrict__ lamb_next, double* __restrict__ theta_out,
+                                      unsigned long long* __restrict__ nsteps) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (status[b] != 0) { phase[b] = GF_PHASE_IDLE; return; }
+    const double lamb = 1.0 / dt[b];
+    if (info[b] != 0) {
+        phase[b] = GF_PHASE_FAILED;
+        lamb_next[b] = 2.0 * lamb;
+        return;
+    }
+    atomicAdd(nsteps, 1ULL);
+    if (fixed) {
+        phase[b] = GF_PHASE_ACCEPT_MID;
+        lamb_next[b] = lamb_init;
+        return;
+    }
+    if (mid_norm[b] <= newton_tol) {                       // residuum_ratio_control.py:33-38
+        phase[b] = GF_PHASE_ACCEPT_MID;
+        lamb_next[b] = fmax(lamb * lamb_red, lamb_min);
+        return;
+    }
+    const double theta = mid_norm[b] / orig_norm[b];
+    theta_out[b] = theta;
+    if (theta <= theta_max) {                              // :50-58, controller.py:44-77
+        const double err = log_theta_ref - log(theta);
+        const double es = err_sum[b] + err;
+        err_sum[b] = es;
+        const double mod = exp(K_P * err + K_I * es);
+        lamb_next[b] = fmax(lamb / mod, lamb_min);
+        phase[b] = GF_PHASE_ACCEPT_MID;
+    } else {
+        lamb_next[b] = lamb * lamb_inc;
+        phase[b] = GF_PHASE_REJECT;
+    }
+}
+
+// ExactController.step (exact_control.py:16-66), one call per stage of its Newton loop.  `live` = instances still
+// inside the loop.  mode 0: after the first step (failure => FAILED, 2 lambda; curr = |F(orig)|); mode 1: look at the
+// residual norm `val` of Newton iterate number `it` (0-based; even iterates live in `mid` -> phase 2, odd in `fin` ->
+// phase 3): converged => accept, lambda / 2; contraction rate > rate_bound or the last iterate => reject, 2 lambda;
+// mode 2: a failed refactorisation after a further step ends the loop like a StepSolverError.
+__global__ void exact_control_kernel(int B, int mode, int it, int last, const int32_t* __restrict__ status,
+                                     const int32_t* __restrict__ info, const double* __restrict__ dt,
+                                     const double* __restrict__ val, const double* __restrict__ orig_norm,
+                                     double newton_tol, double rate_bound, double* __restrict__ curr,
+                                     int32_t* __restrict__ live, int32_t* __restrict__ phase,
+                                     double* __restrict__ lamb_next, unsigned long long* __restrict__ nsteps) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double lamb = 1.0 / dt[b];
+    if (mode == 0) {
+        const bool running = status[b] == 0;
+        const bool failed = running && info[b] != 0;
+        live[b] = (running && !failed) ? 1 : 0;
+        curr[b] = orig_norm[b];
+        phase[b] = failed ? GF_PHASE_FAILED : GF_PHASE_IDLE;
+        lamb_next[b] = failed ? 2.0 * lamb : lamb;
+        return;
+    }
+    if (!live[b]) return;
+    if (mode == 2) {
+        if (info[b] != 0) {
+            phase[b] = GF_PHASE_FAILED;
+            lamb_next[b] = 2.0 * lamb;
+            live[b] = 0;
+        }
+        return;
+    }
+    atomicAdd(nsteps, 1ULL);
+    const double v = val[b];
+    if (v <= newton_tol) {                                  // exact_control.py:44-49
+        phase[b] = GF_PHASE_ACCEPT_MID + (it & 1);
+        lamb_next[b] = 0.5 * lamb;
+        live[b] = 0;
+    } else if ((v / curr[b]) > rate_bound || last) {        // :51-58, :60-66
+        phase[b] = GF_PHASE_REJECT;
+        lamb_next[b] = 2.0 * lamb;
+        live[b] = 0;
+    } else {
+        curr[b] = v;
+    }
+}
+
 // End of an outer iteration (solver.py:318-378): lambda hand-over, lamb_max guard, penalty update
 // (penalty.py:36-113; dual_norm_update = 0 constant, 1 DualNorm, 2 DualEquilibration), iterate <- accepted Newton
 // iterate, counters.
@@ -732,6 +825,33 @@ extern "C" int gf_dr_second(int B, const double* dt, const double* diff1, const 
     if (B <= 0 || !dt || !diff1 || !diff2 || !err_sum || !phase || !lamb_next) return GF_ERR_ARG;
     dr_second_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         B, dt, diff1, diff2, theta_max, log_theta_ref, K_P, K_I, lamb_min, lamb_inc, err_sum, phase, lamb_next, theta);
+    return gf_launch_status();
+}
+
+extern "C" int gf_single_control(int B, int fixed, const int32_t* status, const int32_t* info, const double* dt,
+                                 const double* mid_norm, const double* orig_norm, double newton_tol, double theta_max,
+                                 double log_theta_ref, double K_P, double K_I, double lamb_red, double lamb_min,
+                                 double lamb_inc, double lamb_init, double* err_sum, int32_t* phase, double* lamb_next,
+                                 double* theta, int64_t* nsteps, void* stream) {
+    if (B <= 0 || !status || !info || !dt || !mid_norm || !err_sum || !phase || !lamb_next || !theta || !nsteps ||
+        (!fixed && !orig_norm))
+        return GF_ERR_ARG;
+    single_control_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        B, fixed, status, info, dt, mid_norm, orig_norm, newton_tol, theta_max, log_theta_ref, K_P, K_I, lamb_red,
+        lamb_min, lamb_inc, lamb_init, err_sum, phase, lamb_next, theta, reinterpret_cast<unsigned long long*>(nsteps));
+    return gf_launch_status();
+}
+
+extern "C" int gf_exact_control(int B, int mode, int it, int last, const int32_t* status, const int32_t* info,
+                                const double* dt, const double* val, const double* orig_norm, double newton_tol,
+                                double rate_bound, double* curr, int32_t* live, int32_t* phase, double* lamb_next,
+                                int64_t* nsteps, void* stream) {
+    if (B <= 0 || mode < 0 || mode > 2 || !status || !info || !dt || !curr || !live || !phase || !lamb_next || !nsteps)
+        return GF_ERR_ARG;
+    if ((mode == 0 && !orig_norm) || (mode == 1 && !val)) return GF_ERR_ARG;
+    exact_control_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        B, mode, it, last, status, info, dt, val, orig_norm, newton_tol, rate_bound, curr, live, phase, lamb_next,
+        reinterpret_cast<unsigned long long*>(nsteps));
     return gf_launch_status();
 }
 

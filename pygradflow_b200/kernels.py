@@ -245,6 +245,18 @@ def dr_second(dt, diff1, diff2, theta_max, log_theta_ref, K_P, K_I, lamb_min, la
           lamb_inc, ptr(err_sum), ptr(phase), ptr(lamb_next), ptr(theta), _stream())
 
 
+def single_control(fixed, status, info, dt, mid_norm, orig_norm, prm, err_sum, phase, lamb_next, theta, nsteps):
+    _call("gf_single_control", status.shape[0], 1 if fixed else 0, ptr(status), ptr(info), ptr(dt), ptr(mid_norm),
+          ptr(orig_norm), prm.newton_tol, prm.theta_max, prm.log_theta_ref, prm.K_P, prm.K_I, prm.lamb_red, prm.lamb_min,
+          prm.lamb_inc, prm.lamb_init, ptr(err_sum), ptr(phase), ptr(lamb_next), ptr(theta), ptr(nsteps), _stream())
+
+
+def exact_control(mode, it, last, status, info, dt, val, orig_norm, newton_tol, rate_bound, curr, live, phase, lamb_next,
+                  nsteps):
+    _call("gf_exact_control", status.shape[0], mode, it, 1 if last else 0, ptr(status), ptr(info), ptr(dt), ptr(val),
+          ptr(orig_norm), newton_tol, rate_bound, ptr(curr), ptr(live), ptr(phase), ptr(lamb_next), ptr(nsteps), _stream())
+
+
 def commit(phase, lamb_next, lamb_max, dual_norm_update, mid, fin, cur, lamb, rho, iters, accepted, status):
     """mid / fin / cur: tuples (x, y, grad, cons, obj)."""
     B, n = cur[0].shape

@@ -90,6 +90,7 @@ class BatchedSolver:
         self.diff1, self.diff2, self.mid_norm = (torch.zeros((B,), **f64) for _ in range(3))
         self.fin_norm, self.orig_norm = (torch.zeros((B,), **f64) for _ in range(2))
         self.loop_key = torch.zeros((B,), **i32)
+        self.exact_curr = torch.zeros((B,), **f64)
         self.theta = torch.zeros((B,), **f64)
         self.tau = torch.zeros((B,), **f64)
         self._tau = None
@@ -485,40 +486,19 @@ class BatchedSolver:
 
     def _control_single(self, fixed: bool):
         """ResiduumRatioController.step (residuum_ratio_control.py:18-63) / FixedStepSizeController.step
-        (fixed_control.py:12-19): one Newton step per outer iteration."""
+        (fixed_control.py:12-19): one Newton step per outer iteration; the verdict and the log-PI update of lambda run in
+        gf_single_control."""
         prm, prob, eng = self.params, self.problem, self.engine
         run = self.run
         ls_failed = self._first_newton_step()
-        lamb = 1.0 / self.dt
-        running = self.status == 0
-        failed = running & (eng.info != 0)
-        ok = running & ~failed
-        two, four, five = (torch.full_like(self.phase, v) for v in (2, 4, 5))
-        zero = torch.zeros_like(self.phase)
-        if fixed:
-            self.phase.copy_(torch.where(failed, five, torch.where(ok, two, zero)))
-            self.lamb_next.copy_(torch.where(failed, 2.0 * lamb, torch.full_like(lamb, prm.lamb_init)))
-        else:
+        if not fixed:
             x, y = self.cur[0], self._y(self.cur)
             K.residual(x, y, x, y, self.dL0, self._cons(self.cur), prob.var_lb, prob.var_ub, self.dt, False, 0, None,
                        None, self.orig_norm, run)
-            conv = ok & (self.mid_norm <= prm.newton_tol)
-            rest = ok & ~conv
-            theta = self.mid_norm / self.orig_norm
-            acc = rest & (theta <= prm.theta_max)
-            err = prm.log_theta_ref - torch.log(theta)              # controller.py:44-52,72-77 (log-PI)
-            err_new = self.err_sum + err
-            lmod = torch.exp(prm.K_P * err + prm.K_I * err_new)
-            self.err_sum.copy_(torch.where(acc, err_new, self.err_sum))
-            self.theta.copy_(theta)
-            lam_conv = torch.clamp(lamb * prm.lamb_red, min=prm.lamb_min)
-            lam_acc = torch.clamp(lamb / lmod, min=prm.lamb_min)
-            self.lamb_next.copy_(torch.where(failed, 2.0 * lamb, torch.where(conv, lam_conv, torch.where(
-                acc, lam_acc, lamb * prm.lamb_inc))))
-            self.phase.copy_(torch.where(failed, five, torch.where(conv | acc, two, torch.where(rest, four, zero))))
+        K.single_control(fixed, self.status, eng.info, self.dt, self.mid_norm, None if fixed else self.orig_norm, prm,
+                         self.err_sum, self.phase, self.lamb_next, self.theta, self.newton_step_count)
         if ls_failed is not None:
             self._line_search_failed(ls_failed)
-        self.newton_step_count += ok.sum()
 
     EXACT_MAX_IT = 10      # exact_control.py:11
     EXACT_RATE_BOUND = 0.5
@@ -527,62 +507,46 @@ class BatchedSolver:
         """ExactController.step (exact_control.py:16-66): Newton steps until ||F|| <= newton_tol (accept, lambda / 2)
         or the contraction rate exceeds 1/2 / ten steps are used up (reject, 2 lambda).  The steps alternate
         between the `mid` and `fin` buffers; an instance that stops at an even step is committed from `mid`
-        (phase 2), at an odd step from `fin` (phase 3)."""
+        (phase 2), at an odd step from `fin` (phase 3).  The per-instance verdicts run in gf_exact_control; the list
+        of instances still inside the loop is rebuilt on the device after every stage."""
         prm, prob, eng = self.params, self.problem, self.engine
         run, loop = self.run, self.second
         x, y = self.cur[0], self._y(self.cur)
         K.residual(x, y, x, y, self.dL0, self._cons(self.cur), prob.var_lb, prob.var_ub, self.dt, False, 0, None, None,
                    self.orig_norm, run)
         ls_failed = self._first_newton_step()
-        lamb = 1.0 / self.dt
-        running = self.status == 0
-        failed = running & (eng.info != 0)
-        it = running & ~failed                      # instances still inside the Newton loop
-        curr = self.orig_norm.clone()
-        phase = torch.where(failed, torch.full_like(self.phase, 5), torch.zeros_like(self.phase))
-        lamb_next = torch.where(failed, 2.0 * lamb, lamb)
+        live, curr = self.loop_key, self.exact_curr
+        ctl = lambda mode, i, last, val: K.exact_control(mode, i, last, self.status, eng.info, self.dt, val, self.orig_norm,
+                                                         prm.newton_tol, self.EXACT_RATE_BOUND, curr, live, self.phase,
+                                                         self.lamb_next, self.newton_step_count)
+        ctl(0, 0, False, None)
         if ls_failed is not None:
             self._line_search_failed(ls_failed)
-            it = it & ~ls_failed
+            live.copy_(torch.where(ls_failed, torch.zeros_like(live), live))
         pts = (self.mid, self.fin)
         dLs = (self.dLm, self.dLf)
         norms = (self.mid_norm, self.fin_norm)
         diffs = (self.diff1, self.diff2)
-        nsteps = torch.zeros_like(self.newton_step_count)
+        refactors = (self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet)
+                     or eng.solve_can_fail)
         for i in range(self.EXACT_MAX_IT):
-            val = norms[i % 2]
-            nsteps += it.sum()
-            conv = it & (val <= prm.newton_tol)
-            brk = it & ~conv & ((val / curr) > self.EXACT_RATE_BOUND)
             last = i == self.EXACT_MAX_IT - 1
-            stop = conv | brk | (it if last else torch.zeros_like(it))
-            phase = torch.where(conv, torch.full_like(phase, 2 + (i % 2)), torch.where(stop & ~conv, torch.full_like(phase, 4), phase))
-            lamb_next = torch.where(conv, 0.5 * lamb, torch.where(stop & ~conv, 2.0 * lamb, lamb_next))
-            it = it & ~stop
-            curr = torch.where(it, val, curr)
+            ctl(1, i, last, norms[i % 2])
             if last:
                 break
-            self.loop_key.copy_(it.to(torch.int32))
-            K.build_worklist(self.loop_key, 1, 1, loop, parent=run)
+            K.build_worklist(live, 1, 1, loop, parent=run)
             loop.nwork = run.nwork
             src, dst = pts[i % 2], pts[(i + 1) % 2]
             Jsrc = self.Jbuf[1 + (i % 2)] if (prob.m > 0 and not prob.jac_constant) else self._J0
             st = self._next_newton_step(src, dLs[i % 2], Jsrc, dst, diffs[(i + 1) % 2], loop)
-            # a failed refactorisation (Full / ActiveSet / Globalized) ends the loop like a StepSolverError
-            if (self.globalized is not None or prm.newton_type in (NewtonType.Full, NewtonType.ActiveSet)
-                    or eng.solve_can_fail):
-                bad = it & (eng.info != 0)
-                phase = torch.where(bad, torch.full_like(phase, 5), phase)
-                lamb_next = torch.where(bad, 2.0 * lamb, lamb_next)
-                it = it & ~bad
+            # a failed refactorisation (Full / ActiveSet / Globalized) or iterative solve ends the loop like a StepSolverError
+            if refactors:
+                ctl(2, i, False, None)
             if st is not None:
-                lsf = it & (st == 2)
+                lsf = (live != 0) & (st == 2)
                 self._line_search_failed(lsf)
-                it = it & ~lsf
+                live.copy_(torch.where(lsf, torch.zeros_like(live), live))
             self._eval_point(dst, dLs[(i + 1) % 2], 1 + ((i + 1) % 2), norms[(i + 1) % 2], loop)
-        self.phase.copy_(torch.where(self.status == 0, phase, torch.zeros_like(phase)))
-        self.lamb_next.copy_(lamb_next)
-        self.newton_step_count += nsteps
 
     def _line_search_failed(self, mask):
         """Armijo search exhausted (newton.py:294 raises a bare Exception that ends Solver.solve): the instance
