@@ -246,6 +246,10 @@ int gf_commit(int B, int n, int m, const int32_t* phase, const double* lamb_next
 int gf_merit_grad(int B, int n, int m, const double* H, const double* J, const double* F, const uint8_t* active,
                   const double* dt, const double* rho, const double* dx, const double* dy, double* res, double* inner,
                   const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
+/* Start of the Armijo search for the instances of the work list (newton.py:256-257,273): state = 1 (full step) where
+ * res <= newton_tol, else 0 (searching); alpha = 1, trials = 0.  Instances outside the list keep their state. */
+int gf_ls_begin(int B, const double* res, double newton_tol, int32_t* state, double* alpha, int32_t* trials,
+                const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream);
 /* xt = x - alpha dx, yt = y - alpha dy (newton.py:276-278) */
 int gf_ls_trial(int B, int n, int m, const double* x, const double* y, const double* dx, const double* dy,
                 const double* alpha, double* xt, double* yt, const int32_t* work, const int32_t* nwork_dev, int nwork,

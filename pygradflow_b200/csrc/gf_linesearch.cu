@@ -178,6 +178,29 @@ extern "C" int gf_merit_grad(int B, int n, int m, const double* H, const double*
     return gf_launch_status();
 }
 
+// Start of the Armijo search (newton.py:256-257,273): instances of the work list whose merit value is already below
+// newton_tol return the full step (state 1), the others search (state 0) from alpha = 1; instances outside the list are
+// parked (state 3, set by the caller's fill before this launch).
+__global__ void ls_begin_kernel(const double* __restrict__ res, double newton_tol, int32_t* __restrict__ state,
+                                double* __restrict__ alpha, int32_t* __restrict__ trials, GfWork work, int nwork) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwork) return;
+    const int b = gf_instance(work, w);
+    if (b < 0) return;
+    state[b] = res[b] <= newton_tol ? 1 : 0;
+    alpha[b] = 1.0;
+    trials[b] = 0;
+}
+
+extern "C" int gf_ls_begin(int B, const double* res, double newton_tol, int32_t* state, double* alpha, int32_t* trials,
+                           const int32_t* work, const int32_t* nwork_dev, int nwork, void* stream) {
+    if (B <= 0 || !res || !state || !alpha || !trials) return GF_ERR_ARG;
+    if (nwork <= 0) return GF_OK;
+    ls_begin_kernel<<<(nwork + 127) / 128, 128, 0, (cudaStream_t)stream>>>(res, newton_tol, state, alpha, trials,
+                                                                          GfWork{work, nwork_dev}, nwork);
+    return gf_launch_status();
+}
+
 extern "C" int gf_ls_trial(int B, int n, int m, const double* x, const double* y, const double* dx, const double* dy,
                            const double* alpha, double* xt, double* yt, const int32_t* work,
                            const int32_t* nwork_dev, int nwork, void* stream) {

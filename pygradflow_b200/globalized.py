@@ -77,18 +77,19 @@ class GlobalizedStepper:
             Hr = prob.lag_hess(xc, self.mult if m > 0 else None, self.Hr, work)
         K.merit_grad(Hr, Jc, self.Fc, eng.active, dt, rho, self.dx, self.dy if m > 0 else None, self.res, self.inner,
                      work)
-        # line search state: instances outside `work` are parked, converged ones return the full step (:256-257)
+        # line search state: instances outside `work` are parked (3), converged ones return the full step (:256-257)
         self.state.fill_(3)
-        self._mark_work(work)
-        self.state.copy_(torch.where((self.state == 0) & (self.res <= self.newton_tol),
-                                     torch.ones_like(self.state), self.state))
+        K.ls_begin(self.res, self.newton_tol, self.state, self.alpha, self.trials, work)
         early = self.state == 1
-        self.alpha.fill_(1.0)
-        self.trials.zero_()
+        # Every kernel of a trial takes its instance list from the device, so a trial with nobody searching changes
+        # nothing: while the stream is being captured into a CUDA graph all MAX_TRIALS trials are recorded; run eagerly,
+        # the loop reads the running count back and stops as soon as the search is over.
+        capturing = torch.cuda.is_current_stream_capturing()
+        parent = None if work.list is None and work.count_dev is None else work
         for _ in range(MAX_TRIALS):
-            K.build_worklist(self.state, 0, 0, self.search, parent=None if work.list is None and work.count_dev is None else work)
+            K.build_worklist(self.state, 0, 0, self.search, parent=parent)
             self.search.nwork = work.nwork
-            if int(self.search.count_dev.item()) == 0:
+            if not capturing and int(self.search.count_dev.item()) == 0:
                 break
             self.total_trials += 1
             sw = self.search
@@ -119,13 +120,3 @@ class GlobalizedStepper:
             yn.copy_(torch.where(searched[:, None], yr, torch.where((early & inwork)[:, None], self.ys, yn)))
         diff.copy_(torch.where(searched, ss.sqrt(), torch.where(early & inwork, self.diff, diff)))
         return self.state
-
-    def _mark_work(self, work: WorkList):
-        if work.list is None and work.count_dev is None:
-            self.state[: work.nwork] = 0
-            return
-        cnt = int(work.count_dev.item()) if work.count_dev is not None else work.nwork
-        if work.list is None:
-            self.state[:cnt] = 0
-        else:
-            self.state[work.list[:cnt].long()] = 0

@@ -285,6 +285,10 @@ def merit_grad(H, J, F, active, dt, rho, dx, dy, res, inner, work: WorkList):
           ptr(res), ptr(inner), *_w(work))
 
 
+def ls_begin(res, newton_tol, state, alpha, trials, work: WorkList):
+    _call("gf_ls_begin", res.shape[0], ptr(res), newton_tol, ptr(state), ptr(alpha), ptr(trials), *_w(work))
+
+
 def ls_trial(x, y, dx, dy, alpha, xt, yt, work: WorkList):
     B, n = x.shape
     m = 0 if y is None else y.shape[1]

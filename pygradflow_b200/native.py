@@ -46,6 +46,7 @@ SIGNATURES = {
     "gf_exact_control": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P, _P, _P, _P, _P],
     "gf_commit": [_I, _I, _I, _P, _P, _D, _I] + [_P] * 10 + [_P] * 10 + [_P],
     "gf_merit_grad": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,
+    "gf_ls_begin": [_I, _P, _D, _P, _P, _P] + _WORK,
     "gf_ls_trial": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P] + _WORK,
     "gf_armijo_residual": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I, _P, _P, _P, _P] + _WORK,
     "gf_kkt_ldlt_factor": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + _WORK,

@@ -132,9 +132,9 @@ class BatchedSolver:
                 raise ValueError("NewtonType.Globalized is built on the scaled step formulations only")
             from .globalized import GlobalizedStepper
 
-            # newton.py:218-304; the line search reads its state back per trial, so this mode runs eagerly
+            # newton.py:218-304; under CUDA-graph capture all 30 Armijo trials are recorded (device work lists make the
+            # superfluous ones no-ops), run eagerly the search stops at the running count
             self.globalized = GlobalizedStepper(problem, self.engine, self.params.newton_tol)
-            self.use_graph = False
 
     # ------------------------------------------------------------------------------------------
     def _y(self, pt):
