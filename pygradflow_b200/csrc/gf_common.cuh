@@ -20,9 +20,11 @@ static inline int gf_launch_status() {
 struct GfWork {
     const int32_t* list;
     const int32_t* count_dev;
+    int off = 0;  // slot offset: a launch that covers the slots [off, off + grid) of the list (batches split over streams)
 };
 
 __device__ __forceinline__ int gf_instance(const GfWork& w, int cta) {
+    cta += w.off;
     if (w.count_dev != nullptr && cta >= *w.count_dev) return -1;
     return w.list != nullptr ? w.list[cta] : cta;
 }

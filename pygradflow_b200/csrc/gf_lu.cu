@@ -25,6 +25,10 @@
 //   lu_solve_kernel  blocked substitution, factors streamed once (HBM-bound).
 #include <cstdlib>
 #include "gf_common.cuh"
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+#include <cstdio>
 #include "../../include/gradflow_b200.h"
 
 namespace {
@@ -129,7 +133,7 @@ __global__ void lu_smem_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfi
             record_pivot(best.v, j, &sinfo);
         }
         if (p != j) {
-            for (int c = (j & ~31) + threadIdx.x; c < N; c += blockDim.x) {  // not the earlier 32-column blocks
+            for (int c = (j & ~63) + threadIdx.x; c < N; c += blockDim.x) {  // not the earlier 64-column super-blocks
                 const double t = S[c * pitch + j];
                 S[c * pitch + j] = S[c * pitch + p];
                 S[c * pitch + p] = t;
@@ -340,9 +344,10 @@ template <int NB>
 __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                        double* __restrict__ K, int32_t* __restrict__ piv,
                                                        int32_t* __restrict__ info, GfWork work, int jstart,
-                                                       int one_column, int nwork) {
+                                                       int one_column, int nwork, int trsm_end) {
     // one_column = 0: the whole factorisation (FMA trailing update in this kernel);
-    // one_column = 1: block column jstart only -- panel, interchanges, U12; the trailing update is lu_update_kernel
+    // one_column = 1: block column jstart only -- panel, interchanges, U12 (for the storage rows below trsm_end, < 0:
+    // all; the rows beyond get theirs from lu_trsm_kernel after the delayed update); the trailing update is separate
     // The CTAs stride over the work list, so that a (mostly) empty list -- the LU fallback of the LDL' path --
     // costs a small grid instead of `nwork` CTAs that exit at once.
     for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
         for (int c = 0; c < jb; c++)
             for (int i = threadIdx.x; i < rows; i += T) Kb[(size_t)(j0 + c) * ld + j0 + i] = P[c * pitch + i];
         // ---- row interchanges of M on the storage rows outside the panel, then U12 = L11^{-1} M12
-        for (int c = (j0 & ~31) + threadIdx.x; c < N; c += T) {  // not the earlier 32-column blocks
+        for (int c = (j0 & ~63) + threadIdx.x; c < N; c += T) {  // not the earlier 64-column super-blocks
             if (c >= j0 && c < j0 + jb) continue;
             double* row = Kb + (size_t)c * ld;
             for (int jj = 0; jj < jb; jj++) {
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
                     row[p] = t;
                 }
             }
-            if (c >= j0 + jb) {
+            if (c >= j0 + jb && (trsm_end < 0 || c < trsm_end)) {
                 double u[NB];
 #pragma unroll
                 for (int k = 0; k < NB; k++) u[k] = (k < jb) ? row[j0 + k] : 0.0;
@@ -496,7 +501,8 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(int ld, const int32_t* __
 template <int NB, int R, int TMAX>
 __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
                                                            double* __restrict__ K, int32_t* __restrict__ piv,
-                                                           int32_t* __restrict__ info, GfWork work, int j0, int nwork) {
+                                                           int32_t* __restrict__ info, GfWork work, int j0, int nwork,
+                                                           int rowops) {  // rowops: U12 for the storage rows below it (< 0: all)
     constexpr int NW = TMAX / 32;
     constexpr int NONE = 1 << 20;
     __shared__ double wrow[2][NW][NB];
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
         if (t < jb) piv[(size_t)b * ld + j0 + t] = j0 + spiv[t];
         // ---- interchanges on the storage rows outside the panel + U12
 #pragma unroll 1
-        for (int c = (j0 & ~31) + t; c < N; c += T) {  // not the earlier 32-column blocks
+        for (int c = (j0 & ~63) + t; c < N; c += T) {  // not the earlier 64-column super-blocks
             if (c >= j0 && c < j0 + jb) continue;
             double* rowp = Kb + (size_t)c * ld + j0;
             // all loads of the row are issued before the first dependent use: the entering values (gather by src[])
@@ -613,7 +619,7 @@ __global__ void __launch_bounds__(TMAX) lu_regpanel_kernel(int ld, const int32_t
                     if (sp != p) rowp[p] = uo[sp];
                 }
             }
-            if (c >= j0 + jb) {
+            if (c >= j0 + jb && (rowops < 0 || c < rowops)) {
 #pragma unroll
                 for (int k = 1; k < NB; k++) {
                     double sacc = u[k];
@@ -948,7 +954,12 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
                 }
                 if (lane < jb) v[j0 + lane] = s;
                 __syncwarp();
-                lu_block_swaps(v, pb, j0, jb, lane, true);  // P_kb' : this block's interchanges, in reverse
+                // the interchanges of a 64-column super-block are applied to the L rows of both of its 32-blocks, so
+                // they are undone together, after its first block: second block's in reverse, then the first's
+                if ((kb & 1) == 0) {
+                    if (j0 + 32 < N) lu_block_swaps(v, pb, j0 + 32, min(32, N - j0 - 32), lane, true);
+                    lu_block_swaps(v, pb, j0, jb, lane, true);
+                }
             }
             __syncthreads();
         }
@@ -962,7 +973,10 @@ __global__ void __launch_bounds__(256) lu_solve_kernel(int ld, const int32_t* __
             }
             __syncthreads();
             if (wid == 0) {
-                lu_block_swaps(v, pb, j0, jb, lane, false);  // P_kb : this block's interchanges
+                if (((j0 >> 5) & 1) == 0) {  // both 32-blocks' interchanges of the 64-column super-block, up front
+                    lu_block_swaps(v, pb, j0, jb, lane, false);
+                    if (j0 + 32 < N) lu_block_swaps(v, pb, j0 + 32, min(32, N - j0 - 32), lane, false);
+                }
                 double s = (lane < jb) ? v[j0 + lane] : 0.0;
                 for (int jj = 0; jj < jb; jj++) {
                     const double z = __shfl_sync(0xffffffffu, s, jj);
@@ -1091,53 +1105,416 @@ __global__ void __launch_bounds__(TN * 2, TN == 64 ? 4 : 2) lu_update_kernel(int
     }
 }
 
+// Generalised trailing update for the delayed (two-level) scheme: C[c][i] -= sum_{k < DEPTH} U[c][k0 + k] L[k0 + k][i]
+// for storage rows c in [c_lo, c_hi) and positions i in [i_lo, i_hi) (a bound < 0 means "to the end": N).  Narrow panels
+// (8 / 16 / 32 columns) only update the rest of their 64-column super-block -- its remaining storage rows and, for the
+// rows beyond, its remaining positions -- with DEPTH = panel width; the bulk of the trailing matrix is touched ONCE per
+// super-block with DEPTH = 64: half (32-wide panels) to an eighth (8-wide) of the HBM traffic of updating it after every
+// panel, which is what bounded the right-looking update (8 flop per byte instead of 4 ... 1).
+template <int DEPTH>
+__global__ void __launch_bounds__(128, DEPTH == 64 ? 3 : 4) lu_update_region_kernel(
+    int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k0, int depth, int c_lo, int c_hi, int i_lo, int i_hi,
+    double* __restrict__ K, GfWork work, int nwork) {
+    // depth <= DEPTH (a multiple of 4): the shared tiles are sized for DEPTH
+    constexpr int T = 128, TN = 64;
+    constexpr int AP = DEPTH + 4;  // pitch of the A tile (== 4 or 12 mod 16: conflict-free fragment loads)
+    constexpr int BP = TN + 4;     // pitch of the B tile
+    extern __shared__ double usm[];
+    double* As = usm;             // 64 x AP
+    double* Bs = usm + 64 * AP;   // DEPTH x BP
+    for (int wi = blockIdx.z; wi < nwork; wi += gridDim.z) {
+        const int b = gf_instance(work, wi);
+        if (b < 0) return;
+        const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+        const int ce = c_hi < 0 ? N : min(c_hi, N), ie = i_hi < 0 ? N : min(i_hi, N);
+        const int c0 = c_lo + blockIdx.y * 64, i0 = i_lo + blockIdx.x * TN;
+        if (c0 >= ce || i0 >= ie) continue;
+        double* Kb = K + (size_t)b * ld * ld;
+        const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+        const int wm = wid >> 1, wn = wid & 1, g = lane >> 2, q = lane & 3;
+        double acc[4][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int c = c0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int i = i0 + wn * 32 + ni * 8 + 2 * q;
+                const double* cp = Kb + (size_t)c * ld + i;
+                acc[mi][ni][0] = (c < ce && i < ie) ? cp[0] : 0.0;
+                acc[mi][ni][1] = (c < ce && i + 1 < ie) ? cp[1] : 0.0;
+            }
+        }
+        for (int e = tid; e < 64 * depth; e += T) {
+            const int c = e / depth, k = e - c * depth;
+            As[c * AP + k] = (c0 + c < ce) ? Kb[(size_t)(c0 + c) * ld + k0 + k] : 0.0;
+        }
+        for (int e = tid; e < depth * TN; e += T) {
+            const int k = e / TN, i = e % TN;
+            Bs[k * BP + i] = (i0 + i < ie) ? Kb[(size_t)(k0 + k) * ld + i0 + i] : 0.0;
+        }
+        __syncthreads();
+        const double* as = As + (wm * 32 + g) * AP + q;
+        const double* bs = Bs + q * BP + wn * 32 + g;
+#pragma unroll 4
+        for (int kk = 0; kk < depth; kk += 4) {
+            double a[4], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = lu_dneg(as[mi * 8 * AP + kk]);
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) bf[ni] = bs[kk * BP + ni * 8];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int c = c0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int i = i0 + wn * 32 + ni * 8 + 2 * q;
+                double* cp = Kb + (size_t)c * ld + i;
+                if (c < ce && i < ie) cp[0] = acc[mi][ni][0];
+                if (c < ce && i + 1 < ie) cp[1] = acc[mi][ni][1];
+            }
+        }
+        __syncthreads();  // the shared tiles are reused by the next work item
+    }
+}
+
+// Pipelined variant of the region update: persistent CTAs walk the (matrix, tile) list; while the DMMAs of one 64 x 64
+// tile run, the operand tiles of the NEXT one stream into the other shared-memory stage (8-byte cp.async with zero fill
+// at the ragged edges -- rows of K are only 8-byte aligned when ld is odd) and its C values into registers, so every CTA
+// keeps one tile's worth of loads (~100 KB) in flight behind its math instead of alternating load / compute / store.
+__device__ __forceinline__ void cp_async8_zfill(void* smem, const void* gmem, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(n));
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(256, DEPTH == 64 ? 1 : 2) lu_update_pipe_kernel(
+    int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k0, int depth, int c_lo, int c_hi, int i_lo, int i_hi,
+    int ntc, int nti, double* __restrict__ K, GfWork work, int nwork) {
+    constexpr int T = 256;
+    constexpr int AP = DEPTH + 4, BP = 64 + 4;
+    constexpr int STAGE = 64 * AP + DEPTH * BP;
+    extern __shared__ double usm[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm = wid >> 2, wn = wid & 3, g = lane >> 2, q = lane & 3;  // 2 x 4 warps of 32 x 16
+    const long total = (long)nwork * ntc * nti;
+
+    struct Tile { double* Kb; int c0, i0, ce, ie; bool ok; };
+    auto decode = [&](long t) {
+        Tile tl;
+        tl.ok = false;
+        if (t >= total) return tl;
+        const int wi = (int)(t / (ntc * nti)), r = (int)(t - (long)wi * ntc * nti);
+        const int b = gf_instance(work, wi);
+        if (b < 0) return tl;
+        const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+        tl.ce = c_hi < 0 ? N : min(c_hi, N);
+        tl.ie = i_hi < 0 ? N : min(i_hi, N);
+        tl.c0 = c_lo + (r / nti) * 64;
+        tl.i0 = i_lo + (r % nti) * 64;
+        tl.Kb = K + (size_t)b * ld * ld;
+        tl.ok = tl.c0 < tl.ce && tl.i0 < tl.ie;
+        return tl;
+    };
+    auto fetch_operands = [&](const Tile& tl, int stage) {
+        double* As = usm + stage * STAGE;
+        double* Bs = As + 64 * AP;
+        for (int e = tid; e < 64 * depth; e += T) {
+            const int c = e / depth, k = e - c * depth;
+            const bool v = tl.c0 + c < tl.ce;
+            cp_async8_zfill(As + c * AP + k, tl.Kb + (size_t)(v ? tl.c0 + c : tl.c0) * ld + k0 + k, v);
+        }
+        for (int e = tid; e < depth * 64; e += T) {
+            const int k = e >> 6, i = e & 63;
+            const bool v = tl.i0 + i < tl.ie;
+            cp_async8_zfill(Bs + k * BP + i, tl.Kb + (size_t)(k0 + k) * ld + (v ? tl.i0 + i : tl.i0), v);
+        }
+    };
+    auto fetch_c = [&](const Tile& tl, double (&cv)[4][2][2]) {
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int c = tl.c0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) {
+                const int i = tl.i0 + wn * 16 + ni * 8 + 2 * q;
+                const double* cp = tl.Kb + (size_t)c * ld + i;
+                cv[mi][ni][0] = (c < tl.ce && i < tl.ie) ? cp[0] : 0.0;
+                cv[mi][ni][1] = (c < tl.ce && i + 1 < tl.ie) ? cp[1] : 0.0;
+            }
+        }
+    };
+
+    // first valid tile of this CTA
+    long t = blockIdx.x;
+    Tile cur = decode(t);
+    while (t < total && !cur.ok) { t += gridDim.x; cur = decode(t); }
+    if (t >= total) return;
+    double acc[4][2][2], nxt[4][2][2];
+    int stage = 0;
+    fetch_operands(cur, 0);
+    cp_async_commit();
+    fetch_c(cur, acc);
+    while (true) {
+        // the next valid tile
+        long tn = t + gridDim.x;
+        Tile nx = decode(tn);
+        while (tn < total && !nx.ok) { tn += gridDim.x; nx = decode(tn); }
+        const bool more = tn < total;
+        cp_async_wait<0>();
+        __syncthreads();  // stage `stage` has landed; everybody is done with stage ^ 1 (previous tile's math)
+        if (more) {
+            fetch_operands(nx, stage ^ 1);
+            fetch_c(nx, nxt);
+        }
+        cp_async_commit();
+        const double* As = usm + stage * STAGE;
+        const double* Bs = As + 64 * AP;
+        const double* as = As + (wm * 32 + g) * AP + q;
+        const double* bs = Bs + q * BP + wn * 16 + g;
+#pragma unroll 4
+        for (int kk = 0; kk < depth; kk += 4) {
+            double a[4], bf[2];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = lu_dneg(as[mi * 8 * AP + kk]);
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) bf[ni] = bs[kk * BP + ni * 8];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], bf[ni]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int c = cur.c0 + wm * 32 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) {
+                const int i = cur.i0 + wn * 16 + ni * 8 + 2 * q;
+                double* cp = cur.Kb + (size_t)c * ld + i;
+                if (c < cur.ce && i < cur.ie) cp[0] = acc[mi][ni][0];
+                if (c < cur.ce && i + 1 < cur.ie) cp[1] = acc[mi][ni][1];
+            }
+        }
+        if (!more) break;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) { acc[mi][ni][0] = nxt[mi][ni][0]; acc[mi][ni][1] = nxt[mi][ni][1]; }
+        cur = nx;
+        t = tn;
+        stage ^= 1;
+    }
+}
+
 constexpr int LU_GRID_CAP = 256;
+
+template <int DEPTH>
+int launch_update_region(int ld, int Nmax, const int32_t* Nvec, double* K, GfWork w, int nwork, cudaStream_t s, int k0,
+                         int depth, int c_lo, int c_hi, int i_lo, int i_hi) {
+    if (depth <= 0) return GF_OK;
+    const int cn = (c_hi < 0 ? Nmax : (c_hi < Nmax ? c_hi : Nmax)) - c_lo, in = (i_hi < 0 ? Nmax : (i_hi < Nmax ? i_hi : Nmax)) - i_lo;
+    if (cn <= 0 || in <= 0) return GF_OK;
+    // regions with many tiles per matrix (the bulk updates): persistent pipelined CTAs
+    static const int pipe_min = getenv("GF_LU_PIPE_MIN") ? atoi(getenv("GF_LU_PIPE_MIN")) : 4;
+    const int ntc = (cn + 63) / 64, nti = (in + 63) / 64;
+    if (DEPTH == 64 && (long)ntc * nti >= pipe_min && w.count_dev == nullptr) {
+        constexpr int PSMEM = 2 * (64 * (DEPTH + 4) + DEPTH * 68) * (int)sizeof(double);
+        cudaFuncSetAttribute(lu_update_pipe_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM);
+        const long total = (long)nwork * ntc * nti;
+        const int slots = 148 * (DEPTH == 64 ? 1 : 2);
+        const int grid = total < slots ? (int)total : slots;
+        lu_update_pipe_kernel<DEPTH><<<grid, 256, PSMEM, s>>>(ld, Nvec, Nmax, k0, depth, c_lo, c_hi, i_lo, i_hi, ntc, nti, K,
+                                                             w, nwork);
+        return gf_launch_status();
+    }
+    const int gz = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
+    dim3 grid((in + 63) / 64, (cn + 63) / 64, gz);
+    constexpr int USMEM = (64 * (DEPTH + 4) + DEPTH * 68) * (int)sizeof(double);
+    if (USMEM > 48 * 1024)
+        cudaFuncSetAttribute(lu_update_region_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, USMEM);
+    lu_update_region_kernel<DEPTH><<<grid, 128, USMEM, s>>>(ld, Nvec, Nmax, k0, depth, c_lo, c_hi, i_lo, i_hi, K, w, nwork);
+    return gf_launch_status();
+}
 
 template <int NB>
 int launch_panel(int ld, int Nmax, const int32_t* Nvec, int Nfixed, double* K, int32_t* piv, int32_t* info,
-                 GfWork w, int nwork, cudaStream_t s, int jstart = 0, int one_column = 0) {
+                 GfWork w, int nwork, cudaStream_t s, int jstart = 0, int one_column = 0, int trsm_end = -1) {
     const size_t smem = ((size_t)NB * ((Nmax - jstart) | 1) + 8 * NB) * sizeof(double);
     if (smem > 227 * 1024) return GF_ERR_UNSUPPORTED;
     cudaFuncSetAttribute(lu_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // a device-side count may be far below nwork (fallback lists): bound the grid, the CTAs stride
     const int grid = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
-    lu_panel_kernel<NB><<<grid, 256, smem, s>>>(ld, Nvec, Nfixed, K, piv, info, w, jstart, one_column, nwork);
+    lu_panel_kernel<NB><<<grid, 256, smem, s>>>(ld, Nvec, Nfixed, K, piv, info, w, jstart, one_column, nwork, trsm_end);
     return gf_launch_status();
 }
 
 // One block column of the multi-launch factorisation: pivoted panel (one CTA per matrix), then the DMMA update.
 // R > 0: register-resident panel, R rows per thread (rows left <= 512 R); R = 0: the shared-memory panel.
+// developer timing (GF_LU_TIMING=1): CUDA events around every launch of the multi-launch path, summed per kernel type
+struct LuTiming {
+    bool on;
+    std::vector<cudaEvent_t> ev;   // triples are not needed: events alternate begin / end
+    std::vector<int> kind;         // 0 panel, 1 update
+};
+static LuTiming g_lu_timing = {getenv("GF_LU_TIMING") != nullptr, {}, {}};
+static void lu_time_mark(cudaStream_t s, int kind) {
+    if (!g_lu_timing.on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    g_lu_timing.ev.push_back(e);
+    g_lu_timing.kind.push_back(kind);
+}
+static void lu_time_report(cudaStream_t s) {
+    if (!g_lu_timing.on || g_lu_timing.ev.empty()) return;
+    cudaStreamSynchronize(s);
+    float tot[2] = {0.f, 0.f};
+    for (size_t i = 0; i + 1 < g_lu_timing.ev.size(); i += 2) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_lu_timing.ev[i], g_lu_timing.ev[i + 1]);
+        tot[g_lu_timing.kind[i]] += ms;
+    }
+    float all = 0.f;
+    cudaEventElapsedTime(&all, g_lu_timing.ev.front(), g_lu_timing.ev.back());
+    fprintf(stderr, "[gf_lu timing] panel %.3f ms, update %.3f ms, first-to-last %.3f ms, %zu launches\n", tot[0], tot[1], all,
+            g_lu_timing.ev.size() / 2);
+    for (cudaEvent_t e : g_lu_timing.ev) cudaEventDestroy(e);
+    g_lu_timing.ev.clear();
+    g_lu_timing.kind.clear();
+}
+
+// U12 of block column j0 for the storage rows c >= c_lo (the columns beyond the panel's 64-column super-block), after
+// their delayed update: u = L11^{-1} K[c][j0 .. j0 + jb), forward substitution in the order of the panel kernels' own
+// U12 step.  Thread per storage row, L11 (unit lower; position k of column q = K[j0 + q][j0 + k]) in shared memory.
+template <int NB>
+__global__ void __launch_bounds__(256) lu_trsm_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed, int j0,
+                                                      int c_lo, double* __restrict__ K, GfWork work, int nwork) {
+    __shared__ double L11[NB][NB + 1];
+    for (int wi = blockIdx.y; wi < nwork; wi += gridDim.y) {
+        const int b = gf_instance(work, wi);
+        if (b < 0) return;
+        const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
+        if (c_lo >= N || j0 >= N) continue;
+        const int jb = min(NB, N - j0);
+        double* Kb = K + (size_t)b * ld * ld;
+        for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+            const int k = e / NB, q = e - k * NB;
+            L11[k][q] = (k < jb && q < k) ? Kb[(size_t)(j0 + q) * ld + j0 + k] : 0.0;
+        }
+        __syncthreads();
+        const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
+        if (c < N) {
+            double* rowp = Kb + (size_t)c * ld + j0;
+            double u[NB];
+#pragma unroll
+            for (int k = 0; k < NB; k++) u[k] = (k < jb) ? rowp[k] : 0.0;
+#pragma unroll
+            for (int k = 1; k < NB; k++) {
+                double sacc = u[k];
+#pragma unroll
+                for (int q = 0; q < k; q++) sacc = fma(-L11[k][q], u[q], sacc);
+                u[k] = sacc;
+            }
+#pragma unroll
+            for (int k = 0; k < NB; k++)
+                if (k < jb) rowp[k] = u[k];
+        }
+        __syncthreads();
+    }
+}
+
+// Block column j0 (width NB) of the multi-launch factorisation, delayed-update scheme by 64-column super-blocks:
+//   1. pivoted panel (one CTA per matrix): factorisation, interchanges on every storage row of its super-block and
+//      beyond, U12 for the later storage rows INSIDE the super-block (they are kept fully up to date, step 4) -- and
+//      for all later rows when the panel is the first of its super-block (nothing is pending then);
+//   2. storage rows beyond the super-block: the interchanges have just moved positions of the panel's range in from
+//      anywhere below, so only now the pending contributions of the super-block's earlier panels (depth j0 - jS) are
+//      applied to that range, left-looking;
+//   3. ... and their U12 (lu_trsm_kernel);
+//   4. the rest of the super-block's own storage rows is updated right away (depth NB, all later positions).
+// The bulk -- storage rows and positions beyond the super-block -- is updated once per super-block with depth 64
+// (gf_lu_factor), half to an eighth of the HBM traffic of updating it after every panel.
 template <int NB, int R>
 int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info, GfWork w, int nwork,
                   cudaStream_t s, int j0) {
+    // Delayed updates pay where the panels are narrow (8 / 16 columns: orders above 1024, N = 2048: 1064 -> 676 ms);
+    // with 32-wide panels the depth-64 update kernel loses what the halved traffic gains (N = 512: 56.7 vs 52.4 ms),
+    // so there the plain right-looking update stays.  GF_LU_DELAY=0 / 1 forces one or the other.
+    static const int delay_req = getenv("GF_LU_DELAY") ? atoi(getenv("GF_LU_DELAY")) : -1;
+    const bool nodelay = delay_req == 0 || (delay_req < 0 && Nmax < 1024);
+    const int jS = j0 & ~63, jn = j0 + NB;
+    const int send = (jS + 64) < Nmax ? (jS + 64) : Nmax;
+    const bool first = (j0 == jS) || nodelay;
+    const int trsm_end = first ? -1 : send;
     int rc;
+    lu_time_mark(s, 0);
     if constexpr (R > 0) {
         int threads = ((Nmax - j0 + R - 1) / R + 31) & ~31;
         threads = threads < 256 ? 256 : (threads > 512 ? 512 : threads);
         const int grid = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
-        lu_regpanel_kernel<NB, R, 512><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork);
+        lu_regpanel_kernel<NB, R, 512><<<grid, threads, 0, s>>>(ld, Nvec, Nmax, K, piv, info, w, j0, nwork, trsm_end);
         rc = gf_launch_status();
     } else {
-        rc = launch_panel<NB>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s, j0, 1);
+        rc = launch_panel<NB>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s, j0, 1, trsm_end);
     }
+    lu_time_mark(s, 0);
     if (rc != GF_OK) return rc;
-    const int tr = Nmax - j0 - NB;
-    if (tr > 0) {
-        static const int tn = getenv("GF_LU_TN") ? atoi(getenv("GF_LU_TN")) : 64;  // 128: the wider tile, 3-7 % slower
+    if (nodelay) {  // the plain right-looking update of the whole trailing matrix (fully unrolled depth-NB kernel)
+        const int tr = Nmax - jn;
+        if (tr <= 0) return GF_OK;
+        lu_time_mark(s, 1);
         const int gz = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
-        if (tn == 64) {
-            dim3 grid((tr + 63) / 64, (tr + 63) / 64, gz);
-            constexpr int USMEM = (64 * (NB + 4) + NB * 68) * (int)sizeof(double);
-            lu_update_kernel<NB, 64><<<grid, 128, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w, nwork);
-        } else {
-            dim3 grid((tr + 127) / 128, (tr + 63) / 64, gz);
-            constexpr int USMEM = (64 * (NB + 4) + NB * 132) * (int)sizeof(double);
-            cudaFuncSetAttribute(lu_update_kernel<NB, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, USMEM);
-            lu_update_kernel<NB, 128><<<grid, 256, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w, nwork);
-        }
-        rc = gf_launch_status();
+        dim3 grid((tr + 63) / 64, (tr + 63) / 64, gz);
+        constexpr int USMEM = (64 * (NB + 4) + NB * 68) * (int)sizeof(double);
+        lu_update_kernel<NB, 64><<<grid, 128, USMEM, s>>>(ld, Nvec, Nmax, j0, K, w, nwork);
+        lu_time_mark(s, 1);
+        return gf_launch_status();
     }
+    lu_time_mark(s, 1);
+    if (!first && send < Nmax) {
+        rc = launch_update_region<64>(ld, Nmax, Nvec, K, w, nwork, s, jS, j0 - jS, send, -1, j0, jn < send ? jn : send);
+        if (rc != GF_OK) return rc;
+        const int rows = Nmax - send;
+        const int gy = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
+        lu_trsm_kernel<NB><<<dim3((rows + 255) / 256, gy), 256, 0, s>>>(ld, Nvec, Nmax, j0, send, K, w, nwork);
+        rc = gf_launch_status();
+        if (rc != GF_OK) return rc;
+    }
+    if (jn < send) rc = launch_update_region<NB>(ld, Nmax, Nvec, K, w, nwork, s, j0, NB, jn, send, jn, -1);
+    lu_time_mark(s, 1);
     return rc;
+}
+
+// Lanes (experiment, off by default): the batch split into parts whose launch sequences run on separate streams, so that
+// one part's update could run beside another part's panel.  It cannot: see GF_LU_LANES in gf_lu_factor.
+constexpr int LU_MAX_LANES = 8;
+constexpr int LU_LANES_MIN = 512;  // matrices from which the split pays
+struct LuLanes {
+    cudaStream_t s[LU_MAX_LANES];
+    cudaEvent_t fork, join[LU_MAX_LANES];
+    bool ok;
+};
+LuLanes* lu_lanes() {
+    static std::mutex mu;
+    static LuLanes lanes[64];
+    static bool made[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    LuLanes& L = lanes[dev];
+    if (!made[dev]) {
+        made[dev] = true;
+        L.ok = cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < LU_MAX_LANES; i++) {
+            L.ok = L.ok && cudaStreamCreateWithFlags(&L.s[i], cudaStreamNonBlocking) == cudaSuccess;
+            L.ok = L.ok && cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+    }
+    return L.ok ? &L : nullptr;
 }
 
 }  // namespace
@@ -1173,6 +1550,32 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
     if (nwork_dev != nullptr && Nmax <= 830) return launch_panel<32>(ld, Nmax, Nvec, Nmax, K, piv, info, w, nwork, s);
     // Multi-launch right-looking factorisation: per block column a pivoted panel kernel (panel resident in shared
     // memory, so its width follows the rows that are left) and the DMMA trailing update.
+    // GF_LU_LANES: parts of the batch whose launch sequences interleave on separate streams.  Measured: no gain (N = 512,
+    // B = 4096: 53.4 ms for 1, 2, 4 and 8 lanes) -- the panel kernel holds all of an SM's registers, so another part's
+    // update cannot co-reside with it; off by default (1), kept for the record
+    static const int lanes_req = [] {
+        const char* e = getenv("GF_LU_LANES");
+        const int v = e == nullptr ? 1 : atoi(e);
+        return v < 2 ? 1 : (v > LU_MAX_LANES ? LU_MAX_LANES : v);
+    }();
+    LuLanes* L = (lanes_req > 1 && nwork >= LU_LANES_MIN && nwork_dev == nullptr) ? lu_lanes() : nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (L != nullptr && (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) L = nullptr;
+    static std::mutex issue_mu;  // the lane streams / events are per device: one caller issues at a time (see gf_ldlt.cu)
+    std::unique_lock<std::mutex> issue_lock(issue_mu, std::defer_lock);
+    const int nlane = L != nullptr ? lanes_req : 1;
+    int off[LU_MAX_LANES], cnt[LU_MAX_LANES];
+    cudaStream_t st[LU_MAX_LANES];
+    for (int i = 0; i < nlane; i++) {
+        off[i] = (int)((long)nwork * i / nlane);
+        cnt[i] = (int)((long)nwork * (i + 1) / nlane) - off[i];
+        st[i] = L != nullptr ? L->s[i] : s;
+    }
+    if (L != nullptr) {
+        issue_lock.lock();
+        cudaEventRecord(L->fork, s);
+        for (int i = 0; i < nlane; i++) cudaStreamWaitEvent(L->s[i], L->fork, 0);
+    }
     int j0 = 0, nb = 8;
     while (j0 < Nmax) {
         const int rows = Nmax - j0;
@@ -1181,15 +1584,34 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
         // (the panel lives in registers up to 512 R rows, in shared memory -- 16 wide up to 1700 rows -- beyond)
         const int want = rows <= 512 ? 32 : (rows <= 1700 ? 16 : 8);
         if (want <= nb || j0 % want == 0) nb = want;
-        int rc;
-        if (nb == 32) rc = launch_column<32, 1>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
-        else if (nb == 16 && rows <= 1024) rc = launch_column<16, 2>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
-        else if (nb == 16) rc = launch_column<16, 0>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
-        else if (rows <= 2048) rc = launch_column<8, 4>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
-        else rc = launch_column<8, 0>(ld, Nmax, Nvec, K, piv, info, w, nwork, s, j0);
-        if (rc != GF_OK) return rc;
+        for (int i = 0; i < nlane; i++) {
+            GfWork wl{work, nwork_dev, off[i]};
+            int rc;
+            if (nb == 32) rc = launch_column<32, 1>(ld, Nmax, Nvec, K, piv, info, wl, cnt[i], st[i], j0);
+            else if (nb == 16 && rows <= 1024) rc = launch_column<16, 2>(ld, Nmax, Nvec, K, piv, info, wl, cnt[i], st[i], j0);
+            else if (nb == 16) rc = launch_column<16, 0>(ld, Nmax, Nvec, K, piv, info, wl, cnt[i], st[i], j0);
+            else if (rows <= 2048) rc = launch_column<8, 4>(ld, Nmax, Nvec, K, piv, info, wl, cnt[i], st[i], j0);
+            else rc = launch_column<8, 0>(ld, Nmax, Nvec, K, piv, info, wl, cnt[i], st[i], j0);
+            if (rc != GF_OK) return rc;
+            const int jn = j0 + nb;
+            static const int delay_req = getenv("GF_LU_DELAY") ? atoi(getenv("GF_LU_DELAY")) : -1;
+            const bool nodelay = delay_req == 0 || (delay_req < 0 && Nmax < 1024);
+            if (!nodelay && (jn & 63) == 0 && jn < Nmax) {  // the super-block [jn - 64, jn) is complete: its one depth-64 update
+                lu_time_mark(st[i], 1);
+                rc = launch_update_region<64>(ld, Nmax, Nvec, K, wl, cnt[i], st[i], jn - 64, 64, jn, -1, jn, -1);
+                lu_time_mark(st[i], 1);
+                if (rc != GF_OK) return rc;
+            }
+        }
         j0 += nb;
     }
+    if (L != nullptr) {
+        for (int i = 0; i < nlane; i++) {
+            cudaEventRecord(L->join[i], L->s[i]);
+            cudaStreamWaitEvent(s, L->join[i], 0);
+        }
+    }
+    lu_time_report(s);
     return GF_OK;
 }
 
