@@ -17,7 +17,7 @@ constexpr int ST = 64;        // tile
 constexpr int SK = 32;        // k-chunk
 constexpr int SP = ST + 4;    // shared-memory pitch
 
-__global__ void __launch_bounds__(128) hess_rho_kernel(int n, int m, const double* __restrict__ H,
+__global__ void __launch_bounds__(128, 3) hess_rho_kernel(int n, int m, const double* __restrict__ H,
                                                        const double* __restrict__ J, const double* __restrict__ rho,
                                                        double* __restrict__ out, GfWork work) {
     const int b = gf_instance(work, blockIdx.z);
