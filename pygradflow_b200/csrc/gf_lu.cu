@@ -1192,47 +1192,96 @@ __device__ __forceinline__ void cp_async8_zfill(void* smem, const void* gmem, bo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(n));
 }
 
-template <int DEPTH>
-__global__ void __launch_bounds__(256, DEPTH == 64 ? 1 : 2) lu_update_pipe_kernel(
-    int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k0, int depth, int c_lo, int c_hi, int i_lo, int i_hi,
-    int ntc, int nti, double* __restrict__ K, GfWork work, int nwork) {
+template <int DEPTH, bool VEC>
+__global__ void __launch_bounds__(256, 1) lu_update_pipe_kernel(
+    int ld, const int32_t* __restrict__ Nvec, int Nfixed, int k0, int c_lo, int c_hi, int i_lo, int i_hi, int ntc,
+    int nti, double* __restrict__ K, GfWork work, int nwork) {
+    // depth == DEPTH.  VEC: ld, k0, i_lo even and the matrices 16-byte aligned -> 16-byte cp.async, else 8-byte.
+    // Every CTA owns a contiguous range of the (matrix, tile row, tile column) list and walks it incrementally.
     constexpr int T = 256;
     constexpr int AP = DEPTH + 4, BP = 64 + 4;
     constexpr int STAGE = 64 * AP + DEPTH * BP;
     extern __shared__ double usm[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm = wid >> 2, wn = wid & 3, g = lane >> 2, q = lane & 3;  // 2 x 4 warps of 32 x 16
-    const long total = (long)nwork * ntc * nti;
+    const int tpm = ntc * nti;
+    const long total = (long)nwork * tpm;
+    const long per = (total + gridDim.x - 1) / gridDim.x;
+    const long t_begin = (long)blockIdx.x * per, t_end = t_begin + per < total ? t_begin + per : total;
+    if (t_begin >= t_end) return;
 
-    struct Tile { double* Kb; int c0, i0, ce, ie; bool ok; };
-    auto decode = [&](long t) {
-        Tile tl;
-        tl.ok = false;
-        if (t >= total) return tl;
-        const int wi = (int)(t / (ntc * nti)), r = (int)(t - (long)wi * ntc * nti);
-        const int b = gf_instance(work, wi);
-        if (b < 0) return tl;
-        const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
-        tl.ce = c_hi < 0 ? N : min(c_hi, N);
-        tl.ie = i_hi < 0 ? N : min(i_hi, N);
-        tl.c0 = c_lo + (r / nti) * 64;
-        tl.i0 = i_lo + (r % nti) * 64;
-        tl.Kb = K + (size_t)b * ld * ld;
-        tl.ok = tl.c0 < tl.ce && tl.i0 < tl.ie;
-        return tl;
+    struct Tile { double* Kb; int c0, i0, ce, ie; };
+    struct Cursor { long t; int wi, tc, ti, b, N; };
+    Cursor cu;
+    cu.t = t_begin;
+    cu.wi = (int)(t_begin / tpm);
+    {
+        const int r = (int)(t_begin - (long)cu.wi * tpm);
+        cu.tc = r / nti;
+        cu.ti = r - cu.tc * nti;
+    }
+    cu.b = -2;
+    // advance the cursor to the next tile inside its matrix's range (or past the end); returns false at the end
+    auto settle = [&](Cursor& c, Tile& tl) -> bool {
+        while (c.t < t_end) {
+            if (c.b == -2) {
+                c.b = gf_instance(work, c.wi);
+                c.N = c.b >= 0 ? (Nvec != nullptr ? Nvec[c.b] : Nfixed) : 0;
+            }
+            if (c.b >= 0) {
+                const int ce = c_hi < 0 ? c.N : min(c_hi, c.N), ie = i_hi < 0 ? c.N : min(i_hi, c.N);
+                const int c0 = c_lo + c.tc * 64, i0 = i_lo + c.ti * 64;
+                if (c0 < ce && i0 < ie) {
+                    tl.Kb = K + (size_t)c.b * ld * ld;
+                    tl.c0 = c0; tl.i0 = i0; tl.ce = ce; tl.ie = ie;
+                    return true;
+                }
+            }
+            // skip: next tile
+            ++c.t;
+            if (++c.ti == nti) { c.ti = 0; if (++c.tc == ntc) { c.tc = 0; ++c.wi; c.b = -2; } }
+        }
+        return false;
+    };
+    auto step = [&](Cursor& c) {
+        ++c.t;
+        if (++c.ti == nti) { c.ti = 0; if (++c.tc == ntc) { c.tc = 0; ++c.wi; c.b = -2; } }
     };
     auto fetch_operands = [&](const Tile& tl, int stage) {
         double* As = usm + stage * STAGE;
         double* Bs = As + 64 * AP;
-        for (int e = tid; e < 64 * depth; e += T) {
-            const int c = e / depth, k = e - c * depth;
-            const bool v = tl.c0 + c < tl.ce;
-            cp_async8_zfill(As + c * AP + k, tl.Kb + (size_t)(v ? tl.c0 + c : tl.c0) * ld + k0 + k, v);
-        }
-        for (int e = tid; e < depth * 64; e += T) {
-            const int k = e >> 6, i = e & 63;
-            const bool v = tl.i0 + i < tl.ie;
-            cp_async8_zfill(Bs + k * BP + i, tl.Kb + (size_t)(k0 + k) * ld + (v ? tl.i0 + i : tl.i0), v);
+        if (VEC) {
+            // A: 64 rows x DEPTH doubles = DEPTH/2 16-byte pieces per row
+#pragma unroll
+            for (int e = tid; e < 64 * (DEPTH / 2); e += T) {
+                const int c = e / (DEPTH / 2), k = (e % (DEPTH / 2)) * 2;
+                const bool v = tl.c0 + c < tl.ce;
+                const double* src = tl.Kb + (size_t)(v ? tl.c0 + c : tl.c0) * ld + k0 + k;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(As + c * AP + k);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(src), "r"(v ? 16 : 0));
+            }
+#pragma unroll
+            for (int e = tid; e < DEPTH * 32; e += T) {
+                const int k = e >> 5, i = (e & 31) * 2;
+                const int rem = tl.ie - (tl.i0 + i);           // doubles of this piece inside the range
+                const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+                const double* src = tl.Kb + (size_t)(k0 + k) * ld + (nb ? tl.i0 + i : tl.i0);
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(Bs + k * BP + i);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(src), "r"(nb));
+            }
+        } else {
+#pragma unroll 4
+            for (int e = tid; e < 64 * DEPTH; e += T) {
+                const int c = e / DEPTH, k = e % DEPTH;
+                const bool v = tl.c0 + c < tl.ce;
+                cp_async8_zfill(As + c * AP + k, tl.Kb + (size_t)(v ? tl.c0 + c : tl.c0) * ld + k0 + k, v);
+            }
+#pragma unroll 4
+            for (int e = tid; e < DEPTH * 64; e += T) {
+                const int k = e >> 6, i = e & 63;
+                const bool v = tl.i0 + i < tl.ie;
+                cp_async8_zfill(Bs + k * BP + i, tl.Kb + (size_t)(k0 + k) * ld + (v ? tl.i0 + i : tl.i0), v);
+            }
         }
     };
     auto fetch_c = [&](const Tile& tl, double (&cv)[4][2][2]) {
@@ -1243,28 +1292,28 @@ __global__ void __launch_bounds__(256, DEPTH == 64 ? 1 : 2) lu_update_pipe_kerne
             for (int ni = 0; ni < 2; ni++) {
                 const int i = tl.i0 + wn * 16 + ni * 8 + 2 * q;
                 const double* cp = tl.Kb + (size_t)c * ld + i;
-                cv[mi][ni][0] = (c < tl.ce && i < tl.ie) ? cp[0] : 0.0;
-                cv[mi][ni][1] = (c < tl.ce && i + 1 < tl.ie) ? cp[1] : 0.0;
+                if (VEC && c < tl.ce && i + 1 < tl.ie) {
+                    const double2 v = *reinterpret_cast<const double2*>(cp);
+                    cv[mi][ni][0] = v.x;
+                    cv[mi][ni][1] = v.y;
+                } else {
+                    cv[mi][ni][0] = (c < tl.ce && i < tl.ie) ? cp[0] : 0.0;
+                    cv[mi][ni][1] = (c < tl.ce && i + 1 < tl.ie) ? cp[1] : 0.0;
+                }
             }
         }
     };
 
-    // first valid tile of this CTA
-    long t = blockIdx.x;
-    Tile cur = decode(t);
-    while (t < total && !cur.ok) { t += gridDim.x; cur = decode(t); }
-    if (t >= total) return;
+    Tile cur, nx;
+    if (!settle(cu, cur)) return;
     double acc[4][2][2], nxt[4][2][2];
     int stage = 0;
     fetch_operands(cur, 0);
     cp_async_commit();
     fetch_c(cur, acc);
     while (true) {
-        // the next valid tile
-        long tn = t + gridDim.x;
-        Tile nx = decode(tn);
-        while (tn < total && !nx.ok) { tn += gridDim.x; nx = decode(tn); }
-        const bool more = tn < total;
+        step(cu);
+        const bool more = settle(cu, nx);
         cp_async_wait<0>();
         __syncthreads();  // stage `stage` has landed; everybody is done with stage ^ 1 (previous tile's math)
         if (more) {
@@ -1276,8 +1325,8 @@ __global__ void __launch_bounds__(256, DEPTH == 64 ? 1 : 2) lu_update_pipe_kerne
         const double* Bs = As + 64 * AP;
         const double* as = As + (wm * 32 + g) * AP + q;
         const double* bs = Bs + q * BP + wn * 16 + g;
-#pragma unroll 4
-        for (int kk = 0; kk < depth; kk += 4) {
+#pragma unroll
+        for (int kk = 0; kk < DEPTH; kk += 4) {
             double a[4], bf[2];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++) a[mi] = lu_dneg(as[mi * 8 * AP + kk]);
@@ -1295,8 +1344,12 @@ __global__ void __launch_bounds__(256, DEPTH == 64 ? 1 : 2) lu_update_pipe_kerne
             for (int ni = 0; ni < 2; ni++) {
                 const int i = cur.i0 + wn * 16 + ni * 8 + 2 * q;
                 double* cp = cur.Kb + (size_t)c * ld + i;
-                if (c < cur.ce && i < cur.ie) cp[0] = acc[mi][ni][0];
-                if (c < cur.ce && i + 1 < cur.ie) cp[1] = acc[mi][ni][1];
+                if (VEC && c < cur.ce && i + 1 < cur.ie) {
+                    *reinterpret_cast<double2*>(cp) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                } else {
+                    if (c < cur.ce && i < cur.ie) cp[0] = acc[mi][ni][0];
+                    if (c < cur.ce && i + 1 < cur.ie) cp[1] = acc[mi][ni][1];
+                }
             }
         }
         if (!more) break;
@@ -1305,7 +1358,6 @@ __global__ void __launch_bounds__(256, DEPTH == 64 ? 1 : 2) lu_update_pipe_kerne
 #pragma unroll
             for (int ni = 0; ni < 2; ni++) { acc[mi][ni][0] = nxt[mi][ni][0]; acc[mi][ni][1] = nxt[mi][ni][1]; }
         cur = nx;
-        t = tn;
         stage ^= 1;
     }
 }
@@ -1321,14 +1373,20 @@ int launch_update_region(int ld, int Nmax, const int32_t* Nvec, double* K, GfWor
     // regions with many tiles per matrix (the bulk updates): persistent pipelined CTAs
     static const int pipe_min = getenv("GF_LU_PIPE_MIN") ? atoi(getenv("GF_LU_PIPE_MIN")) : 4;
     const int ntc = (cn + 63) / 64, nti = (in + 63) / 64;
-    if (DEPTH == 64 && (long)ntc * nti >= pipe_min && w.count_dev == nullptr) {
+    if (DEPTH == 64 && depth == DEPTH && (long)ntc * nti >= pipe_min && w.count_dev == nullptr) {
         constexpr int PSMEM = 2 * (64 * (DEPTH + 4) + DEPTH * 68) * (int)sizeof(double);
-        cudaFuncSetAttribute(lu_update_pipe_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM);
         const long total = (long)nwork * ntc * nti;
-        const int slots = 148 * (DEPTH == 64 ? 1 : 2);
-        const int grid = total < slots ? (int)total : slots;
-        lu_update_pipe_kernel<DEPTH><<<grid, 256, PSMEM, s>>>(ld, Nvec, Nmax, k0, depth, c_lo, c_hi, i_lo, i_hi, ntc, nti, K,
-                                                             w, nwork);
+        const int grid = total < 148 ? (int)total : 148;
+        const bool vec = (ld % 2 == 0) && (k0 % 2 == 0) && (i_lo % 2 == 0) && (((size_t)K) % 16 == 0);
+        if (vec) {
+            cudaFuncSetAttribute(lu_update_pipe_kernel<DEPTH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM);
+            lu_update_pipe_kernel<DEPTH, true><<<grid, 256, PSMEM, s>>>(ld, Nvec, Nmax, k0, c_lo, c_hi, i_lo, i_hi, ntc, nti,
+                                                                       K, w, nwork);
+        } else {
+            cudaFuncSetAttribute(lu_update_pipe_kernel<DEPTH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM);
+            lu_update_pipe_kernel<DEPTH, false><<<grid, 256, PSMEM, s>>>(ld, Nvec, Nmax, k0, c_lo, c_hi, i_lo, i_hi, ntc, nti,
+                                                                        K, w, nwork);
+        }
         return gf_launch_status();
     }
     const int gz = (w.count_dev != nullptr && nwork > LU_GRID_CAP) ? LU_GRID_CAP : nwork;
@@ -1441,11 +1499,11 @@ __global__ void __launch_bounds__(256) lu_trsm_kernel(int ld, const int32_t* __r
 template <int NB, int R>
 int launch_column(int ld, int Nmax, const int32_t* Nvec, double* K, int32_t* piv, int32_t* info, GfWork w, int nwork,
                   cudaStream_t s, int j0) {
-    // Delayed updates pay where the panels are narrow (8 / 16 columns: orders above 1024, N = 2048: 1064 -> 676 ms);
-    // with 32-wide panels the depth-64 update kernel loses what the halved traffic gains (N = 512: 56.7 vs 52.4 ms),
-    // so there the plain right-looking update stays.  GF_LU_DELAY=0 / 1 forces one or the other.
+    // Delayed updates pay from N = 512 on (B200, B = 4096 / 1024: N = 512 53.4 -> 50.0 ms, N = 1024 106 -> 87 ms,
+    // N = 2048 1064 -> 551 ms); below, the plain right-looking update is as fast.  GF_LU_DELAY=0 / 1 forces one or the
+    // other.
     static const int delay_req = getenv("GF_LU_DELAY") ? atoi(getenv("GF_LU_DELAY")) : -1;
-    const bool nodelay = delay_req == 0 || (delay_req < 0 && Nmax < 1024);
+    const bool nodelay = delay_req == 0 || (delay_req < 0 && Nmax < 512);
     const int jS = j0 & ~63, jn = j0 + NB;
     const int send = (jS + 64) < Nmax ? (jS + 64) : Nmax;
     const bool first = (j0 == jS) || nodelay;
@@ -1595,7 +1653,7 @@ extern "C" int gf_lu_factor(int B, int ld, int Nmax, const int32_t* Nvec, double
             if (rc != GF_OK) return rc;
             const int jn = j0 + nb;
             static const int delay_req = getenv("GF_LU_DELAY") ? atoi(getenv("GF_LU_DELAY")) : -1;
-            const bool nodelay = delay_req == 0 || (delay_req < 0 && Nmax < 1024);
+            const bool nodelay = delay_req == 0 || (delay_req < 0 && Nmax < 512);
             if (!nodelay && (jn & 63) == 0 && jn < Nmax) {  // the super-block [jn - 64, jn) is complete: its one depth-64 update
                 lu_time_mark(st[i], 1);
                 rc = launch_update_region<64>(ld, Nmax, Nvec, K, wl, cnt[i], st[i], jn - 64, 64, jn, -1, jn, -1);
