@@ -155,7 +155,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 //   * panel below the pivot block: W = S_panel Y' (2 DMMAs per 8 rows), L = W D^{-1};
 //   * trailing update S += (-W) L' by 8 x 8 tiles (2 DMMAs each), the next pivot block first, by warp 0, which
 //     keeps it in registers and goes straight on to eliminate it while the other warps finish the update;
-//   * X = inv(L) from the Y blocks by block recursion 8 -> 16 -> 32 -> 64 (DMMA products).
+//   * X = inv(L) by block rows (DMMA products of 8 x 8 tiles) by warps 1..7 while warp 0 is busy with the next pivot block.
 constexpr int DP = NB + 4;                   // pitch of S and X (== 4 mod 16: conflict-free DMMA fragment loads)
 constexpr int WNP = 12;                      // pitch of the -W panel (64 x 8)
 constexpr int TP = 36;                       // pitch of the 32 x 32 product scratch
@@ -163,29 +163,6 @@ constexpr int DG_S = NB * DP;                // S: 64 x 68
 constexpr int DG_OPS = NB * DP;              // X = inv(L): 64 x 68
 constexpr int DG_MISC = NB * WNP + 32 * TP + NB + 2;  // -W panel, product scratch, 1/d, flags
 constexpr int DG_SMEM = (DG_S + DG_OPS + DG_MISC) * (int)sizeof(double);
-
-// For every pair h < npair (o = 2 bs h): Out_h (bs x bs, at Out + oo_h) = +-A_h (at A + ao_h) * B_h (at Bm + bo_h), by
-// 8 x 8 output tiles round-robin over the 8 warps.  Offsets: *_row / *_col multiples of o plus constants.
-struct PairOperand {
-    double* base;
-    int pitch;
-    int pair_stride;  // offset between consecutive pairs
-};
-__device__ __forceinline__ void smem_pair_products(PairOperand Out, PairOperand A, PairOperand Bm, int npair, int tb,
-                                                   bool negate) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
-    const int per = tb * tb;
-    for (int e = wid; e < npair * per; e += 8) {
-        const int h = e / per, r = e - h * per, ti = r / tb, tj = r - ti * tb;
-        double c0 = 0.0, c1 = 0.0;
-        const double* ap = A.base + h * A.pair_stride + (ti * 8 + g) * A.pitch + q;
-        const double* bp = Bm.base + h * Bm.pair_stride + q * Bm.pitch + tj * 8 + g;
-        for (int kk = 0; kk < tb * 8; kk += 4) dmma884(c0, c1, ap[kk], bp[kk * Bm.pitch]);
-        if (negate) { c0 = dneg(c0); c1 = dneg(c1); }
-        *reinterpret_cast<double2*>(Out.base + h * Out.pair_stride + (ti * 8 + g) * Out.pitch + tj * 8 + 2 * q) =
-            make_double2(c0, c1);
-    }
-}
 
 // Factorise the updated diagonal tile of block k, held in shared memory S[64][DP] (lower triangle valid):
 // S = L D L', X = inv(L); writes L / d / inv(L)' to K, d to dvec, pivot diagnostics to info / nneg.
@@ -208,7 +185,6 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
     const int N = Nvec != nullptr ? Nvec[b] : Nfixed;
     const int npos = npos_expected != nullptr ? npos_expected[b] : -1;
     if (tid == 0) { s_bad = 0x7fffffff; s_neg = 0; s_sign = 0; }
-    for (int e = tid; e < NB * NB; e += 256) X[(e >> 6) * DP + (e & 63)] = 0.0;
     TRACE_BEGIN(k, 0);
 
     // ---- factorisation
@@ -221,10 +197,72 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
     __syncthreads();  // X zeroed, flags initialised
     FINE_DECL
     FINE_MARK();
+    // X = inv(L) (unit lower) by block rows, behind warp 0's pivot chain: once Y_i = inv(L_ii) and the block row L[i, 0..i) are
+    // known, X[i][c] = -Y_i sum_{c <= k < i} L[i][k] X[k][c] for c < i.  Warps 1..7 (one 8 x 8 tile each) compute block row
+    // jb - 1 while warp 0 eliminates pivot block jb -- they have nothing else to do there -- so that only the last block row
+    // is left after the loop (the block recursion 8 -> 16 -> 32 -> 64 after the factorisation cost 7-16 k cycles per diagonal block).
+    // No tile above the block diagonal of X is ever read, so X needs no initialisation.
+    auto x_row_tile = [&](int i, int c) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int k = c; k < i; k++) {
+            const double* ap = S + (i * 8 + g) * DP + k * 8 + q;
+            const double* bp = X + (k * 8 + q) * DP + c * 8 + g;
+            dmma884(t0, t1, ap[0], bp[0]);
+            dmma884(t0, t1, ap[4], bp[4 * DP]);
+        }
+        double* scr = T + wid * 64;  // the 8 x 8 product as the B operand of the second product
+        *reinterpret_cast<double2*>(scr + g * 8 + 2 * q) = make_double2(t0, t1);
+        __syncwarp();
+        const double* ya = X + (i * 8 + g) * DP + i * 8 + q;
+        double x0 = 0.0, x1 = 0.0;
+        dmma884(x0, x1, ya[0], scr[q * 8 + g]);
+        dmma884(x0, x1, ya[4], scr[(q + 4) * 8 + g]);
+        __syncwarp();
+        *reinterpret_cast<double2*>(X + (i * 8 + g) * DP + c * 8 + 2 * q) = make_double2(dneg(x0), dneg(x1));
+    };
     for (int jb = 0; jb < 8; jb++) {
         const int c0 = jb * 8;
+        if (wid != 0 && wid < jb) x_row_tile(jb - 1, wid - 1);  // block row jb - 1: tiles c = 0 .. jb - 2
         if (wid == 0) {
             // eliminate the 8 x 8 pivot block in registers
+#ifndef GF_LDLT_PIVOT_SHFL
+            // Every rank-1 update of a pivot step is ONE DMMA whose operands sit in the registers of the lanes that
+            // already own them: column j of P lives in the lanes with q == j / 2 (slot j & 1), which are exactly the lanes
+            // that supply k-slot j / 2 of the A fragment (rows) and of the B fragment (columns) -- no exchange at all.
+            // What is left per pivot is one broadcast of d_j, the reciprocal and the scaling of the column; the shuffle
+            // version below needs six 64-bit shuffles per pivot and ran at 275 cycles per pivot (tools/ldlt_trace).
+            // Y = inv(L_pivot) is updated the same way; its B operand (row j of Y) comes from Z = Y', kept alongside.
+            double y0 = (2 * q == g) ? 1.0 : 0.0, y1 = (2 * q + 1 == g) ? 1.0 : 0.0;
+            double z0 = y0, z1 = y1;
+            double rc0 = 0.0, rc1 = 0.0;
+            double ls0 = 0.0, ls1 = 0.0;                             // L[g][2q], L[g][2q + 1] once their columns are final
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool mine = q == (j >> 1);
+                const double pj = (j & 1) ? p1 : p0;                 // P[g][j] in the lanes with q == j / 2
+                const double dj = __shfl_sync(0xffffffffu, pj, j * 4 + (j >> 1));
+                double r0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(dj));
+                // zero / denormal pivot (the seed flushes to zero): no elimination with it, the column is reported by the
+                // diagnostics.  Tested on the exponent bits of the high word: an FP64 compare would sit on the chain.
+                if ((__double2hiint(dj) & 0x7ff00000) == 0) r0 = 0.0;
+                const double w = (mine && g > j) ? pj : 0.0;         // column j below the pivot, zero elsewhere
+                const double t = w * r0;                             // beside e -> sc on the way to 1 / dj
+                const double e = fma(-dj, r0, 1.0);
+                const double sc = fma(e, e, e);                      // 1 / dj = r0 (1 + e + e^2): cubic in the seed's error
+                const double l = fma(t, sc, t);                      // L[g][j]
+                const double rj = fma(r0, sc, r0);
+                if (j == 2 * q) rc0 = rj;
+                if (j == 2 * q + 1) rc1 = rj;
+                dmma884(p0, p1, dneg(w), l);                         // P[g][n] -= w_g l_n   (g, n > j)
+                const double zj = mine ? ((j & 1) ? z1 : z0) : 0.0;  // Z[n][j] = Y[j][n]
+                dmma884(y0, y1, dneg(l), zj);                        // Y[g][n] -= l_g Y[j][n]
+                dmma884(z0, z1, dneg(zj), l);                        // Z[n][g] -= Y[j][n] l_g
+                // column j is final: L[g][j] is the value the update used (kept apart: a select on p0 / p1 would sit on the
+                // pivot-to-pivot chain)
+                if (mine && g > j) { if (j & 1) ls1 = l; else ls0 = l; }
+            }
+#else
             double y0 = (2 * q == g) ? 1.0 : 0.0, y1 = (2 * q + 1 == g) ? 1.0 : 0.0;
             double rc0 = 0.0, rc1 = 0.0;
 #pragma unroll
@@ -256,19 +294,15 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 y0 = fma(-lr, yj0, y0);
                 y1 = fma(-lr, yj1, y1);
             }
-            // pivots: diagnostics, d, 1/d
-            if ((g >> 1) == q) {
-                const double d = (g & 1) ? p1 : p0;
-                const int jl = c0 + g, j = j0 + jl;
-                if (!(isfinite(d)) || d == 0.0) atomicMin(&s_bad, jl + 1);
-                if (d < 0.0 && j < N) atomicAdd(&s_neg, 1);
-                // quasi-definite sign pattern: the first npos pivots positive, the remaining (up to N) negative
-                if (npos >= 0 && j < N && ((j < npos) != (d > 0.0))) s_sign = 1;
-                dvec[(size_t)b * ld + j] = d;
-                rinv[jl] = (g & 1) ? rc1 : rc0;
-            }
+#endif
+            // 1 / d for the panel below (diagnostics: warp 7, after the barrier)
+            if ((g >> 1) == q) rinv[c0 + g] = (g & 1) ? rc1 : rc0;
             // L (strict lower, scaled), d on the diagonal; Y = inv(L_pivot) into the diagonal block of X
+#ifndef GF_LDLT_PIVOT_SHFL
+            const double l0 = (2 * q < g) ? ls0 : p0, l1 = (2 * q + 1 < g) ? ls1 : p1;
+#else
             const double l0 = (2 * q < g) ? p0 * rc0 : p0, l1 = (2 * q + 1 < g) ? p1 * rc1 : p1;
+#endif
             if (2 * q + 1 <= g) *reinterpret_cast<double2*>(S + (c0 + g) * DP + c0 + 2 * q) = make_double2(l0, l1);
             else if (2 * q == g) S[(c0 + g) * DP + c0 + 2 * q] = l0;
             *reinterpret_cast<double2*>(X + (c0 + g) * DP + c0 + 2 * q) = make_double2(y0, y1);
@@ -276,6 +310,16 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
         FINE_MARK();  // [0] pivot block
         __syncthreads();  // pivot block published; all trailing updates of the previous panel are done
         FINE_MARK();  // [1] barrier
+        // pivot diagnostics and d of this block, off warp 0's critical path: warp 7 has no panel tile (t = jb + 8)
+        if (wid == 7 && lane < 8) {
+            const int jl = c0 + lane, j = j0 + jl;
+            const double d = S[jl * DP + jl];
+            if (!(isfinite(d)) || fabs(d) < 2.2250738585072014e-308) atomicMin(&s_bad, jl + 1);  // zero, denormal, inf, nan
+            if (d < 0.0 && j < N) atomicAdd(&s_neg, 1);
+            // quasi-definite sign pattern: the first npos pivots positive, the remaining (up to N) negative
+            if (npos >= 0 && j < N && ((j < npos) != (d > 0.0))) s_sign = 1;
+            dvec[(size_t)b * ld + j] = d;
+        }
         if (jb == 7) break;
         // panel below the pivot block: row tile t = jb + 1 + wid
         {
@@ -294,7 +338,20 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
             }
         }
         FINE_MARK();  // [2] panel
+        // Warp 0's next pivot block (tile jb + 1, jb + 1) only needs the panel rows warp 0 produced itself (t = jb + 1): it
+        // signals the barrier for the others and goes on.  (Nothing it writes before the next full barrier is read by a
+        // trailing update: diagonal block jb + 1 of S and X, rinv[c0 + 8 ..].)
+#ifndef GF_LDLT_NO_ARRIVE
+        if (wid == 0) {
+            __threadfence_block();
+            asm volatile("bar.arrive 1, 256;" ::: "memory");
+            __syncwarp();
+        } else {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+#else
         __syncthreads();
+#endif
         FINE_MARK();  // [3] barrier
         // trailing update by 8 x 8 tiles (ti, tj), jb < tj <= ti < 8: warp 0 takes the next pivot block and keeps
         // it in registers, warps 1..7 share the rest
@@ -323,15 +380,9 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
     FINE_FLUSH();
     TRACE_MARK(8);
 
-    // ---- X = inv(L) (unit lower) by block recursion: X[hi, lo] = -X[hi, hi] (L[hi, lo] X[lo, lo]) for the pairs of
-    // diagonal blocks of size bs = 8, 16, 32 (the pairs of one level are independent)
-    for (int bs = 8; bs < NB; bs *= 2) {
-        const int tb = bs / 8, npair = NB / (2 * bs), ps = 2 * bs * (DP + 1);
-        smem_pair_products({T, TP, bs}, {S + bs * DP, DP, ps}, {X, DP, ps}, npair, tb, false);
-        __syncthreads();
-        smem_pair_products({X + bs * DP, DP, ps}, {X + bs * (DP + 1), DP, ps}, {T, TP, bs}, npair, tb, true);
-        __syncthreads();
-    }
+    // ---- last block row of X = inv(L) (the loop left at its barrier after pivot block 7)
+    if (wid < 7) x_row_tile(7, wid);
+    __syncthreads();
     TRACE_MARK(9);
 
     // ---- write back: L (strict lower), d (diagonal), inv(L)' (strict upper)

@@ -47,6 +47,27 @@ __global__ void bench(double* out, int iters) {
             double s = fma(e, e, e);
             x = fma(-r, s, x);
         }
+        if (MODE == 6) {  // pivot step on the tensor pipe only: shfl -> MUFU -> 5 dependent DMMAs (k = 0 slot used)
+            const bool q0 = (lane & 3) == 0;
+            double d = __shfl_sync(0xffffffffu, x, it & 31);
+            double r; asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+            double e0 = 1.0, e1 = 1.0;
+            dmma884(e0, e1, q0 ? -d : 0.0, q0 ? r : 0.0);          // e = 1 - d r
+            double s0 = e0, s1 = e0;
+            dmma884(s0, s1, q0 ? e0 : 0.0, q0 ? e0 : 0.0);         // sc = e + e e
+            double t0_ = r, t1_ = r;
+            dmma884(t0_, t1_, q0 ? r : 0.0, q0 ? s0 : 0.0);        // rj = r + r sc
+            double m0 = 0.0, m1 = 0.0;
+            dmma884(m0, m1, q0 ? y : 0.0, q0 ? t0_ : 0.0);         // w rj
+            dmma884(w0, w1, q0 ? -y : 0.0, q0 ? m0 : 0.0);         // P -= w (w rj)
+            x = w0 + 1.0;
+        }
+        if (MODE == 7) {  // two dependent DMMAs only
+            dmma884(w0, w1, x, y);
+            double m0 = 0.0, m1 = 0.0;
+            dmma884(m0, m1, w0, y);
+            x = m0;
+        }
         if (MODE == 5) {  // 4 independent DFMAs then 1 dependent
             double a0 = fma(x, y, z), a1 = fma(x, z, y), a2 = fma(y, x, x), a3 = fma(z, x, x);
             x = (a0 + a1) + (a2 + a3);
@@ -76,5 +97,7 @@ int main() {
     run<3>("dependent MUFU.RCP64H", out);
     run<4>("pivot step shfl+MUFU+3 DFMA", out);
     run<5>("4 indep DFMA + 3 DADD tree", out);
+    run<6>("pivot step shfl+MUFU+5 dep DMMA", out);
+    run<7>("2 dependent DMMA (through a operand)", out);
     return 0;
 }
