@@ -235,7 +235,6 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
             double y0 = (2 * q == g) ? 1.0 : 0.0, y1 = (2 * q + 1 == g) ? 1.0 : 0.0;
             double z0 = y0, z1 = y1;
             double rc0 = 0.0, rc1 = 0.0;
-            double ls0 = 0.0, ls1 = 0.0;                             // L[g][2q], L[g][2q + 1] once their columns are final
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const bool mine = q == (j >> 1);
@@ -243,9 +242,7 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 const double dj = __shfl_sync(0xffffffffu, pj, j * 4 + (j >> 1));
                 double r0;
                 asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(dj));
-                // zero / denormal pivot (the seed flushes to zero): no elimination with it, the column is reported by the
-                // diagnostics.  Tested on the exponent bits of the high word: an FP64 compare would sit on the chain.
-                if ((__double2hiint(dj) & 0x7ff00000) == 0) r0 = 0.0;
+                if (dj == 0.0) r0 = 0.0;
                 const double w = (mine && g > j) ? pj : 0.0;         // column j below the pivot, zero elsewhere
                 const double t = w * r0;                             // beside e -> sc on the way to 1 / dj
                 const double e = fma(-dj, r0, 1.0);
@@ -258,9 +255,8 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 const double zj = mine ? ((j & 1) ? z1 : z0) : 0.0;  // Z[n][j] = Y[j][n]
                 dmma884(y0, y1, dneg(l), zj);                        // Y[g][n] -= l_g Y[j][n]
                 dmma884(z0, z1, dneg(zj), l);                        // Z[n][g] -= Y[j][n] l_g
-                // column j is final: L[g][j] is the value the update used (kept apart: a select on p0 / p1 would sit on the
-                // pivot-to-pivot chain)
-                if (mine && g > j) { if (j & 1) ls1 = l; else ls0 = l; }
+                // column j is final: keep L[g][j] itself (the value the update used) in its slot
+                if (mine && g > j) { if (j & 1) p1 = l; else p0 = l; }
             }
 #else
             double y0 = (2 * q == g) ? 1.0 : 0.0, y1 = (2 * q + 1 == g) ? 1.0 : 0.0;
@@ -295,11 +291,20 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 y1 = fma(-lr, yj1, y1);
             }
 #endif
-            // 1 / d for the panel below (diagnostics: warp 7, after the barrier)
-            if ((g >> 1) == q) rinv[c0 + g] = (g & 1) ? rc1 : rc0;
+            // pivots: diagnostics, d, 1/d
+            if ((g >> 1) == q) {
+                const double d = (g & 1) ? p1 : p0;
+                const int jl = c0 + g, j = j0 + jl;
+                if (!(isfinite(d)) || d == 0.0) atomicMin(&s_bad, jl + 1);
+                if (d < 0.0 && j < N) atomicAdd(&s_neg, 1);
+                // quasi-definite sign pattern: the first npos pivots positive, the remaining (up to N) negative
+                if (npos >= 0 && j < N && ((j < npos) != (d > 0.0))) s_sign = 1;
+                dvec[(size_t)b * ld + j] = d;
+                rinv[jl] = (g & 1) ? rc1 : rc0;
+            }
             // L (strict lower, scaled), d on the diagonal; Y = inv(L_pivot) into the diagonal block of X
 #ifndef GF_LDLT_PIVOT_SHFL
-            const double l0 = (2 * q < g) ? ls0 : p0, l1 = (2 * q + 1 < g) ? ls1 : p1;
+            const double l0 = p0, l1 = p1;
 #else
             const double l0 = (2 * q < g) ? p0 * rc0 : p0, l1 = (2 * q + 1 < g) ? p1 * rc1 : p1;
 #endif
@@ -310,16 +315,6 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
         FINE_MARK();  // [0] pivot block
         __syncthreads();  // pivot block published; all trailing updates of the previous panel are done
         FINE_MARK();  // [1] barrier
-        // pivot diagnostics and d of this block, off warp 0's critical path: warp 7 has no panel tile (t = jb + 8)
-        if (wid == 7 && lane < 8) {
-            const int jl = c0 + lane, j = j0 + jl;
-            const double d = S[jl * DP + jl];
-            if (!(isfinite(d)) || fabs(d) < 2.2250738585072014e-308) atomicMin(&s_bad, jl + 1);  // zero, denormal, inf, nan
-            if (d < 0.0 && j < N) atomicAdd(&s_neg, 1);
-            // quasi-definite sign pattern: the first npos pivots positive, the remaining (up to N) negative
-            if (npos >= 0 && j < N && ((j < npos) != (d > 0.0))) s_sign = 1;
-            dvec[(size_t)b * ld + j] = d;
-        }
         if (jb == 7) break;
         // panel below the pivot block: row tile t = jb + 1 + wid
         {
@@ -338,20 +333,7 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
             }
         }
         FINE_MARK();  // [2] panel
-        // Warp 0's next pivot block (tile jb + 1, jb + 1) only needs the panel rows warp 0 produced itself (t = jb + 1): it
-        // signals the barrier for the others and goes on.  (Nothing it writes before the next full barrier is read by a
-        // trailing update: diagonal block jb + 1 of S and X, rinv[c0 + 8 ..].)
-#ifndef GF_LDLT_NO_ARRIVE
-        if (wid == 0) {
-            __threadfence_block();
-            asm volatile("bar.arrive 1, 256;" ::: "memory");
-            __syncwarp();
-        } else {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-#else
         __syncthreads();
-#endif
         FINE_MARK();  // [3] barrier
         // trailing update by 8 x 8 tiles (ti, tj), jb < tj <= ti < 8: warp 0 takes the next pivot block and keeps
         // it in registers, warps 1..7 share the rest
@@ -820,11 +802,22 @@ __global__ void __launch_bounds__(256, 2) ldlt_column_kernel(int ld, const int32
                                                              int k, double* __restrict__ K, double* __restrict__ dvec,
                                                              int32_t* __restrict__ info, int32_t* __restrict__ nneg,
                                                              const int32_t* __restrict__ npos_expected, GfWork work,
-                                                             int woff, int cnt, int tiles, KktSrc src) {
+                                                             int woff, int cnt, int tiles, KktSrc src, int order) {
     // 1-D grid of cnt * tiles CTAs: the cnt chain CTAs (the long ones) come first, then the panel tiles
+    // (order 1 / 2, developer experiments GF_LDLT_ORDER: matrix by matrix / panel tiles first)
     const int lin = blockIdx.x;
-    const int wi = lin < cnt ? lin : (lin - cnt) / (tiles - 1);
-    const int tile = lin < cnt ? 0 : 1 + (lin - cnt) % (tiles - 1);
+    int wi, tile;
+    if (order == 0) {
+        wi = lin < cnt ? lin : (lin - cnt) / (tiles - 1);
+        tile = lin < cnt ? 0 : 1 + (lin - cnt) % (tiles - 1);
+    } else if (order == 1) {
+        wi = lin / tiles;
+        tile = lin % tiles;
+    } else {
+        const int np = cnt * (tiles - 1);
+        wi = lin < np ? lin / (tiles - 1) : lin - np;
+        tile = lin < np ? 1 + lin % (tiles - 1) : 0;
+    }
     const int b = gf_instance(work, woff + wi);
     if (b < 0) return;
     extern __shared__ double sm[];
@@ -1100,7 +1093,7 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
                 if (have_p[i]) cudaStreamWaitEvent(st[i], L->evp[i], 0);
                 if (t64 > 0) cudaStreamWaitEvent(L->sp[i], L->evc[i], 0);
                 ldlt_column_kernel<<<cnt[i], 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg, npos_expected, w,
-                                                                    off[i], cnt[i], 1, src);
+                                                                    off[i], cnt[i], 1, src, 0);
                 if (t64 > 0)
                     ldlt_panel64_kernel<<<dim3(t64, cnt[i]), 256, P64_SMEM, L->sp[i]>>>(ld, Nvec, Nmax, k, K, dvec, w, off[i], src);
                 cudaEventRecord(L->evc[i], st[i]);
@@ -1113,6 +1106,7 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
         for (int i = 0; i < 2; i++)
             if (have_p[i]) cudaStreamWaitEvent(st[i], L->evp[i], 0);
     } else {
+    static const int order_req = [] { const char* e = getenv("GF_LDLT_ORDER"); return e == nullptr ? 0 : atoi(e); }();
     // issue order interleaves the lanes launch by launch
     for (int i = 0; i < nlane; i++)
         ldlt_diag0_kernel<<<cnt[i], 256, DG_SMEM, st[i]>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w, off[i], src);
@@ -1121,7 +1115,8 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
         const int tiles = 1 + (below + TM - 1) / TM;      // chain CTA + 128-row panel tiles
         for (int i = 0; i < nlane; i++)
             ldlt_column_kernel<<<tiles * cnt[i], 256, COL_SMEM, st[i]>>>(ld, Nvec, Nmax, k, K, dvec, info, nneg,
-                                                                         npos_expected, w, off[i], cnt[i], tiles, src);
+                                                                         npos_expected, w, off[i], cnt[i], tiles, src,
+                                                                         tiles > 1 ? order_req : 0);
     }
     }
     if (L != nullptr) {
