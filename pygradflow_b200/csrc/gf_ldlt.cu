@@ -131,31 +131,33 @@ __device__ __forceinline__ double dneg(double x) {
     return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ULL);
 }
 
-// 1 / d to ~1 ulp: MUFU seed + two Newton steps (4 dependent DFMAs; __drcp_rn is about twice as long, and this sits
-// on the pivot-to-pivot critical path of the factorisation).  d == 0 gives 0: the pivot is flagged separately.
-__device__ __forceinline__ double fast_rcp(double d) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    return d != 0.0 ? r : 0.0;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Diagonal block: S = L D L' and X = inv(L) for a 64 x 64 tile in shared memory.
 //
-// The FP64 FMA pipe is shared with the DMMAs of the CTA next door, so every dependent scalar FP64 instruction
-// here waits behind 16-cycle DMMAs.  The scheme therefore keeps scalar FP64 work to the unavoidable pivot
-// chain and does everything else as DMMA products:
-//   * 8 panels of 8 columns.  Warp 0 holds the 8 x 8 pivot block in registers (DMMA C layout: lane (g, q) owns
-//     P[g][2q], P[g][2q+1]) and eliminates it with warp shuffles: per pivot one reciprocal, one scale, and
-//     rank-1 updates of P and of Y = inv(L_pivot) -- 10 FP64 warp instructions;
+// A latency problem: 64 dependent pivots.  The FP64 pipe is shared with the DMMAs of the CTA next door and the warp
+// scheduler favours a warp that streams DMMAs over one that waits on a dependent result
+// (tools/fp64_contention_bench.cu, profiles/r02_fp64_contention.txt: a dependent DFMA / DMMA takes 9 / 27 cycles alone,
+// 137 / 280 next to one, 26 000 / 1 000 next to two streaming warps on the sub-partition -- it does not matter which of
+// the two instructions the chain is made of).  The scheme keeps the chain short and everything else off it:
+//   * 8 panels of 8 columns.  Warp 0 holds the 8 x 8 pivot block P in registers in the DMMA C layout (lane (g, q) owns
+//     P[g][2q], P[g][2q+1]).  Column j of P then lives in the lanes with q == j / 2, which are exactly the lanes that supply
+//     k-slot j / 2 of an A fragment (rows) and of a B fragment (columns): the rank-1 update of a pivot step is ONE DMMA
+//     with operands taken from the owning lanes' registers, no exchange.  Per pivot: broadcast d_j (one shuffle), MUFU
+//     reciprocal seed, e = 1 - d r0, sc = e + e^2, l = (w r0)(1 + sc), DMMA.  Y = inv(L_pivot) is updated the same way
+//     (its B operand, row j of Y, comes from Z = Y', kept alongside).  ~200 cycles per pivot (round 1: six 64-bit
+//     shuffles per pivot and scalar updates, 275);
 //   * panel below the pivot block: W = S_panel Y' (2 DMMAs per 8 rows), L = W D^{-1};
 //   * trailing update S += (-W) L' by 8 x 8 tiles (2 DMMAs each), the next pivot block first, by warp 0, which
 //     keeps it in registers and goes straight on to eliminate it while the other warps finish the update;
-//   * X = inv(L) by block rows (DMMA products of 8 x 8 tiles) by warps 1..7 while warp 0 is busy with the next pivot block.
+//   * X = inv(L) by block rows (DMMA products of 8 x 8 tiles) by warps 1..7 while warp 0 is busy with the next pivot
+//     block: only the last block row is left after the loop (the block recursion 8 -> 16 -> 32 -> 64 of round 1 cost
+//     7-16 k cycles per diagonal block after the factorisation).
+// Measured per diagonal block, alone on the SM (tools/ldlt_trace, profiles/r02_ldlt_trace_{before,after}.txt):
+// factor 24.3 k -> 19.5 k cycles, inverse 7.0 k -> 0.9 k.  Tried, not adopted: the row tiles below the pivot block eliminated
+// TOGETHER with it by four warps (the same rank-1 DMMAs applied to the row tile, no inv(L_pivot) on the critical path, no
+// panel phase, trailing update overlapped with the next elimination): every DMMA a chain warp issues costs it ~35 cycles,
+// three per pivot made the elimination 2.15 k cycles per panel and the block 24 k; warp 0 only signalling the second
+// barrier of a panel (bar.arrive) instead of waiting at it: slower (27.9 k).
 constexpr int DP = NB + 4;                   // pitch of S and X (== 4 mod 16: conflict-free DMMA fragment loads)
 constexpr int WNP = 12;                      // pitch of the -W panel (64 x 8)
 constexpr int TP = 36;                       // pitch of the 32 x 32 product scratch
@@ -225,12 +227,11 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
         if (wid != 0 && wid < jb) x_row_tile(jb - 1, wid - 1);  // block row jb - 1: tiles c = 0 .. jb - 2
         if (wid == 0) {
             // eliminate the 8 x 8 pivot block in registers
-#ifndef GF_LDLT_PIVOT_SHFL
             // Every rank-1 update of a pivot step is ONE DMMA whose operands sit in the registers of the lanes that
             // already own them: column j of P lives in the lanes with q == j / 2 (slot j & 1), which are exactly the lanes
             // that supply k-slot j / 2 of the A fragment (rows) and of the B fragment (columns) -- no exchange at all.
             // What is left per pivot is one broadcast of d_j, the reciprocal and the scaling of the column; the shuffle
-            // version below needs six 64-bit shuffles per pivot and ran at 275 cycles per pivot (tools/ldlt_trace).
+            // version of round 1 (six 64-bit shuffles per pivot, scalar updates) ran at 275 cycles per pivot (tools/ldlt_trace).
             // Y = inv(L_pivot) is updated the same way; its B operand (row j of Y) comes from Z = Y', kept alongside.
             double y0 = (2 * q == g) ? 1.0 : 0.0, y1 = (2 * q + 1 == g) ? 1.0 : 0.0;
             double z0 = y0, z1 = y1;
@@ -258,39 +259,6 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 // column j is final: keep L[g][j] itself (the value the update used) in its slot
                 if (mine && g > j) { if (j & 1) p1 = l; else p0 = l; }
             }
-#else
-            double y0 = (2 * q == g) ? 1.0 : 0.0, y1 = (2 * q + 1 == g) ? 1.0 : 0.0;
-            double rc0 = 0.0, rc1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const double pj = (j & 1) ? p1 : p0;
-                const double dj = __shfl_sync(0xffffffffu, pj, j * 4 + (j >> 1));
-                const double wr = __shfl_sync(0xffffffffu, pj, g * 4 + (j >> 1));
-                const double wc0 = __shfl_sync(0xffffffffu, pj, (2 * q) * 4 + (j >> 1));
-                const double wc1 = __shfl_sync(0xffffffffu, pj, (2 * q + 1) * 4 + (j >> 1));
-                const double yj0 = __shfl_sync(0xffffffffu, y0, j * 4 + q);
-                const double yj1 = __shfl_sync(0xffffffffu, y1, j * 4 + q);
-                // 1 / dj = r0 (1 + e + e^2) with e = 1 - dj r0 (cubic: the MUFU seed has ~20 bits).  The pivot-to-pivot
-                // chain is shfl -> MUFU -> e -> s -> fma: the products with r0 and the subtraction run beside it.
-                double r0;
-                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(dj));
-                if (dj == 0.0) r0 = 0.0;
-                const double e = fma(-dj, r0, 1.0);
-                const double sc = fma(e, e, e);
-                // branch-free: entries outside the trailing block get a zero update (r0, sc are finite)
-                const bool below = g > j;
-                const double u0 = (below && 2 * q > j) ? (wr * wc0) * r0 : 0.0;
-                const double u1 = (below && 2 * q + 1 > j) ? (wr * wc1) * r0 : 0.0;
-                const double rj = fma(r0, sc, r0);
-                if (j == 2 * q) rc0 = rj;
-                if (j == 2 * q + 1) rc1 = rj;
-                const double lr = below ? wr * rj : 0.0;
-                p0 = fma(-u0, sc, p0 - u0);
-                p1 = fma(-u1, sc, p1 - u1);
-                y0 = fma(-lr, yj0, y0);
-                y1 = fma(-lr, yj1, y1);
-            }
-#endif
             // pivots: diagnostics, d, 1/d
             if ((g >> 1) == q) {
                 const double d = (g & 1) ? p1 : p0;
@@ -303,11 +271,7 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 rinv[jl] = (g & 1) ? rc1 : rc0;
             }
             // L (strict lower, scaled), d on the diagonal; Y = inv(L_pivot) into the diagonal block of X
-#ifndef GF_LDLT_PIVOT_SHFL
             const double l0 = p0, l1 = p1;
-#else
-            const double l0 = (2 * q < g) ? p0 * rc0 : p0, l1 = (2 * q + 1 < g) ? p1 * rc1 : p1;
-#endif
             if (2 * q + 1 <= g) *reinterpret_cast<double2*>(S + (c0 + g) * DP + c0 + 2 * q) = make_double2(l0, l1);
             else if (2 * q == g) S[(c0 + g) * DP + c0 + 2 * q] = l0;
             *reinterpret_cast<double2*>(X + (c0 + g) * DP + c0 + 2 * q) = make_double2(y0, y1);

@@ -10,7 +10,7 @@ import os
 from ctypes import c_double, c_int, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgradflow_b200.so")
+LIB_PATH = os.environ.get("GF_LIB_PATH") or os.path.join(_HERE, "csrc", "libgradflow_b200.so")  # GF_LIB_PATH: A/B of builds
 
 _P = c_void_p  # device pointer
 _I = c_int
