@@ -215,6 +215,9 @@ int gf_dr_first(int B, const int32_t* status, const int32_t* info, const double*
 int gf_dr_second(int B, const double* dt, const double* diff1, const double* diff2, double theta_max,
                  double log_theta_ref, double K_P, double K_I, double lamb_min, double lamb_inc, double* err_sum,
                  int32_t* phase, double* lamb_next, double* theta, void* stream);
+/* Newton steps of one DistanceRatio outer iteration (the driver's display counter): adds, over all instances, one step for
+ * phase 2..4 and a second one for phase 3, 4 to nsteps (device int64). */
+int gf_count_newton_steps(int B, const int32_t* phase, int64_t* nsteps, void* stream);
 /* ResiduumRatioController.step (residuum_ratio_control.py:18-63; fixed != 0: FixedStepSizeController.step,
  * fixed_control.py:12-19) after their single Newton step; nsteps (device int64) counts the Newton steps taken. */
 int gf_single_control(int B, int fixed, const int32_t* status, const int32_t* info, const double* dt,

@@ -828,6 +828,32 @@ extern "C" int gf_dr_second(int B, const double* dt, const double* diff1, const 
     return gf_launch_status();
 }
 
+// Newton steps of one DistanceRatio outer iteration, counted from the phases after dr_second: one step for an instance that
+// accepted at mid / final or rejected (phase 2..4), a second one where the second step was taken (phase 3, 4).
+__global__ void count_newton_steps_kernel(int B, const int32_t* __restrict__ phase, unsigned long long* __restrict__ nsteps) {
+    __shared__ int part[32];
+    int c = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int ph = phase[b];
+        c += (ph >= 2 && ph <= 4 ? 1 : 0) + (ph == 3 || ph == 4 ? 1 : 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += part[w];
+        if (t > 0) atomicAdd(nsteps, (unsigned long long)t);
+    }
+}
+
+extern "C" int gf_count_newton_steps(int B, const int32_t* phase, int64_t* nsteps, void* stream) {
+    if (B <= 0 || !phase || !nsteps) return GF_ERR_ARG;
+    count_newton_steps_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(B, phase, reinterpret_cast<unsigned long long*>(nsteps));
+    return gf_launch_status();
+}
+
 extern "C" int gf_single_control(int B, int fixed, const int32_t* status, const int32_t* info, const double* dt,
                                  const double* mid_norm, const double* orig_norm, double newton_tol, double theta_max,
                                  double log_theta_ref, double K_P, double K_I, double lamb_red, double lamb_min,

@@ -245,6 +245,10 @@ def dr_second(dt, diff1, diff2, theta_max, log_theta_ref, K_P, K_I, lamb_min, la
           lamb_inc, ptr(err_sum), ptr(phase), ptr(lamb_next), ptr(theta), _stream())
 
 
+def count_newton_steps(phase, nsteps):
+    _call("gf_count_newton_steps", phase.shape[0], ptr(phase), ptr(nsteps), _stream())
+
+
 def single_control(fixed, status, info, dt, mid_norm, orig_norm, prm, err_sum, phase, lamb_next, theta, nsteps):
     _call("gf_single_control", status.shape[0], 1 if fixed else 0, ptr(status), ptr(info), ptr(dt), ptr(mid_norm),
           ptr(orig_norm), prm.newton_tol, prm.theta_max, prm.log_theta_ref, prm.K_P, prm.K_I, prm.lamb_red, prm.lamb_min,

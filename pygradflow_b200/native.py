@@ -42,6 +42,7 @@ SIGNATURES = {
     "gf_check_terminate": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _P, _P, _P] + _WORK,
     "gf_dr_first": [_I, _P, _P, _P, _P, _P, _D, _D, _D, _P, _P, _P],
     "gf_dr_second": [_I, _P, _P, _P, _D, _D, _D, _D, _D, _D, _P, _P, _P, _P, _P],
+    "gf_count_newton_steps": [_I, _P, _P, _P],
     "gf_single_control": [_I, _I, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D, _D, _D, _D, _D, _P, _P, _P, _P, _P, _P],
     "gf_exact_control": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _D, _D, _P, _P, _P, _P, _P, _P],
     "gf_commit": [_I, _I, _I, _P, _P, _D, _I] + [_P] * 10 + [_P] * 10 + [_P],

@@ -481,8 +481,7 @@ class BatchedSolver:
                     prm.lamb_min, prm.lamb_inc, self.err_sum, self.phase, self.lamb_next, self.theta)
         xf, yf, gf, cf, of = self.fin
         prob.eval(xf, gf, cf, of, second)
-        ph = self.phase
-        self.newton_step_count += ((ph >= 2) & (ph <= 4)).sum() + ((ph == 3) | (ph == 4)).sum()
+        K.count_newton_steps(self.phase, self.newton_step_count)  # one launch (was a dozen eager elementwise kernels)
 
     def _control_single(self, fixed: bool):
         """ResiduumRatioController.step (residuum_ratio_control.py:18-63) / FixedStepSizeController.step
