@@ -18,6 +18,8 @@ from dataclasses import dataclass
 from typing import Callable, Optional
 
 import numpy as np
+import os
+
 import torch
 
 from . import kernels as K
@@ -481,7 +483,11 @@ class BatchedSolver:
                     prm.lamb_min, prm.lamb_inc, self.err_sum, self.phase, self.lamb_next, self.theta)
         xf, yf, gf, cf, of = self.fin
         prob.eval(xf, gf, cf, of, second)
-        K.count_newton_steps(self.phase, self.newton_step_count)  # one launch (was a dozen eager elementwise kernels)
+        if os.environ.get("GF_EAGER_COUNT") == "1":  # A/B hook: the counter as the eager elementwise launches it used to be
+            ph = self.phase
+            self.newton_step_count += ((ph >= 2) & (ph <= 4)).sum() + ((ph == 3) | (ph == 4)).sum()
+        else:
+            K.count_newton_steps(self.phase, self.newton_step_count)  # one launch (was a dozen eager elementwise kernels)
 
     def _control_single(self, fixed: bool):
         """ResiduumRatioController.step (residuum_ratio_control.py:18-63) / FixedStepSizeController.step
