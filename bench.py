@@ -250,7 +250,7 @@ def ncu_traffic():
     """DRAM bytes (read + write) of one whole factorisation of the bench batch, summed over its launches, from the
     newest committed `ncu --set full` capture under profiles/ (a profiler run cannot happen inside the timed bench);
     (None, None) when no capture is at hand."""
-    for name in ("r02_ncu_ldlt_factor_dram.json", "r01_ncu_ldlt_factor_dram.json"):
+    for name in ("r02g_ncu_ldlt_factor_dram.json", "r02_ncu_ldlt_factor_dram.json", "r01_ncu_ldlt_factor_dram.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 return float(json.load(f)["dram_bytes_per_factorisation"]), "profiles/" + name
