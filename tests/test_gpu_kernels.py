@@ -434,3 +434,14 @@ def test_fused_assembly_factor_is_bit_identical(K, n, m):
         assert np.array_equal(out[0][1][b, :Np], out[1][1][b, :Np])
     assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
     assert (out[0][2] == 0).all()
+
+
+def test_count_newton_steps_matches_the_phase_expression(K):
+    """gf_count_newton_steps: one step for phase 2..4, a second one for phase 3 / 4, added to the device counter."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for B in (1, 31, 256, 4097):
+        phase = torch.randint(0, 7, (B,), generator=gen, device="cuda", dtype=torch.int32)
+        cnt = torch.full((1,), 11, dtype=torch.int64, device="cuda")
+        K.count_newton_steps(phase, cnt)
+        want = 11 + int((((phase >= 2) & (phase <= 4)).sum() + ((phase == 3) | (phase == 4)).sum()).item())
+        assert int(cnt.item()) == want
