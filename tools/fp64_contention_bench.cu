@@ -10,9 +10,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __device__ long long g_res[8];
 __device__ volatile int g_stop;
 // warps [0, 4): probe warps (one per SMSP); warps [4, 4 + 4*nd): DMMA streamers
-template <int MODE>
+// LAST: the probe warps are the four HIGHEST warp indices of the block instead of the four lowest
+template <int MODE, bool LAST = false>
 __global__ void bench(double* out, int iters) {
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw_ = blockDim.x >> 5;
+    const int wid = LAST ? (int)(nw_ - 1 - (threadIdx.x >> 5)) : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     __shared__ volatile int stop;
     if (threadIdx.x == 0) stop = 0;
     __syncthreads();
@@ -74,16 +76,16 @@ __global__ void bench(double* out, int iters) {
         }
     }
     long long t1 = clock64();
-    if (threadIdx.x == 0) { g_res[0] = t1 - t0; }
+    if (wid == 0 && lane == 0) { g_res[0] = t1 - t0; }
     __syncwarp();
     if (wid == 0 && lane == 0) stop = 1;
     out[blockIdx.x * blockDim.x + threadIdx.x] = x + w0 + w1;
 }
-template <int MODE>
+template <int MODE, bool LAST = false>
 void run(const char* name, double* out) {
     const int iters = 2000;
     for (int nd = 0; nd <= 3; nd++) {
-        bench<MODE><<<1, 32 * (4 + 4 * nd)>>>(out, iters);
+        bench<MODE, LAST><<<1, 32 * (4 + 4 * nd)>>>(out, iters);
         cudaDeviceSynchronize();
         long long r; cudaMemcpyFromSymbol(&r, g_res, 8);
         printf("%-34s DMMA warps/SMSP=%d : %7.1f cycles per step  (%s)\n", name, nd, (double)r / iters, cudaGetErrorString(cudaGetLastError()));
@@ -99,5 +101,8 @@ int main() {
     run<5>("4 indep DFMA + 3 DADD tree", out);
     run<6>("pivot step shfl+MUFU+5 dep DMMA", out);
     run<7>("2 dependent DMMA (through a operand)", out);
+    run<0, true>("dependent DFMA, probe = LAST warps", out);
+    run<2, true>("dependent DMMA, probe = LAST warps", out);
+    run<4, true>("pivot step 3 DFMA, probe = LAST warps", out);
     return 0;
 }
