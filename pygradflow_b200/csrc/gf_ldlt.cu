@@ -169,15 +169,24 @@ constexpr int DG_SMEM = (DG_S + DG_OPS + DG_MISC) * (int)sizeof(double);
 // Factorise the updated diagonal tile of block k, held in shared memory S[64][DP] (lower triangle valid):
 // S = L D L', X = inv(L); writes L / d / inv(L)' to K, d to dvec, pivot diagnostics to info / nneg.
 // Xp (DG_OPS doubles) and misc (DG_MISC doubles) are scratch regions disjoint from S.
+// MERGED (the small-order kernel, where shared memory decides how many matrices an SM holds): X is not a second tile --
+// inv(L)' lives in the strict upper triangle of S itself, as in the global layout (X[r][c], r > c, at S[c][r]; unit
+// diagonal and zeros implied), the 8 x 8 product of x_row_tile changes layout by shuffles instead of through a scratch
+// tile, the -W panel has pitch 10: S + 706 doubles (40 KB) instead of 2 tiles + 1986 doubles (85 KB).  Same arithmetic
+// in the same order: both variants produce the same bits.
+constexpr int WNPM = 10;
+constexpr int DGM_MISC = NB * WNPM + NB + 2;  // -W panel, 1/d, flags
+template <bool MERGED = false>
 __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* misc, int b, int ld,
                                                  const int32_t* __restrict__ Nvec, int Nfixed, int k,
                                                  double* __restrict__ K, double* __restrict__ dvec,
                                                  int32_t* __restrict__ info, int32_t* __restrict__ nneg,
                                                  const int32_t* __restrict__ npos_expected) {
+    constexpr int WP = MERGED ? WNPM : WNP;  // pitch of the -W panel
     const int j0 = k * NB;
-    double* Wn = misc;                       // 64 x WNP : -W of the current panel
-    double* T = Wn + NB * WNP;               // 32 x TP
-    double* rinv = T + 32 * TP;              // 64
+    double* Wn = misc;                       // 64 x WP : -W of the current panel
+    double* T = Wn + NB * WNP;               // 32 x TP (not MERGED)
+    double* rinv = MERGED ? Wn + NB * WNPM : T + 32 * TP;  // 64
     int* flags = reinterpret_cast<int*>(rinv + NB);
     int& s_bad = flags[0];
     int& s_neg = flags[1];
@@ -208,19 +217,47 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
         double t0 = 0.0, t1 = 0.0;
         for (int k = c; k < i; k++) {
             const double* ap = S + (i * 8 + g) * DP + k * 8 + q;
-            const double* bp = X + (k * 8 + q) * DP + c * 8 + g;
-            dmma884(t0, t1, ap[0], bp[0]);
-            dmma884(t0, t1, ap[4], bp[4 * DP]);
+            if constexpr (!MERGED) {
+                const double* bp = X + (k * 8 + q) * DP + c * 8 + g;
+                dmma884(t0, t1, ap[0], bp[0]);
+                dmma884(t0, t1, ap[4], bp[4 * DP]);
+            } else {
+                // B[kk][n] = X[8k + kk][8c + n] sits at S[8c + n][8k + kk]; k == c: the unit lower 8 x 8 block Y_c
+                const double* bp = S + (c * 8 + g) * DP + k * 8 + q;
+                double v0 = bp[0], v1 = bp[4];
+                if (k == c) {
+                    v0 = q > g ? v0 : (q == g ? 1.0 : 0.0);
+                    v1 = q + 4 > g ? v1 : (q + 4 == g ? 1.0 : 0.0);
+                }
+                dmma884(t0, t1, ap[0], v0);
+                dmma884(t0, t1, ap[4], v1);
+            }
         }
-        double* scr = T + wid * 64;  // the 8 x 8 product as the B operand of the second product
-        *reinterpret_cast<double2*>(scr + g * 8 + 2 * q) = make_double2(t0, t1);
-        __syncwarp();
-        const double* ya = X + (i * 8 + g) * DP + i * 8 + q;
         double x0 = 0.0, x1 = 0.0;
-        dmma884(x0, x1, ya[0], scr[q * 8 + g]);
-        dmma884(x0, x1, ya[4], scr[(q + 4) * 8 + g]);
-        __syncwarp();
-        *reinterpret_cast<double2*>(X + (i * 8 + g) * DP + c * 8 + 2 * q) = make_double2(dneg(x0), dneg(x1));
+        if constexpr (!MERGED) {
+            double* scr = T + wid * 64;  // the 8 x 8 product as the B operand of the second product
+            *reinterpret_cast<double2*>(scr + g * 8 + 2 * q) = make_double2(t0, t1);
+            __syncwarp();
+            const double* ya = X + (i * 8 + g) * DP + i * 8 + q;
+            dmma884(x0, x1, ya[0], scr[q * 8 + g]);
+            dmma884(x0, x1, ya[4], scr[(q + 4) * 8 + g]);
+            __syncwarp();
+            *reinterpret_cast<double2*>(X + (i * 8 + g) * DP + c * 8 + 2 * q) = make_double2(dneg(x0), dneg(x1));
+        } else {
+            // T[r][n] is held by lane (r, n / 2), slot n & 1; this lane's B fragment is T[q][g], T[q + 4][g]
+            const int s0 = q * 4 + (g >> 1), s1 = (q + 4) * 4 + (g >> 1);
+            const double ta0 = __shfl_sync(0xffffffffu, t0, s0), ta1 = __shfl_sync(0xffffffffu, t1, s0);
+            const double tb0 = __shfl_sync(0xffffffffu, t0, s1), tb1 = __shfl_sync(0xffffffffu, t1, s1);
+            const double b0 = (g & 1) ? ta1 : ta0, b1 = (g & 1) ? tb1 : tb0;
+            // A[g][kk] = Y_i[g][kk] sits at S[8i + kk][8i + g] for kk < g
+            const double* yp = S + (i * 8 + q) * DP + i * 8 + g;
+            const double a0 = q < g ? yp[0] : (q == g ? 1.0 : 0.0);
+            const double a1 = q + 4 < g ? yp[4 * DP] : (q + 4 == g ? 1.0 : 0.0);
+            dmma884(x0, x1, a0, b0);
+            dmma884(x0, x1, a1, b1);
+            S[(c * 8 + 2 * q) * DP + i * 8 + g] = dneg(x0);      // X[8i + g][8c + 2q] transposed
+            S[(c * 8 + 2 * q + 1) * DP + i * 8 + g] = dneg(x1);
+        }
     };
     for (int jb = 0; jb < 8; jb++) {
         const int c0 = jb * 8;
@@ -274,7 +311,12 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
             const double l0 = p0, l1 = p1;
             if (2 * q + 1 <= g) *reinterpret_cast<double2*>(S + (c0 + g) * DP + c0 + 2 * q) = make_double2(l0, l1);
             else if (2 * q == g) S[(c0 + g) * DP + c0 + 2 * q] = l0;
-            *reinterpret_cast<double2*>(X + (c0 + g) * DP + c0 + 2 * q) = make_double2(y0, y1);
+            if constexpr (!MERGED) {
+                *reinterpret_cast<double2*>(X + (c0 + g) * DP + c0 + 2 * q) = make_double2(y0, y1);
+            } else {  // strictly lower part of Y, transposed into the upper triangle of the pivot block
+                if (2 * q < g) S[(c0 + 2 * q) * DP + c0 + g] = y0;
+                if (2 * q + 1 < g) S[(c0 + 2 * q + 1) * DP + c0 + g] = y1;
+            }
         }
         FINE_MARK();  // [0] pivot block
         __syncthreads();  // pivot block published; all trailing updates of the previous panel are done
@@ -285,15 +327,24 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
             const int t = jb + 1 + wid;
             if (t < 8) {
                 const double* ap = S + (t * 8 + g) * DP + c0 + q;
-                const double* bp = X + (c0 + g) * DP + c0 + q;  // B[kk][n] = Y[n][kk]
                 double w0 = 0.0, w1 = 0.0;
                 const double a0 = ap[0], a1 = ap[4];
-                dmma884(w0, w1, a0, bp[0]);
-                dmma884(w0, w1, a1, bp[4]);
+                double b0, b1;  // B[kk][n] = Y[n][kk], kk = q, q + 4, n = g
+                if constexpr (!MERGED) {
+                    const double* bp = X + (c0 + g) * DP + c0 + q;
+                    b0 = bp[0];
+                    b1 = bp[4];
+                } else {
+                    const double* bp = S + (c0 + q) * DP + c0 + g;  // Y[n][kk] at S[c0 + kk][c0 + n] for n > kk
+                    b0 = g > q ? bp[0] : (g == q ? 1.0 : 0.0);
+                    b1 = g > q + 4 ? bp[4 * DP] : (g == q + 4 ? 1.0 : 0.0);
+                }
+                dmma884(w0, w1, a0, b0);
+                dmma884(w0, w1, a1, b1);
                 __syncwarp();
                 const double2 rv = *reinterpret_cast<const double2*>(rinv + c0 + 2 * q);
                 *reinterpret_cast<double2*>(S + (t * 8 + g) * DP + c0 + 2 * q) = make_double2(w0 * rv.x, w1 * rv.y);
-                *reinterpret_cast<double2*>(Wn + (t * 8 + g) * WNP + 2 * q) = make_double2(dneg(w0), dneg(w1));
+                *reinterpret_cast<double2*>(Wn + (t * 8 + g) * WP + 2 * q) = make_double2(dneg(w0), dneg(w1));
             }
         }
         FINE_MARK();  // [2] panel
@@ -312,7 +363,7 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
                 const int ti = jb + 1 + tr, tj = jb + 1 + tc;
                 double* cp = S + (ti * 8 + g) * DP + tj * 8 + 2 * q;
                 double2 cv = *reinterpret_cast<const double2*>(cp);
-                const double* ap = Wn + (ti * 8 + g) * WNP + q;
+                const double* ap = Wn + (ti * 8 + g) * WP + q;
                 const double* bp = S + (tj * 8 + g) * DP + c0 + q;
                 dmma884(cv.x, cv.y, ap[0], bp[0]);
                 dmma884(cv.x, cv.y, ap[4], bp[4]);
@@ -334,7 +385,7 @@ __device__ __forceinline__ void ldlt_diag_factor(double* S, double* X, double* m
     // ---- write back: L (strict lower), d (diagonal), inv(L)' (strict upper)
     for (int e = tid; e < NB * NB; e += blockDim.x) {
         const int r = e >> 6, c = e & 63;
-        const double v = (c <= r) ? S[r * DP + c] : X[c * DP + r];  // K[j0 + r][j0 + c] = X[c][r], c > r
+        const double v = (MERGED || c <= r) ? S[r * DP + c] : X[c * DP + r];  // K[j0 + r][j0 + c] = X[c][r], c > r
         Kb[(size_t)(j0 + r) * ld + j0 + c] = v;
     }
     if (tid == 0) {
@@ -848,6 +899,136 @@ __global__ void __launch_bounds__(256, 2) ldlt_whole_kernel(int ld, const int32_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Padded order <= 128 (one or two 64-blocks): the whole matrix in ONE CTA, three CTAs per SM.  Orders this small are
+// bound by the latency of the diagonal-block chain times the number of matrices an SM holds at a time -- two with the
+// per-column kernels (85 / 104 KB of shared memory per CTA).  Here the first diagonal block is factorised in tile R0
+// with inv(L)' in its own upper triangle (ldlt_diag_factor<true>), block row 1 passes through tile R1 exactly as in the
+// chain CTA of block column 0 (same products in the same order: the factors and the scratch triangle come out
+// bit-identical to the per-column kernels), and its diagonal block is factorised in R0 again: 2 tiles + 706 doubles =
+// 75.3 KB.  Measured (B = 4096): N = 64 0.233 -> 0.193 ms, N = 128 0.592 -> 0.49 ms -- 1.2x from 1.5x the matrices per
+// SM: three chains on an SM slow each other.  Giving the pivot chain of co-resident CTAs different warps (sub-partitions)
+// changed nothing (0.497 vs 0.491 ms); a 4-byte static __shared__ variable next to the dynamic tiles cost the per-column
+// kernels 9 % (N = 768: 27.8 vs 25.45 ms) and this kernel 4 % -- the tiles want the dynamic segment at offset 0.
+constexpr int SMALL_SMEM = (2 * NB * DP + DGM_MISC) * (int)sizeof(double);
+static_assert(EP == DP, "the small kernel uses one pitch for the tiles of both roles");
+static_assert(NB <= NB * WNPM, "1 / d of block 0 is parked in the (idle) -W panel");
+__global__ void __launch_bounds__(256, 3) ldlt_small_kernel(int ld, const int32_t* __restrict__ Nvec, int Nfixed,
+                                                             double* __restrict__ K, double* __restrict__ dvec,
+                                                             int32_t* __restrict__ info, int32_t* __restrict__ nneg,
+                                                             const int32_t* __restrict__ npos_expected, GfWork work) {
+    const int b = gf_instance(work, blockIdx.x);
+    if (b < 0) return;
+    extern __shared__ double sm[];
+    const int Np = padded_order(Nvec, Nfixed, b, ld);
+    if (Np <= 0) {
+        if (threadIdx.x == 0) { info[b] = 0; nneg[b] = 0; }
+        return;
+    }
+    double* R0 = sm;
+    double* R1 = sm + NB * DP;
+    double* misc = sm + 2 * NB * DP;
+    double* Kb = K + (size_t)b * ld * ld;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, q = lane & 3;
+    for (int e = tid; e < NB * NB / 2; e += 256) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)r * ld + c);
+        R0[r * DP + c] = v.x;
+        R0[r * DP + c + 1] = v.y;
+    }
+    __syncthreads();
+    ldlt_diag_factor<true>(R0, nullptr, misc, b, ld, Nvec, Nfixed, 0, K, dvec, info, nneg, npos_expected);
+    if (Np <= NB) return;
+    // ---- block row 1 = the chain CTA of block column 0 (ldlt_chain_body with nothing to its left)
+    const int i0 = NB;
+    double* Xs = R0;          // storage layout of diagonal block 0: inv(L_00)' above the diagonal; later L[1,0]
+    double* Cs = R1;          // A[1,0]; later W' = -C X'
+    double* rinv = misc;      // 1 / d of block 0 (IEEE quotient, as the column kernels form it)
+    for (int e = tid; e < NB * NB / 2; e += 256) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)(i0 + r) * ld + c);
+        Cs[r * EP + c] = v.x;
+        Cs[r * EP + c + 1] = v.y;
+    }
+    if (tid < NB) rinv[tid] = 1.0 / R0[tid * DP + tid];
+    __syncthreads();
+    {   // W = C X' (every warp 8 full rows), L = W D^{-1}
+        double t[8][2];
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) { t[ni][0] = 0.0; t[ni][1] = 0.0; }
+        const double* as = Cs + (wid * 8 + g) * EP + q;
+#pragma unroll
+        for (int kk = 0; kk < NB; kk += 4) {
+            const double a = as[kk];
+#pragma unroll
+            for (int ni = 0; ni < 8; ni++) {
+                if (kk < ni * 8 + 8) dmma884(t[ni][0], t[ni][1], a, xt_fragment(Xs, kk + q, ni * 8 + g));
+            }
+        }
+        __syncthreads();  // all reads of Cs / Xs are done: overwrite them with W' and L
+        const int r = wid * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) {
+            const int c = ni * 8 + 2 * q;
+            const double r0 = rinv[c], r1 = rinv[c + 1];
+            const double2 wv = make_double2(-t[ni][0], -t[ni][1]);
+            const double2 lv = make_double2(t[ni][0] * r0, t[ni][1] * r1);
+            *reinterpret_cast<double2*>(Cs + r * EP + c) = wv;
+            *reinterpret_cast<double2*>(Xs + r * EP + c) = lv;
+            *reinterpret_cast<double2*>(Kb + (size_t)(i0 + r) * ld + c) = lv;
+            *reinterpret_cast<double2*>(Kb + (size_t)r * ld + i0 + c) = wv;
+        }
+    }
+    __syncthreads();
+    {   // S = A[1,1] + W' L'  (4 x 2 warps of 16 x 32, strictly upper quadrant skipped), accumulators from global
+        const int wm2 = wid >> 1, wn2 = wid & 1;
+        const bool on = !((wn2 == 1) && (wm2 < 2));
+        double s2[2][4][2];
+        if (on) {
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm2 * 16 + mi * 8 + g;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    const int c = wn2 * 32 + ni * 8 + 2 * q;
+                    const double2 v = *reinterpret_cast<const double2*>(Kb + (size_t)(i0 + r) * ld + i0 + c);
+                    s2[mi][ni][0] = v.x;
+                    s2[mi][ni][1] = v.y;
+                }
+            }
+            const double* as = Cs + (wm2 * 16 + g) * EP + q;
+            const double* bs = Xs + (wn2 * 32 + g) * EP + q;
+#pragma unroll 4
+            for (int kk = 0; kk < NB; kk += 4) {
+                double a[2], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) a[mi] = as[mi * 8 * EP + kk];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) bf[ni] = bs[ni * 8 * EP + kk];
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(s2[mi][ni][0], s2[mi][ni][1], a[mi], bf[ni]);
+            }
+        }
+        __syncthreads();  // W' and L are no longer needed in shared memory: the diagonal tile goes into R0
+        if (on) {
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int r = wm2 * 16 + mi * 8 + g;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    const int c = wn2 * 32 + ni * 8 + 2 * q;
+                    R0[r * DP + c] = s2[mi][ni][0];
+                    R0[r * DP + c + 1] = s2[mi][ni][1];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    ldlt_diag_factor<true>(R0, nullptr, misc, b, ld, Nvec, Nfixed, 1, K, dvec, info, nneg, npos_expected);
+}
+
 // Panel tiles only, 64 rows each, three CTAs per SM (<= 85 registers, 74 KB shared memory): the rows below block
 // k + 1 of block column k.  Launched beside the chain kernel of the same column.
 constexpr int P64_SMEM = STAGES * 2 * NB * PSP * (int)sizeof(double);
@@ -1003,6 +1184,15 @@ static int ldlt_factor_impl(int B, int ld, int Nmax, const int32_t* Nvec, double
 #endif
     cudaFuncSetAttribute(ldlt_diag0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM);
     cudaFuncSetAttribute(ldlt_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM);
+    // padded order <= 128: the whole matrix in one CTA, three CTAs per SM (GF_LDLT_SMALL=0: the per-column kernels)
+    if (nblk <= 2 && src.H == nullptr) {
+        const char* e = getenv("GF_LDLT_SMALL");
+        if (e == nullptr || e[0] != '0') {
+            cudaFuncSetAttribute(ldlt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM);
+            ldlt_small_kernel<<<nwork, 256, SMALL_SMEM, s>>>(ld, Nvec, Nmax, K, dvec, info, nneg, npos_expected, w);
+            return gf_launch_status();
+        }
+    }
     // GF_LDLT_WHOLE=1: one CTA per matrix (experiment, 5 % slower than the per-column launches; see ldlt_whole_kernel)
     static const bool whole_req = [] { const char* e = getenv("GF_LDLT_WHOLE"); return e != nullptr && e[0] == '1'; }();
     static_assert(DG_SMEM <= PN_SMEM, "the first diagonal block must fit into the column kernel's shared memory");

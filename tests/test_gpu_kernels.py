@@ -445,3 +445,27 @@ def test_count_newton_steps_matches_the_phase_expression(K):
         K.count_newton_steps(phase, cnt)
         want = 11 + int((((phase >= 2) & (phase <= 4)).sum() + ((phase == 3) | (phase == 4)).sum()).item())
         assert int(cnt.item()) == want
+
+
+@pytest.mark.parametrize("sizes", [[1, 2, 5, 63, 64], [65, 66, 100, 127, 128, 9, 64], [128] * 5])
+def test_ldlt_small_order_kernel_is_bit_identical_to_the_column_kernels(K, sizes, monkeypatch):
+    """Padded order <= 128: one CTA per matrix with inv(L)' kept in the tile's own upper triangle (ldlt_small_kernel).
+    Same products in the same order as the per-column kernels: factors, pivots, the scratch triangle, info and the
+    inertia count must come out bit for bit the same (GF_LDLT_SMALL=0 selects the per-column kernels)."""
+    mats, rhss, ms = [], [], []
+    for i, N in enumerate(sizes):
+        Km, r, m = synth.kkt_instance(N, k=i + 3)
+        mats.append(Km)
+        rhss.append(r)
+        ms.append(m)
+    npos = [N - m for N, m in zip(sizes, ms)]
+    monkeypatch.setenv("GF_LDLT_SMALL", "1")
+    sol1, info1, nneg1, fac1, d1 = _ldlt_gpu(K, mats, rhss, npos=npos)
+    monkeypatch.setenv("GF_LDLT_SMALL", "0")
+    sol0, info0, nneg0, fac0, d0 = _ldlt_gpu(K, mats, rhss, npos=npos)
+    assert np.array_equal(info1, info0) and np.array_equal(nneg1, nneg0) and (info1 == 0).all()
+    assert np.array_equal(d1, d0)
+    assert np.array_equal(fac1, fac0)
+    assert np.array_equal(sol1, sol0)
+    for k, N in enumerate(sizes):
+        assert rel_err(sol1[k, :N], np.linalg.solve(mats[k], rhss[k])) <= 1e-11
